@@ -1,0 +1,437 @@
+// Per-replicate PLS-PM solver in the covariance domain.
+//
+// One CTA solves one fit (the original sample or one bootstrap replicate) from the
+// replicate's weighted second moments
+//     G[p,q]   = sum_i c_i x~_ip x~_iq        (8x8 tiles, see plspm_model.h)
+//     colsum_p = sum_i c_i x~_ip
+// where x~ = x - mu (global column means removed once at upload) and c_i is the
+// multiplicity of row i in the resample.  With m = colsum/N and
+//     S = (G/N - m m') / scale^2       (population covariance of the TREATED data,
+//                                       config.py:299-305, util.py:33-39)
+// every quantity of the reference's iteration is a function of S:
+//     Y = Xc W            ->  var(Y_l) = w_l' S_ll w_l,   R = D W' S W D
+//     Z = Ystd E,  X_l' Z_l / N  ->  sum_j a d_j E[j,l] S_lj w_j           (mode.py:28-29)
+//     lstsq(X_l, Z_l)            ->  S_ll^-1 (same vector)                  (mode.py:50-52)
+// so the N-length arrays Y and Z are never formed (the Gram form
+// reproduces the reference to 7e-16 in the same number of iterations).
+//
+// The same source compiles (a) as device code, one CTA per replicate, and (b) with
+// PLSPM_HOST_EMUL as a single-"thread" host function that tests/ uses to check the solver
+// logic against the oracle without a GPU.  (b) is test infrastructure, never shipped.
+#pragma once
+#include <math.h>
+
+#include "plspm_model.h"
+
+#if defined(__CUDACC__) && !defined(PLSPM_HOST_EMUL)
+#define PL_DEVICE_BUILD 1
+#define PL_HD __device__ __forceinline__
+#define PL_TID ((int)threadIdx.x)
+#define PL_NT ((int)blockDim.x)
+#define PL_SYNC() __syncthreads()
+#else
+#define PL_DEVICE_BUILD 0
+#define PL_HD inline
+#define PL_TID 0
+#define PL_NT 1
+#define PL_SYNC() ((void)0)
+#endif
+
+namespace plspm {
+
+struct SolveArgs {
+  ModelView M;
+  const double* G;       // [n_tiles*64] raw weighted Gram tiles of this replicate
+  const double* colsum;  // [Ppad]
+  const double* mu;      // [Ppad] global column means removed at upload
+  double N;              // observations in the (re)sample
+  int scheme;
+  double tol;
+  int max_iter;
+  const int* ext_votes;  // [L] sign votes computed elsewhere (sparse tile sets), or null
+  double* ws;            // [M.ws_doubles] global scratch private to this CTA
+  // outputs; any pointer may be null
+  double* out_row;        // [2P+L+2n_eff] weights | r_squared | total effects | direct effects | loadings
+  double* weights;        // [P]
+  double* loadings;       // [P]
+  double* r2;             // [L]
+  double* paths;          // [L*L]
+  double* total;          // [L*L]
+  double* crossloadings;  // [P*L]
+  double* score_coef;     // [Ppad] sign_l * wf_p / scale  (scores = (x~ - m) . coef)
+  double* score_shift;    // [L]    sum_p m_p coef_p
+  int* iters;
+  int* status;
+};
+
+PL_HD double block_sum(double v, double* red) {
+#if PL_DEVICE_BUILD
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+  int nw = (blockDim.x + 31) >> 5;
+  for (int i = 0; i < nw; ++i) t += red[i];
+  return t;
+#else
+  (void)red;
+  return v;
+#endif
+}
+
+PL_HD void vote_add(int* votes, int l, int v) {
+#if PL_DEVICE_BUILD
+  atomicAdd(&votes[l], v);
+#else
+  votes[l] += v;
+#endif
+}
+
+// raw weighted cross moment sum_i c_i x~_ip x~_iq from the tile store
+PL_HD double gram_raw(const ModelView& M, const double* G, int p, int q) {
+  int t = M.tile_of[(p >> 3) * M.ns + (q >> 3)];
+  if (t >= 0) return G[(size_t)t * TILE + (p & 7) * SLOT + (q & 7)];
+  t = -(t + 2);
+  return G[(size_t)t * TILE + (q & 7) * SLOT + (p & 7)];
+}
+
+// In-place Cholesky of the lower triangle (row-major, leading dimension ld). false if not PD.
+PL_HD bool chol_factor(double* A, int n, int ld) {
+  for (int j = 0; j < n; ++j) {
+    double diag0 = A[j * ld + j];
+    double s = diag0;
+    for (int k = 0; k < j; ++k) s -= A[j * ld + k] * A[j * ld + k];
+    if (!(s > 1e-13 * fabs(diag0)) || !(diag0 > 0.0)) return false;
+    double r = sqrt(s);
+    A[j * ld + j] = r;
+    for (int i = j + 1; i < n; ++i) {
+      double t = A[i * ld + j];
+      for (int k = 0; k < j; ++k) t -= A[i * ld + k] * A[j * ld + k];
+      A[i * ld + j] = t / r;
+    }
+  }
+  return true;
+}
+
+PL_HD void chol_solve(const double* A, int n, int ld, double* b) {
+  for (int i = 0; i < n; ++i) {
+    double t = b[i];
+    for (int k = 0; k < i; ++k) t -= A[i * ld + k] * b[k];
+    b[i] = t / A[i * ld + i];
+  }
+  for (int i = n - 1; i >= 0; --i) {
+    double t = b[i];
+    for (int k = i + 1; k < n; ++k) t -= A[k * ld + i] * b[k];
+    b[i] = t / A[i * ld + i];
+  }
+}
+
+// Regression of LV i on its predecessors from a correlation matrix R (L x L):
+// beta = R_pp^-1 R_pi.  scratch: [deg*deg + deg].  Returns false if R_pp is not PD.
+PL_HD bool regress_on_predecessors(const ModelView& M, const double* R, int i, double* scratch, double* beta_out) {
+  int b0 = M.pred_begin[i], n = M.pred_begin[i + 1] - b0;
+  double* A = scratch;
+  for (int a = 0; a < n; ++a)
+    for (int c = 0; c <= a; ++c) A[a * n + c] = R[M.pred_idx[b0 + a] * M.L + M.pred_idx[b0 + c]];
+  for (int a = 0; a < n; ++a) beta_out[a] = R[M.pred_idx[b0 + a] * M.L + i];
+  if (!chol_factor(A, n, n)) return false;
+  chol_solve(A, n, n, beta_out);
+  return true;
+}
+
+// Shared-memory layout (doubles): see HostModel::solver_smem_doubles().
+PL_HD void solve_replicate(const SolveArgs& A, double* smem) {
+  const ModelView& M = A.M;
+  const int L = M.L, Ppad = M.Ppad, tid = PL_TID, nt = PL_NT;
+  double* w = smem;                  // [Ppad] current outer weights (un-normalised)
+  double* wold = w + Ppad;           // [Ppad]
+  double* u = wold + Ppad;           // [Ppad] new weights / temporaries
+  double* m = u + Ppad;              // [Ppad] replicate column means of x~
+  double* V = m + Ppad;              // [n_v]
+  double* dinv = V + M.n_v;          // [L] 1/sd_pop(Y_l)
+  double* sgn = dinv + L;            // [L]
+  double* r2 = sgn + L;              // [L]
+  double* bsum = r2 + L;             // [L]
+  double* R = bsum + L;              // [L*L]
+  double* E = R + (size_t)L * L;     // [L*L]  inner weights; reused for total effects
+  double* Bm = E + (size_t)L * L;    // [L*L]  path coefficients
+  double* red = Bm + (size_t)L * L;  // [40] reduction scratch + flags
+  int* flag = (int*)(red + 34);      // [0] status
+  int* votes = (int*)(red + 40);     // [L] ints
+
+  const double N = A.N, invN = 1.0 / A.N;
+  const double a_fac = (N - 1.0) / N;  // 1/correction^2, weights.py:44 (treat(..)/correction)
+
+  for (int p = tid; p < Ppad; p += nt) m[p] = A.colsum[p] * invN;
+  if (tid == 0) { flag[0] = STATUS_OK; flag[1] = 0; }
+  PL_SYNC();
+
+  // pooled scale (config.py:302-303): sd over all N*P raw values, ddof=1, times sqrt((N-1)/N)
+  double iss = 1.0;
+  if (M.scaled) {
+    double ss = 0.0, gs = 0.0;
+    for (int p = tid; p < Ppad; p += nt)
+      if (M.col_lv[p] >= 0) {
+        ss += gram_raw(M, A.G, p, p) - A.colsum[p] * A.colsum[p] * invN;
+        gs += A.mu[p] + m[p];
+      }
+    ss = block_sum(ss, red);
+    gs = block_sum(gs, red);
+    double grand = gs / (double)M.P, dev = 0.0;
+    for (int p = tid; p < Ppad; p += nt)
+      if (M.col_lv[p] >= 0) {
+        double d = A.mu[p] + m[p] - grand;
+        dev += d * d;
+      }
+    dev = block_sum(dev, red);
+    double var1 = (ss + N * dev) / (N * (double)M.P - 1.0);
+    iss = 1.0 / (var1 * a_fac);
+  }
+#define PL_S(p, q) ((gram_raw(M, A.G, (p), (q)) * invN - m[p] * m[q]) * iss)
+
+  // ---- initial weights (weights.py:28-34): 1/sd of the block sum (correction cancels) ----------
+  for (int l = tid; l < L; l += nt) {
+    double bs = 0.0;
+    int o = M.lv_off[l], k = M.lv_k[l];
+    for (int r = 0; r < k; ++r)
+      for (int c = 0; c < k; ++c) bs += PL_S(o + r, o + c);
+    double wi = 1.0 / sqrt(bs);
+    for (int r = 0; r < SLOT * ((k + SLOT - 1) / SLOT); ++r) {
+      w[o + r] = (r < k) ? wi : 0.0;
+      wold[o + r] = w[o + r];
+      u[o + r] = 0.0;
+    }
+    // Mode B: factor S_ll once per replicate (the block Gram is iteration-invariant)
+    if (M.lv_mode[l] == MODE_B) {
+      double* C = A.ws + M.chol_b_off[l];
+      for (int r = 0; r < k; ++r)
+        for (int c = 0; c <= r; ++c) C[r * k + c] = PL_S(o + r, o + c);
+      if (!chol_factor(C, k, k)) flag[0] = STATUS_SINGULAR;
+    }
+  }
+  PL_SYNC();
+
+  double* ols = A.ws + (M.ws_doubles - L * (M.max_deg * M.max_deg + 2 * M.max_deg));
+  const int ols_stride = M.max_deg * M.max_deg + 2 * M.max_deg;
+
+  int iteration = 0;
+  bool finalize = false;
+  for (;;) {
+    // ---- V_d = S_lj w_j for every needed directed LV pair  (Y = X W, weights.py:43) -----------
+    for (int t = tid; t < M.n_pairs * M.kmax; t += nt) {
+      int d = t / M.kmax, r = t - d * M.kmax;
+      int l = M.pair_l[d], j = M.pair_j[d];
+      if (r >= M.lv_k[l]) continue;
+      int kj = M.lv_k[j], ol = M.lv_off[l], oj = M.lv_off[j];
+      double acc = 0.0;
+      for (int c = 0; c < kj; ++c) acc += PL_S(ol + r, oj + c) * w[oj + c];
+      V[M.pair_voff[d] + r] = acc;
+    }
+    PL_SYNC();
+    // ---- population variance of Y_l, standardisation factor (weights.py:44) ---------------------
+    for (int l = tid; l < L; l += nt) {
+      int d = M.lv_pair_begin[l], o = M.lv_off[l];
+      double var = 0.0;
+      for (int r = 0; r < M.lv_k[l]; ++r) var += w[o + r] * V[M.pair_voff[d] + r];
+      dinv[l] = 1.0 / sqrt(var);
+      R[l * L + l] = 1.0;
+    }
+    PL_SYNC();
+    // ---- correlations of the LV scores for the needed pairs -------------------------------------
+    for (int d = tid; d < M.n_pairs; d += nt) {
+      int l = M.pair_l[d], j = M.pair_j[d];
+      if (l > j) {
+        int o = M.lv_off[l];
+        double acc = 0.0;
+        for (int r = 0; r < M.lv_k[l]; ++r) acc += w[o + r] * V[M.pair_voff[d] + r];
+        acc *= dinv[l] * dinv[j];
+        R[l * L + j] = acc;
+        R[j * L + l] = acc;
+      }
+    }
+    PL_SYNC();
+    if (finalize) break;
+
+    // ---- inner weights E (scheme.py:27-28, 36-37, 45-54); E[j*L+l] multiplies Y_j in Z_l --------
+    if (A.scheme == SCHEME_PATH) {
+      for (int e = tid; e < L * L; e += nt) E[e] = 0.0;
+      PL_SYNC();
+      for (int i = tid; i < L; i += nt) {
+        int n = M.pred_begin[i + 1] - M.pred_begin[i];
+        if (n > 0) {
+          double* sc = ols + (size_t)i * ols_stride;
+          double* beta = sc + M.max_deg * M.max_deg;
+          if (!regress_on_predecessors(M, R, i, sc, beta)) flag[0] = STATUS_SINGULAR;
+          for (int a = 0; a < n; ++a) E[M.pred_idx[M.pred_begin[i] + a] * L + i] = beta[a];
+        }
+        for (int a = M.succ_begin[i]; a < M.succ_begin[i + 1]; ++a) {
+          int k = M.succ_idx[a];
+          E[k * L + i] = R[k * L + i];
+        }
+      }
+    } else {
+      for (int e = tid; e < L * L; e += nt) {
+        int j = e / L, l = e - j * L;
+        double val = 0.0;
+        if (M.path[j * L + l] | M.path[l * L + j]) {
+          double r = R[e];
+          if (A.scheme == SCHEME_CENTROID) val = (r > 0.0) ? 1.0 : ((r < 0.0) ? -1.0 : r);  // numpy.sign
+          else val = a_fac * r;  // cov ddof=1 of scores scaled by a (quirk Q3)
+        }
+        E[e] = val;
+      }
+    }
+    PL_SYNC();
+    // ---- outer weights (weights.py:46-50): (1/N) X_l' Z_l, Z_l = sum_j a d_j E[j,l] Y_j ----------
+    for (int p = tid; p < Ppad; p += nt) {
+      int l = M.col_lv[p];
+      if (l < 0) continue;
+      int r = p - M.lv_off[l];
+      double acc = 0.0;
+      for (int d = M.lv_pair_begin[l] + 1; d < M.lv_pair_begin[l + 1]; ++d) {
+        int j = M.pair_j[d];
+        double e = E[j * L + l];
+        if (e != 0.0) acc += a_fac * dinv[j] * e * V[M.pair_voff[d] + r];
+      }
+      u[p] = acc;
+    }
+    PL_SYNC();
+    for (int l = tid; l < L; l += nt)
+      if (M.lv_mode[l] == MODE_B && flag[0] == STATUS_OK)
+        chol_solve(A.ws + M.chol_b_off[l], M.lv_k[l], M.lv_k[l], u + M.lv_off[l]);  // mode.py:50-52
+    PL_SYNC();
+    // ---- convergence (weights.py:51-53) ----------------------------------------------------------
+    double part = 0.0;
+    for (int p = tid; p < Ppad; p += nt) {
+      double df = fabs(wold[p]) - fabs(u[p]);
+      part += df * df;
+      wold[p] = u[p];
+      w[p] = u[p];
+    }
+    double conv = block_sum(part, red);
+    ++iteration;
+    PL_SYNC();
+    // weights.py:183  (a NaN criterion keeps iterating until the cap, like the reference)
+    if ((conv < A.tol) || (iteration > A.max_iter) || flag[0] != STATUS_OK) finalize = true;
+  }
+  int status = flag[0];
+  if (status == STATUS_OK && iteration > A.max_iter) status = STATUS_NOT_CONVERGED;  // weights.py:185 (Q4)
+
+  // ---- final normalisation, sign vote (weights.py:56-68) --------------------------------------------
+  // after the loop V, dinv and R hold the values for the final weights
+  for (int p = tid; p < Ppad; p += nt) {
+    int l = M.col_lv[p];
+    u[p] = (l >= 0) ? w[p] * dinv[l] : 0.0;  // wf: scores have unit population variance
+  }
+  for (int l = tid; l < L; l += nt) votes[l] = 0;
+  PL_SYNC();
+  if (A.ext_votes) {
+    for (int l = tid; l < L; l += nt) votes[l] = A.ext_votes[l];
+  } else {
+    // cov(x_p, score_l) for ALL (p, l): every manifest variable votes on every LV (quirk Q6)
+    for (int t = tid; t < Ppad * L; t += nt) {
+      int p = t / L, l = t - p * L;
+      if (M.col_lv[p] < 0) continue;
+      int o = M.lv_off[l];
+      double acc = 0.0;
+      for (int c = 0; c < M.lv_k[l]; ++c) acc += PL_S(p, o + c) * u[o + c];
+      if (A.crossloadings) A.crossloadings[(size_t)M.col_src[p] * L + l] = acc / sqrt(PL_S(p, p));
+      // copysign(1, cor): +1 for cor >= +0, -1 for cor < 0 or -0 (weights.py:63-64); NaN does not vote
+      if (acc == acc) vote_add(votes, l, signbit(acc) ? -1 : 1);
+    }
+  }
+  PL_SYNC();
+  for (int l = tid; l < L; l += nt) sgn[l] = (votes[l] < 0) ? -1.0 : 1.0;
+  PL_SYNC();
+  // flip score correlations
+  for (int e = tid; e < L * L; e += nt) {
+    int i = e / L, j = e - i * L;
+    R[e] *= sgn[i] * sgn[j];
+    Bm[e] = 0.0;
+  }
+  PL_SYNC();
+  // ---- inner model (inner_model.py:72-83): OLS with intercept on centred unit-variance scores ----
+  for (int i = tid; i < L; i += nt) {
+    int n = M.pred_begin[i + 1] - M.pred_begin[i];
+    double rr = 0.0;
+    if (n > 0) {
+      double* sc = ols + (size_t)i * ols_stride;
+      double* beta = sc + M.max_deg * M.max_deg;
+      if (!regress_on_predecessors(M, R, i, sc, beta)) {
+        if (status == STATUS_OK) flag[0] = STATUS_SINGULAR;
+      } else {
+        for (int a = 0; a < n; ++a) {
+          int j = M.pred_idx[M.pred_begin[i] + a];
+          Bm[i * L + j] = beta[a];
+          rr += beta[a] * R[j * L + i];
+        }
+      }
+    }
+    r2[i] = rr;
+  }
+  PL_SYNC();
+  if (status == STATUS_OK) status = flag[0];
+  // ---- total effects (inner_model.py:33-49): T = B + B T, column by column ----------------------
+  double* T = E;
+  for (int j = tid; j < L; j += nt)
+    for (int i = 0; i < L; ++i) {
+      double acc = Bm[i * L + j];
+      for (int k = j + 1; k < i; ++k) acc += Bm[i * L + k] * T[k * L + j];
+      T[i * L + j] = (i > j) ? acc : 0.0;
+    }
+  PL_SYNC();
+
+  // ---- outputs -------------------------------------------------------------------------------------
+  const int P = M.P, ne = M.n_eff;
+  const double inv_scale = sqrt(iss);
+  for (int p = tid; p < Ppad; p += nt) {
+    int l = M.col_lv[p];
+    if (l < 0) {
+      if (A.score_coef) A.score_coef[p] = 0.0;
+      continue;
+    }
+    int src = M.col_src[p];
+    double wfp = u[p];
+    // in-block loading = corr(x_p, flipped score_l) = sgn * (S_ll wf)_p / sd(x_p)   (bootstrap.py:65-66)
+    double load = sgn[l] * V[M.pair_voff[M.lv_pair_begin[l]] + (p - M.lv_off[l])] * dinv[l] / sqrt(PL_S(p, p));
+    if (A.out_row) {
+      A.out_row[src] = wfp;
+      A.out_row[P + L + 2 * ne + src] = load;
+    }
+    if (A.weights) A.weights[src] = wfp;
+    if (A.loadings) A.loadings[src] = load;
+    if (A.score_coef) A.score_coef[p] = sgn[l] * wfp * inv_scale;
+  }
+  for (int l = tid; l < L; l += nt) {
+    if (A.out_row) A.out_row[P + l] = r2[l];
+    if (A.r2) A.r2[l] = r2[l];
+    if (A.score_shift) {
+      double sh = 0.0;
+      for (int r = 0; r < M.lv_k[l]; ++r) sh += m[M.lv_off[l] + r] * sgn[l] * u[M.lv_off[l] + r] * inv_scale;
+      A.score_shift[l] = sh;
+    }
+  }
+  for (int e = tid; e < ne; e += nt) {
+    int f = M.eff_from[e], t = M.eff_to[e];
+    if (A.out_row) {
+      A.out_row[P + L + e] = T[t * L + f];
+      A.out_row[P + L + ne + e] = Bm[t * L + f];
+    }
+  }
+  for (int e = tid; e < L * L; e += nt) {
+    if (A.paths) A.paths[e] = Bm[e];
+    if (A.total) A.total[e] = T[e];
+  }
+  if (A.crossloadings && !A.ext_votes) {
+    PL_SYNC();
+    for (int t = tid; t < P * L; t += nt) A.crossloadings[t] *= sgn[t % L];
+  }
+  if (tid == 0) {
+    if (A.iters) *A.iters = iteration;
+    if (A.status) *A.status = status;
+  }
+#undef PL_S
+}
+
+}  // namespace plspm

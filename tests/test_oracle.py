@@ -1,0 +1,179 @@
+"""Pins the CPU oracle (oracle/plspm_oracle.py) against
+ (1) the R-generated golden vectors used by the reference's own tests
+     (/root/reference/tests/data/satisfaction.*.csv, test_regression_metric.py:43-94), and
+ (2) outputs of the reference itself (tests/golden/make_golden.py).
+CPU only."""
+import numpy as np
+import pytest
+
+from oracle import plspm_oracle as orc
+from plspm_b200.synth import make_synthetic
+
+SCHEMES = ("centroid", "factorial", "path")
+
+
+def rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300))) if a.size else 0.0
+
+
+def sat_fit(sat, scheme, mode, scaled):
+    L = len(sat["block_sizes"])
+    return orc.fit(sat["X"], sat["block_sizes"], [mode] * L, sat["path"], scheme, scaled)
+
+
+def test_r_golden_scores_weights_paths(sat):
+    r = sat_fit(sat, "centroid", orc.MODE_A, False)
+    assert r["iterations"] == 4
+    np.testing.assert_allclose(r["scores"], sat["R/scores"], rtol=1e-7, atol=1e-10)
+    np.testing.assert_allclose(r["weights"], sat["R/centroid/weight"], rtol=1e-9)
+    np.testing.assert_allclose(r["loadings"], sat["R/centroid/loading"], rtol=1e-9)
+    np.testing.assert_allclose(r["crossloadings"], sat["R/crossloadings"], rtol=1e-7, atol=1e-12)
+    np.testing.assert_allclose(r["r_squared"], sat["R/inner_summary/r_squared"], rtol=1e-9, atol=1e-14)
+    lvs = list(sat["lvs"])
+    for f, t, d, ind, tot in zip(sat["R/effects_from"], sat["R/effects_to"], sat["R/effects_direct"],
+                                 sat["R/effects_indirect"], sat["R/effects_total"]):
+        i, j = lvs.index(t), lvs.index(f)
+        np.testing.assert_allclose(r["path_coefficients"][i, j], d, rtol=1e-8, atol=1e-13)
+        np.testing.assert_allclose(r["indirect_effects"][i, j], ind, rtol=1e-8, atol=1e-13)
+        np.testing.assert_allclose(r["total_effects"][i, j], tot, rtol=1e-8, atol=1e-13)
+
+
+@pytest.mark.parametrize("scheme", ("path", "factorial"))
+def test_r_golden_other_schemes(sat, scheme):
+    r = sat_fit(sat, scheme, orc.MODE_A, False)
+    np.testing.assert_allclose(r["weights"], sat["R/%s/weight" % scheme], rtol=1e-9)
+    np.testing.assert_allclose(r["loadings"], sat["R/%s/loading" % scheme], rtol=1e-9)
+
+
+def test_r_golden_mode_b_rsquared(sat):
+    r = sat_fit(sat, "centroid", orc.MODE_B, False)
+    np.testing.assert_allclose(r["r_squared"], sat["R/modeb/inner_summary/r_squared"], rtol=1e-7, atol=1e-12)
+
+
+@pytest.mark.parametrize("scheme", SCHEMES)
+@pytest.mark.parametrize("mode", ("A", "B"))
+@pytest.mark.parametrize("scaled", (False, True))
+def test_vs_reference_satisfaction(sat, scheme, mode, scaled):
+    tag = "ref/%s/%s/%s/" % (scheme, mode, "scaled" if scaled else "unscaled")
+    r = sat_fit(sat, scheme, orc.MODE_A if mode == "A" else orc.MODE_B, scaled)
+    assert r["iterations"] == int(sat[tag + "iterations"])
+    tol = 1e-9 if mode == "A" else 1e-8
+    assert rel(r["weights"], sat[tag + "weights"]) < tol
+    np.testing.assert_allclose(r["scores"], sat[tag + "scores"], rtol=tol, atol=1e-11)
+    np.testing.assert_allclose(r["path_coefficients"], sat[tag + "path_coefficients"], rtol=tol, atol=1e-12)
+    np.testing.assert_allclose(r["r_squared"], sat[tag + "r_squared"], rtol=tol, atol=1e-12)
+    np.testing.assert_allclose(r["loadings"], sat[tag + "loadings"], rtol=tol, atol=1e-12)
+    np.testing.assert_allclose(r["crossloadings"], sat[tag + "crossloadings"], rtol=tol, atol=1e-12)
+
+
+def test_vs_reference_mixed_modes(sat):
+    r = orc.fit(sat["X"], sat["block_sizes"], sat["mixed_modes"], sat["path"], "path", True)
+    tag = "ref/path/mixed/scaled/"
+    assert r["iterations"] == int(sat[tag + "iterations"])
+    assert rel(r["weights"], sat[tag + "weights"]) < 1e-8
+    np.testing.assert_allclose(r["path_coefficients"], sat[tag + "path_coefficients"], rtol=1e-8, atol=1e-12)
+
+
+def test_vs_reference_synthetic(syn):
+    for name in syn["cases"]:
+        N, L, K, seed = (int(v) for v in syn[name + "/gen"])
+        X, path = make_synthetic(N, L, K, seed, reverse_blocks=tuple(int(v) for v in syn[name + "/reverse"]))
+        mode = orc.MODE_A if str(syn[name + "/mode"]) == "A" else orc.MODE_B
+        r = orc.fit(X, [K] * L, [mode] * L, path, str(syn[name + "/scheme"]), bool(syn[name + "/scaled"]))
+        assert r["iterations"] == int(syn[name + "/iterations"]), name
+        assert rel(r["weights"], syn[name + "/weights"]) < 1e-8, name
+        np.testing.assert_allclose(r["scores"], syn[name + "/scores"], rtol=1e-8, atol=1e-10, err_msg=name)
+        np.testing.assert_allclose(r["path_coefficients"], syn[name + "/path_coefficients"], rtol=1e-8, atol=1e-11)
+        np.testing.assert_allclose(r["total_effects"][np.tril_indices(L, -1)],
+                                   _total_from_effects(syn, name, L)[np.tril_indices(L, -1)], rtol=1e-8, atol=1e-11)
+
+
+def _total_from_effects(fx, name, L):
+    lvs = list(fx[name + "/lvs"])
+    T = np.zeros((L, L))
+    for f, t, v in zip(fx[name + "/effects_from"], fx[name + "/effects_to"], fx[name + "/effects_total"]):
+        T[lvs.index(t), lvs.index(f)] = v
+    return T
+
+
+def test_sign_flip_case_present(syn):
+    # syn_b has reverse-coded blocks: scores flipped, weights keep their sign (quirk Q6)
+    N, L, K, seed = (int(v) for v in syn["syn_b/gen"])
+    X, path = make_synthetic(N, L, K, seed, reverse_blocks=(1, 3))
+    r = orc.fit(X, [K] * L, [0] * L, path, "centroid", False)
+    assert (r["signs"] < 0).any()
+    np.testing.assert_allclose(r["weights"], syn["syn_b/weights"], rtol=1e-8)
+    np.testing.assert_allclose(r["loadings"], syn["syn_b/loadings"], rtol=1e-8)
+
+
+@pytest.mark.parametrize("case", ("centroid/A/unscaled", "path/B/scaled", "factorial/A/scaled"))
+def test_bootstrap_replicates_vs_reference(sat, case):
+    scheme, mode, sc = case.split("/")
+    L = len(sat["block_sizes"])
+    nrep = int(sat["boot/n_replicates"])
+    idx = np.random.default_rng(1234).integers(0, 250, (1000, 250), dtype=np.int32)[:nrep]
+    out, iters, status = orc.bootstrap(sat["X"], idx, sat["block_sizes"],
+                                       [orc.MODE_A if mode == "A" else orc.MODE_B] * L, sat["path"], scheme,
+                                       sc == "scaled")
+    tag = "boot/%s/" % case
+    assert (status == 0).all() and sat[tag + "ok"].all()
+    np.testing.assert_array_equal(iters, sat[tag + "iterations"])
+    P = int(sat["block_sizes"].sum())
+    pairs = orc.effect_pairs(sat["path"])
+    tol = 1e-8 if mode == "A" else 1e-7
+    np.testing.assert_allclose(out[:, :P], sat[tag + "weights"], rtol=tol)
+    np.testing.assert_allclose(out[:, P:P + L], sat[tag + "r_squared"], rtol=tol, atol=1e-12)
+    tot = np.array([[sat[tag + "total_effects"][b, t, f] for f, t in pairs] for b in range(nrep)])
+    direct = np.array([[sat[tag + "path_coefficients"][b, t, f] for f, t in pairs] for b in range(nrep)])
+    ne = len(pairs)
+    np.testing.assert_allclose(out[:, P + L:P + L + ne], tot, rtol=tol, atol=1e-12)
+    np.testing.assert_allclose(out[:, P + L + ne:P + L + 2 * ne], direct, rtol=tol, atol=1e-12)
+    np.testing.assert_allclose(out[:, P + L + 2 * ne:], sat[tag + "loadings"], rtol=tol, atol=1e-12)
+
+
+def test_effect_pairs_match_reference_effects_index(sat):
+    lvs = list(sat["lvs"])
+    pairs = orc.effect_pairs(sat["path"])
+    ref = list(zip(sat["ref/centroid/A/unscaled/effects_from"], sat["ref/centroid/A/unscaled/effects_to"]))
+    assert [(lvs[f], lvs[t]) for f, t in pairs] == [(str(f), str(t)) for f, t in ref]
+
+
+def test_philox_known_answers():
+    # Random123 kat_vectors, philox4x32-10
+    z = np.zeros(1, dtype=np.uint64)
+    out = orc.philox4x32(z, z, z, z, 0, 0)
+    assert [int(v[0]) for v in out] == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+    f = z + np.uint64(0xFFFFFFFF)
+    out = orc.philox4x32(f, f, f, f, 0xFFFFFFFF, 0xFFFFFFFF)
+    assert [int(v[0]) for v in out] == [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]
+    p = z + np.uint64(0x243F6A88)
+    out = orc.philox4x32(p, z + np.uint64(0x85A308D3), z + np.uint64(0x13198A2E), z + np.uint64(0x03707344),
+                         0xA4093822, 0x299F31D0)
+    assert [int(v[0]) for v in out] == [0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]
+
+
+def test_philox_indices_range_and_determinism():
+    a = orc.philox_indices(7, 3, 1001)
+    b = orc.philox_indices(7, 3, 1001)
+    c = orc.philox_indices(7, 4, 1001)
+    assert a.shape == (1001,) and a.min() >= 0 and a.max() < 1001
+    assert (a == b).all() and (a != c).any()
+    cnt = np.bincount(a, minlength=1001)
+    assert 0.30 < (cnt == 0).mean() < 0.43  # ~ e^-1 of the rows are left out of a resample
+
+
+def test_missing_values_are_mean_imputed():
+    X, path = make_synthetic(120, 3, 3, seed=1)
+    Xm = X.copy()
+    Xm[5, 2] = np.nan
+    Xi = X.copy()
+    Xi[5, 2] = np.delete(X[:, 2], 5).mean()
+    a = orc.fit(Xm, [3, 3, 3], [0, 0, 0], path, "centroid", True)
+    b = orc.fit(Xi, [3, 3, 3], [0, 0, 0], path, "centroid", True)
+    np.testing.assert_allclose(a["weights"], b["weights"], rtol=1e-12)
+
+
+def test_not_converged_raises(sat):
+    with pytest.raises(orc.NotConverged):
+        orc.fit(sat["X"], sat["block_sizes"], [1] * 6, sat["path"], "centroid", True, tol=1e-30, max_iter=3)
