@@ -1,0 +1,31 @@
+"""Builds libplspm_b200.so in-tree with nvcc for sm_100a (no torch extension machinery needed:
+the library is plain CUDA runtime + a C ABI)."""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OUT = os.path.join(HERE, "plspm_b200", "libplspm_b200.so")
+SOURCES = [os.path.join(CSRC, "plspm_b200.cu"), os.path.join(CSRC, "plspm_model.cpp")]
+DEPS = SOURCES + [os.path.join(CSRC, f) for f in ("plspm_model.h", "solver_core.h")] + \
+    [os.path.join(os.path.dirname(HERE), "include", "plspm_b200.h")]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
+              "-shared"]
+
+
+def up_to_date() -> bool:
+    return os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(d) for d in DEPS)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and up_to_date():
+        return OUT
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SOURCES
+    subprocess.check_call(cmd)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,912 @@
+// plspm_b200: sm_100a kernels + C ABI (include/plspm_b200.h).
+//
+// Data flow of one bootstrap batch (replicates are the batch dimension):
+//
+//   counts_kernel   Philox4x32-10 (or injected) resample indices -> multiplicity c[b][i] (u32)
+//   gram_kernel     weighted second moments per replicate, fp64:
+//                     G_b[p,q] = sum_i c_bi x~_ip x~_iq  (8x8 register tiles),  colsum_b[p]
+//                   X~ row tiles are staged global->shared by the TMA engine (cp.async.bulk +
+//                   mbarrier ring, one producer warp) and shared by every (replicate, tile
+//                   group) warp of the CTA: X is read from HBM once per wave of replicates,
+//                   not once per replicate and iteration.
+//   reduce_kernel   fixed-order sum over row chunks (only when rows are split, e.g. one fit)
+//   solve_kernel    one CTA per replicate: the whole PLS-PM iteration in the covariance
+//                   domain (solver_core.h), inner model, effects, loadings
+//   scores_kernel   single fit only: scores = X~ . coef - shift   (N x L, HBM-bound)
+//
+// Nothing here falls back to a CPU path: without a CUDA device every entry point fails.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/plspm_b200.h"
+#include "plspm_model.h"
+#include "solver_core.h"
+
+using namespace plspm;
+
+// ------------------------------------------------------------------------------------------------
+// error handling / profiling
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CK(expr)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (expr);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(e_ == cudaErrorMemoryAllocation ? PLSPM_ERR_NOMEM : PLSPM_ERR_CUDA,              \
+                  std::string(#expr) + ": " + cudaGetErrorString(e_));                             \
+  } while (0)
+
+enum { ST_COUNTS = 0, ST_GRAM = 1, ST_REDUCE = 2, ST_SOLVE = 3, ST_SCORES = 4, ST_UPLOAD = 5, ST_N = 8 };
+struct Profile {
+  std::mutex mu;
+  double ms[ST_N] = {0};
+  int64_t launches[ST_N] = {0};
+};
+static Profile g_prof;
+
+// A timed launch region: events on the launching stream; durations are collected when the
+// stream is synchronised at the end of the API call.
+struct StageTimer {
+  struct Rec { int stage; cudaEvent_t a, b; };
+  std::vector<Rec> recs;
+  std::vector<cudaEvent_t> pool;
+  cudaEvent_t get() {
+    if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+  }
+  void begin(int stage, cudaStream_t s) {
+    Rec r{stage, get(), get()};
+    cudaEventRecord(r.a, s);
+    recs.push_back(r);
+  }
+  void end(cudaStream_t s) { cudaEventRecord(recs.back().b, s); }
+  void collect() {  // call after the stream is synchronised
+    std::lock_guard<std::mutex> lk(g_prof.mu);
+    for (auto& r : recs) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) g_prof.ms[r.stage] += ms;
+      g_prof.launches[r.stage] += 1;
+      pool.push_back(r.a);
+      pool.push_back(r.b);
+    }
+    recs.clear();
+  }
+  ~StageTimer() {
+    for (auto& r : recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (auto e : pool) cudaEventDestroy(e);
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// handles
+// ------------------------------------------------------------------------------------------------
+struct plspm_model {
+  HostModel h;
+  int device = 0;
+  std::vector<void*> dev_allocs;
+  ModelView dv;  // device pointers
+};
+
+struct Workspace {
+  void* ptr = nullptr;
+  size_t bytes = 0;
+};
+
+struct plspm_data {
+  const plspm_model* model = nullptr;
+  int64_t N = 0;
+  double* X = nullptr;   // [N][Ppad] slot layout, globally centred
+  double* mu = nullptr;  // [Ppad]
+  cudaStream_t stream = nullptr;
+  Workspace ws;          // grown on demand, reused across calls
+  StageTimer timer;
+  int sm_count = 148;
+  int max_smem = 227 * 1024;
+};
+
+template <class T>
+static int upload_vec(plspm_model* m, const std::vector<T>& v, const T** out) {
+  void* p = nullptr;
+  size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(T);
+  CK(cudaMalloc(&p, bytes));
+  m->dev_allocs.push_back(p);
+  if (!v.empty()) CK(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  *out = (const T*)p;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + bulk async copy (TMA engine, 1-D)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// Philox4x32-10 (Random123); counter = (row group, 0, replicate lo, replicate hi), key = seed
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                                      uint32_t k1, uint32_t out[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+    uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1;
+    uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+__host__ __device__ __forceinline__ uint32_t index_from_u32(uint32_t u, uint32_t N) {
+  return (uint32_t)(((uint64_t)u * (uint64_t)N) >> 32);
+}
+
+// counts[b][i] += multiplicity of row i in replicate b.  One thread = 4 consecutive draws.
+__global__ void counts_kernel(uint32_t* __restrict__ counts, const int32_t* __restrict__ idx, int64_t N, int64_t nrep,
+                              int64_t rep_begin, uint64_t seed) {
+  const int64_t groups = (N + 3) / 4;
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= groups * nrep) return;
+  const int64_t b = gid / groups, g = gid - b * groups;
+  uint32_t* c = counts + b * N;
+  if (idx) {
+    const int32_t* ib = idx + b * N;
+    for (int k = 0; k < 4; ++k) {
+      int64_t i = g * 4 + k;
+      if (i < N) atomicAdd(&c[(uint32_t)ib[i]], 1u);
+    }
+  } else {
+    uint64_t rep = (uint64_t)(rep_begin + b);
+    uint32_t r[4];
+    philox4x32_10((uint32_t)g, (uint32_t)((uint64_t)g >> 32), (uint32_t)rep, (uint32_t)(rep >> 32), (uint32_t)seed,
+                  (uint32_t)(seed >> 32), r);
+    for (int k = 0; k < 4; ++k)
+      if (g * 4 + k < N) atomicAdd(&c[index_from_u32(r[k], (uint32_t)N)], 1u);
+  }
+}
+
+__global__ void indices_kernel(int32_t* __restrict__ out, int64_t N, uint64_t rep, uint64_t seed) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= (N + 3) / 4) return;
+  uint32_t r[4];
+  philox4x32_10((uint32_t)g, (uint32_t)((uint64_t)g >> 32), (uint32_t)rep, (uint32_t)(rep >> 32), (uint32_t)seed,
+                (uint32_t)(seed >> 32), r);
+  for (int k = 0; k < 4; ++k)
+    if (g * 4 + k < N) out[g * 4 + k] = (int32_t)index_from_u32(r[k], (uint32_t)N);
+}
+
+// ------------------------------------------------------------------------------------------------
+// upload: column means (two-stage, fixed order) and slot-layout relayout with centring
+// ------------------------------------------------------------------------------------------------
+__global__ void colsum_partial_kernel(const double* __restrict__ X, int64_t N, int64_t ld, int P, int64_t rows_per_block,
+                                      double* __restrict__ partial) {
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block, r1 = min(r0 + rows_per_block, N);
+  for (int p = threadIdx.x; p < P; p += blockDim.x) {
+    double s = 0.0;
+    for (int64_t i = r0; i < r1; ++i) s += X[i * ld + p];
+    partial[(int64_t)blockIdx.x * P + p] = s;
+  }
+}
+__global__ void colmean_final_kernel(const double* __restrict__ partial, int nblocks, int P, int64_t N,
+                                     const int* __restrict__ src_col, double* __restrict__ mu) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  double s = 0.0;
+  for (int b = 0; b < nblocks; ++b) s += partial[(int64_t)b * P + p];
+  mu[src_col[p]] = s / (double)N;
+}
+__global__ void relayout_kernel(const double* __restrict__ X, int64_t N, int64_t ld, int Ppad,
+                                const int* __restrict__ col_src, const double* __restrict__ mu,
+                                double* __restrict__ out) {
+  const int64_t total = N * Ppad;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    int64_t i = e / Ppad;
+    int c = (int)(e - i * Ppad);
+    int s = col_src[c];
+    out[e] = (s >= 0) ? X[i * ld + s] - mu[c] : 0.0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// weighted Gram kernel
+// ------------------------------------------------------------------------------------------------
+constexpr int GRAM_WARPS = 8;    // consumer warps per CTA, each = one (replicate, tile group) item
+constexpr int GRAM_THREADS = GRAM_WARPS * 32;  // 2 warps per SM sub-partition: up to 255 registers per thread
+constexpr int GRAM_MAX_STAGES = 4;
+constexpr int GRAM_CS = 8;       // column-sum accumulators per lane
+
+struct GramParams {
+  const double* X;          // [N][Ppad]
+  const uint32_t* counts;   // [nrep][N] or null (every row once)
+  int64_t N;
+  int Ppad, n_tiles, n_tg;
+  const int *tile_sa, *tile_sb;
+  int64_t n_items;          // nrep * n_tg
+  int n_chunks;
+  int64_t chunk_rows;       // multiple of RT
+  int RT, stages;
+  int cs_cols;              // columns per tile group for the column sums (<= 32*GRAM_CS)
+  double* G;                // [nrep][n_chunks][n_tiles*64]
+  double* colsum;           // [nrep][n_chunks][Ppad]
+};
+
+__global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const GramParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[GRAM_MAX_STAGES], empty_bar[GRAM_MAX_STAGES];
+  double* tiles = reinterpret_cast<double*>(smem_raw);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t n_groups = (p.n_items + GRAM_WARPS - 1) / GRAM_WARPS;
+  const int chunk = (int)(blockIdx.x / n_groups);
+  const int64_t group = blockIdx.x - (int64_t)chunk * n_groups;
+  const int64_t item0 = group * GRAM_WARPS;
+  const int n_active = (int)min((int64_t)GRAM_WARPS, p.n_items - item0);
+  const int64_t r0 = (int64_t)chunk * p.chunk_rows, r1 = min(r0 + p.chunk_rows, p.N);
+  const int n_rt = (int)((r1 - r0 + p.RT - 1) / p.RT);
+  const size_t stage_doubles = (size_t)p.RT * p.Ppad;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], n_active);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  // ---- producer duty: lane 0 of warp 0 feeds the ring through the TMA engine ------------------
+  // (a ninth warp would put three warps on one SM sub-partition and cap every thread at 168
+  // registers; the 8x8 fp64 accumulator tile alone needs 128)
+  auto issue_tile = [&](int tn) {
+    const int s = tn % p.stages;
+    const uint32_t use = (uint32_t)(tn / p.stages);
+    if (use > 0) mbar_wait(&empty_bar[s], (use - 1) & 1);
+    const int64_t row = r0 + (int64_t)tn * p.RT;
+    const uint32_t rows = (uint32_t)min((int64_t)p.RT, r1 - row);
+    const uint32_t bytes = rows * (uint32_t)p.Ppad * 8u;
+    mbar_arrive_expect_tx(&full_bar[s], bytes);
+    bulk_g2s(tiles + (size_t)s * stage_doubles, p.X + row * p.Ppad, bytes, &full_bar[s]);
+  };
+  const bool producer = (threadIdx.x == 0);
+  if (producer)
+    for (int tn = 0; tn < p.stages - 1 && tn < n_rt; ++tn) issue_tile(tn);
+  if (warp >= n_active) return;
+
+  // ---- consumer warp: one (replicate, tile group); lane = one 8x8 tile ------------------------
+  const int64_t item = item0 + warp;
+  const int64_t rep = item / p.n_tg;
+  const int tg = (int)(item - rep * p.n_tg);
+  const int tile = tg * 32 + lane;
+  const bool tile_ok = tile < p.n_tiles;
+  const int sa = tile_ok ? p.tile_sa[tile] : 0, sb = tile_ok ? p.tile_sb[tile] : 0;
+  // 16-byte chunks of a slot are read in a lane-dependent rotated order so that the 32 LDS.128 of
+  // a warp spread over all bank quads (slot stride 64 B would otherwise be a 16-way conflict)
+  const int rot_a = (sa >> 1) & 3, rot_b = (sb >> 1) & 3;
+  int off_a[4], off_b[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    off_a[k] = sa * SLOT + 2 * ((k + rot_a) & 3);
+    off_b[k] = sb * SLOT + 2 * ((k + rot_b) & 3);
+  }
+  const int cs0 = tg * p.cs_cols, cs1 = min(cs0 + p.cs_cols, p.Ppad);
+  const int ncs = (cs1 - cs0 + 31) / 32;  // warp-uniform
+
+  double acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
+  double cs[GRAM_CS];
+#pragma unroll
+  for (int k = 0; k < GRAM_CS; ++k) cs[k] = 0.0;
+
+  const uint32_t* cnt_row = p.counts ? p.counts + rep * p.N : nullptr;
+
+  for (int t = 0; t < n_rt; ++t) {
+    if (producer && t + p.stages - 1 < n_rt) issue_tile(t + p.stages - 1);  // refills the stage of tile t-1
+    const int s = t % p.stages;
+    const uint32_t use = (uint32_t)(t / p.stages);
+    const int64_t row = r0 + (int64_t)t * p.RT;
+    const int rows = (int)min((int64_t)p.RT, r1 - row);
+    uint32_t cnt = 0;
+    if (lane < rows) cnt = cnt_row ? __ldg(cnt_row + row + lane) : 1u;
+    uint32_t mask = __ballot_sync(0xffffffffu, cnt != 0);
+    mbar_wait(&full_bar[s], use & 1);
+    const double* base = tiles + (size_t)s * stage_doubles;
+    while (mask) {
+      const int r = __ffs(mask) - 1;
+      mask &= mask - 1;
+      const double c = (double)__shfl_sync(0xffffffffu, cnt, r);
+      const double* xr = base + (size_t)r * p.Ppad;
+      double xa[8], xb[8];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const double2 va = *reinterpret_cast<const double2*>(xr + off_a[k]);
+        const double2 vb = *reinterpret_cast<const double2*>(xr + off_b[k]);
+        xa[2 * k] = va.x; xa[2 * k + 1] = va.y;
+        xb[2 * k] = vb.x * c; xb[2 * k + 1] = vb.y * c;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fma(xa[i], xb[j], acc[i][j]);
+#pragma unroll
+      for (int k = 0; k < GRAM_CS; ++k)
+        if (k < ncs) {
+          const int col = cs0 + lane + 32 * k;
+          if (col < cs1) cs[k] = fma(c, xr[col], cs[k]);
+        }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[s]);
+  }
+
+  // ---- write the partial tile (undo the chunk rotation) and the column sums --------------------
+  const size_t slab = (size_t)rep * p.n_chunks + chunk;
+  if (tile_ok) {
+    double* g = p.G + (slab * p.n_tiles + tile) * TILE;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int ra = 2 * (((i >> 1) + rot_a) & 3) + (i & 1);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int cb = 2 * (((j >> 1) + rot_b) & 3) + (j & 1);
+        g[ra * SLOT + cb] = acc[i][j];
+      }
+    }
+  }
+  double* co = p.colsum + slab * p.Ppad;
+#pragma unroll
+  for (int k = 0; k < GRAM_CS; ++k)
+    if (k < ncs) {
+      const int col = cs0 + lane + 32 * k;
+      if (col < cs1) co[col] = cs[k];
+    }
+}
+
+// sum of the per-chunk partials in chunk order (deterministic)
+__global__ void reduce_chunks_kernel(const double* __restrict__ part, int64_t nrep, int n_chunks, int64_t per_rep,
+                                     double* __restrict__ out) {
+  const int64_t total = nrep * per_rep;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = e / per_rep, k = e - b * per_rep;
+    const double* src = part + (b * n_chunks) * per_rep + k;
+    double s = 0.0;
+    for (int c = 0; c < n_chunks; ++c) s += src[(int64_t)c * per_rep];
+    out[e] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-replicate solver kernel (one CTA per replicate)
+// ------------------------------------------------------------------------------------------------
+struct SolveBatch {
+  ModelView M;
+  const double* G; int64_t g_stride;
+  const double* colsum; int64_t cs_stride;
+  const double* mu;
+  double N;
+  int scheme; double tol; int max_iter;
+  double* ws;
+  double* out_rows; int64_t out_stride;  // may be null
+  double *weights, *loadings, *r2, *paths, *total, *crossloadings, *score_coef, *score_shift;  // single fit
+  int *iters, *status;
+};
+
+constexpr int SOLVE_THREADS = 128;
+
+__global__ void __launch_bounds__(SOLVE_THREADS) solve_kernel(const SolveBatch b) {
+  extern __shared__ __align__(16) double solver_smem[];
+  const int64_t rep = blockIdx.x;
+  SolveArgs A;
+  A.M = b.M;
+  A.G = b.G + rep * b.g_stride;
+  A.colsum = b.colsum + rep * b.cs_stride;
+  A.mu = b.mu;
+  A.N = b.N;
+  A.scheme = b.scheme;
+  A.tol = b.tol;
+  A.max_iter = b.max_iter;
+  A.ext_votes = nullptr;
+  A.ws = b.ws + rep * (int64_t)b.M.ws_doubles;
+  A.out_row = b.out_rows ? b.out_rows + rep * b.out_stride : nullptr;
+  A.weights = b.weights; A.loadings = b.loadings; A.r2 = b.r2; A.paths = b.paths; A.total = b.total;
+  A.crossloadings = b.crossloadings; A.score_coef = b.score_coef; A.score_shift = b.score_shift;
+  A.iters = b.iters + rep;
+  A.status = b.status + rep;
+  solve_replicate(A, solver_smem);
+}
+
+// scores[i][l] = sum_{c in block l} x~[i][c] coef[c] - shift[l]     (weights.py:60, 65-68)
+__global__ void scores_kernel(const double* __restrict__ X, int64_t N, int Ppad, int L, const int* __restrict__ lv_off,
+                              const int* __restrict__ lv_k, const double* __restrict__ coef,
+                              const double* __restrict__ shift, double* __restrict__ scores) {
+  const int64_t total = N * L;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = e / L;
+    const int l = (int)(e - i * L);
+    const int o = lv_off[l], k = lv_k[l];
+    const double* x = X + i * Ppad + o;
+    const double* cf = coef + o;
+    double s = 0.0;
+    for (int c = 0; c < k; ++c) s = fma(x[c], cf[c], s);
+    scores[e] = s - shift[l];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int plspm_version(void) { return 100; }
+const char* plspm_last_error(void) { return g_err.c_str(); }
+
+int plspm_device_count(int32_t* count) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) { *count = 0; return fail(PLSPM_ERR_CUDA, cudaGetErrorString(e)); }
+  *count = n;
+  return PLSPM_OK;
+}
+int plspm_set_device(int32_t device) {
+  CK(cudaSetDevice(device));
+  return PLSPM_OK;
+}
+
+int plspm_model_create(int32_t L, const int32_t* block_sizes, const int8_t* modes, const int8_t* path, int32_t scaled,
+                       int32_t tile_policy, plspm_model** out) {
+  if (!block_sizes || !modes || !path || !out) return fail(PLSPM_ERR_INVALID, "null argument");
+  plspm_model* m = new plspm_model();
+  std::string err;
+  if (build_model(L, block_sizes, modes, path, scaled, tile_policy, m->h, err)) {
+    delete m;
+    return fail(PLSPM_ERR_INVALID, err);
+  }
+  if (!m->h.full) {
+    delete m;
+    return fail(PLSPM_ERR_UNSUPPORTED, "sparse tile sets need the cross-moment sign pass (not built yet)");
+  }
+  if ((size_t)m->h.Ppad * 8 > 64 * 1024) {
+    delete m;
+    return fail(PLSPM_ERR_UNSUPPORTED, "more than 8192 (padded) manifest variables");
+  }
+  CK(cudaGetDevice(&m->device));
+  HostModel& h = m->h;
+  ModelView v = h.host_view();
+  int rc = 0;
+  rc |= upload_vec(m, h.lv_off, &v.lv_off);
+  rc |= upload_vec(m, h.lv_k, &v.lv_k);
+  rc |= upload_vec(m, h.lv_mode, &v.lv_mode);
+  rc |= upload_vec(m, h.col_lv, &v.col_lv);
+  rc |= upload_vec(m, h.col_src, &v.col_src);
+  rc |= upload_vec(m, h.path, &v.path);
+  rc |= upload_vec(m, h.tile_sa, &v.tile_sa);
+  rc |= upload_vec(m, h.tile_sb, &v.tile_sb);
+  rc |= upload_vec(m, h.tile_of, &v.tile_of);
+  rc |= upload_vec(m, h.pair_l, &v.pair_l);
+  rc |= upload_vec(m, h.pair_j, &v.pair_j);
+  rc |= upload_vec(m, h.pair_voff, &v.pair_voff);
+  rc |= upload_vec(m, h.lv_pair_begin, &v.lv_pair_begin);
+  rc |= upload_vec(m, h.eff_from, &v.eff_from);
+  rc |= upload_vec(m, h.eff_to, &v.eff_to);
+  rc |= upload_vec(m, h.chol_b_off, &v.chol_b_off);
+  rc |= upload_vec(m, h.pred_begin, &v.pred_begin);
+  rc |= upload_vec(m, h.pred_idx, &v.pred_idx);
+  rc |= upload_vec(m, h.succ_begin, &v.succ_begin);
+  rc |= upload_vec(m, h.succ_idx, &v.succ_idx);
+  if (rc) {
+    plspm_model_destroy(m);
+    return PLSPM_ERR_CUDA;
+  }
+  m->dv = v;
+  *out = m;
+  return PLSPM_OK;
+}
+
+void plspm_model_destroy(plspm_model* m) {
+  if (!m) return;
+  for (void* p : m->dev_allocs) cudaFree(p);
+  delete m;
+}
+
+int plspm_model_query(const plspm_model* m, int32_t* info) {
+  if (!m || !info) return fail(PLSPM_ERR_INVALID, "null argument");
+  std::memset(info, 0, 16 * sizeof(int32_t));
+  const HostModel& h = m->h;
+  info[0] = h.L; info[1] = h.P; info[2] = h.Ppad; info[3] = h.n_tiles; info[4] = h.n_tg; info[5] = h.n_pairs;
+  info[6] = h.n_eff; info[7] = h.n_out(); info[8] = h.full; info[9] = h.scaled;
+  return PLSPM_OK;
+}
+
+int plspm_model_effects(const plspm_model* m, int32_t* from, int32_t* to) {
+  if (!m || !from || !to) return fail(PLSPM_ERR_INVALID, "null argument");
+  for (int e = 0; e < m->h.n_eff; ++e) { from[e] = m->h.eff_from[e]; to[e] = m->h.eff_to[e]; }
+  return PLSPM_OK;
+}
+
+static int ws_reserve(plspm_data* d, size_t bytes) {
+  if (d->ws.bytes >= bytes) return 0;
+  if (d->ws.ptr) CK(cudaFree(d->ws.ptr));
+  d->ws.ptr = nullptr;
+  d->ws.bytes = 0;
+  CK(cudaMalloc(&d->ws.ptr, bytes));
+  d->ws.bytes = bytes;
+  return 0;
+}
+
+int plspm_data_create(const plspm_model* m, const double* X, int64_t N, int64_t ld, int32_t x_is_device,
+                      plspm_data** out) {
+  if (!m || !X || !out) return fail(PLSPM_ERR_INVALID, "null argument");
+  const HostModel& h = m->h;
+  if (N < 2) return fail(PLSPM_ERR_INVALID, "need at least two observations");
+  if (N >= ((int64_t)1 << 32)) return fail(PLSPM_ERR_UNSUPPORTED, "more than 2^32-1 observations");
+  if (ld < h.P) return fail(PLSPM_ERR_INVALID, "leading dimension smaller than the number of manifest variables");
+  plspm_data* d = new plspm_data();
+  d->model = m;
+  d->N = N;
+  int dev = 0;
+  cudaDeviceProp prop;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
+    delete d;
+    return fail(PLSPM_ERR_CUDA, "no CUDA device: plspm_b200 has no CPU path");
+  }
+  d->sm_count = prop.multiProcessorCount;
+  d->max_smem = (int)prop.sharedMemPerBlockOptin;
+  auto bail = [&](int rc) { plspm_data_destroy(d); return rc; };
+  if (cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking) != cudaSuccess)
+    return bail(fail(PLSPM_ERR_CUDA, "cudaStreamCreate failed"));
+  cudaStream_t st = d->stream;
+  double* raw = nullptr;
+  const double* Xd = X;
+  int rc = 0;
+  auto body = [&]() -> int {
+    CK(cudaMalloc((void**)&d->X, (size_t)N * h.Ppad * sizeof(double)));
+    CK(cudaMalloc((void**)&d->mu, (size_t)h.Ppad * sizeof(double)));
+    CK(cudaMemsetAsync(d->mu, 0, (size_t)h.Ppad * sizeof(double), st));
+    if (!x_is_device) {
+      CK(cudaMalloc((void**)&raw, (size_t)N * h.P * sizeof(double)));
+      CK(cudaMemcpy2DAsync(raw, (size_t)h.P * sizeof(double), X, (size_t)ld * sizeof(double),
+                           (size_t)h.P * sizeof(double), (size_t)N, cudaMemcpyHostToDevice, st));
+      Xd = raw;
+      ld = h.P;
+    }
+    const int nblocks = (int)std::min<int64_t>(1024, (N + 63) / 64);
+    const int64_t rpb = (N + nblocks - 1) / nblocks;
+    double* partial = nullptr;
+    CK(cudaMalloc((void**)&partial, (size_t)nblocks * h.P * sizeof(double)));
+    int* src_col = nullptr;
+    CK(cudaMalloc((void**)&src_col, (size_t)h.P * sizeof(int)));
+    CK(cudaMemcpyAsync(src_col, h.src_col.data(), (size_t)h.P * sizeof(int), cudaMemcpyHostToDevice, st));
+    d->timer.begin(ST_UPLOAD, st);
+    colsum_partial_kernel<<<nblocks, 256, 0, st>>>(Xd, N, ld, h.P, rpb, partial);
+    d->timer.end(st);
+    d->timer.begin(ST_UPLOAD, st);
+    colmean_final_kernel<<<(h.P + 127) / 128, 128, 0, st>>>(partial, nblocks, h.P, N, src_col, d->mu);
+    d->timer.end(st);
+    d->timer.begin(ST_UPLOAD, st);
+    relayout_kernel<<<d->sm_count * 8, 256, 0, st>>>(Xd, N, ld, h.Ppad, m->dv.col_src, d->mu, d->X);
+    d->timer.end(st);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));
+    d->timer.collect();
+    cudaFree(partial);
+    cudaFree(src_col);
+    return 0;
+  };
+  rc = body();
+  if (raw) cudaFree(raw);
+  if (rc) return bail(rc);
+  *out = d;
+  return PLSPM_OK;
+}
+
+void plspm_data_destroy(plspm_data* d) {
+  if (!d) return;
+  if (d->X) cudaFree(d->X);
+  if (d->mu) cudaFree(d->mu);
+  if (d->ws.ptr) cudaFree(d->ws.ptr);
+  if (d->stream) cudaStreamDestroy(d->stream);
+  delete d;
+}
+
+// Launch plan of the Gram kernel for nb replicates.
+struct GramPlan {
+  int RT, stages, n_chunks;
+  int64_t chunk_rows, n_groups;
+  size_t smem;
+};
+static int plan_gram(const plspm_data* d, int64_t nb, GramPlan& g) {
+  const HostModel& h = d->model->h;
+  const size_t row_bytes = (size_t)h.Ppad * 8;
+  int RT = 32;
+  while (RT > 1 && RT * row_bytes > 48 * 1024) RT >>= 1;
+  const size_t stage_bytes = RT * row_bytes;
+  const size_t budget = (size_t)d->max_smem - 1024;
+  int stages = (int)std::min<size_t>(GRAM_MAX_STAGES, budget / stage_bytes);
+  if (stages < 2) return fail(PLSPM_ERR_UNSUPPORTED, "manifest rows too wide for the shared-memory ring");
+  const int64_t n_tiles_rt = (d->N + RT - 1) / RT;
+  stages = (int)std::min<int64_t>(stages, std::max<int64_t>(2, n_tiles_rt));
+  const int64_t n_items = nb * h.n_tg;
+  const int64_t n_groups = (n_items + GRAM_WARPS - 1) / GRAM_WARPS;
+  // split rows only when there are too few (replicate, tile group) items to fill the chip
+  int64_t n_chunks = 1;
+  const int64_t want = (int64_t)d->sm_count * 2;
+  if (n_groups < want) n_chunks = (want + n_groups - 1) / n_groups;
+  n_chunks = std::max<int64_t>(1, std::min<int64_t>(n_chunks, n_tiles_rt / 4 > 0 ? n_tiles_rt / 4 : 1));
+  int64_t chunk_rows = ((n_tiles_rt + n_chunks - 1) / n_chunks) * RT;
+  n_chunks = (d->N + chunk_rows - 1) / chunk_rows;
+  g.RT = RT; g.stages = stages; g.n_chunks = (int)n_chunks; g.chunk_rows = chunk_rows; g.n_groups = n_groups;
+  g.smem = (size_t)stages * stage_bytes;
+  return 0;
+}
+
+// Shared implementation of fit (counts == null, one "replicate") and bootstrap batches.
+struct BatchOut {
+  double* out_rows = nullptr;  // device [nb][n_out] or null
+  double *weights = nullptr, *loadings = nullptr, *r2 = nullptr, *paths = nullptr, *total = nullptr,
+         *crossloadings = nullptr, *score_coef = nullptr, *score_shift = nullptr;  // device, single fit
+  int *iters = nullptr, *status = nullptr;  // device [nb]
+};
+
+static int run_batch(plspm_data* d, int64_t nb, const uint32_t* counts_dev, double* G, double* Gpart, double* colsum,
+                     double* cspart, double* ws_solver, int scheme, double tol, int max_iter, const GramPlan& gp,
+                     const BatchOut& o) {
+  const plspm_model* m = d->model;
+  const HostModel& h = m->h;
+  cudaStream_t st = d->stream;
+  GramParams p;
+  p.X = d->X; p.counts = counts_dev; p.N = d->N; p.Ppad = h.Ppad; p.n_tiles = h.n_tiles; p.n_tg = h.n_tg;
+  p.tile_sa = m->dv.tile_sa; p.tile_sb = m->dv.tile_sb;
+  p.n_items = nb * h.n_tg; p.n_chunks = gp.n_chunks; p.chunk_rows = gp.chunk_rows; p.RT = gp.RT; p.stages = gp.stages;
+  p.cs_cols = std::min(32 * GRAM_CS, ((h.Ppad + h.n_tg - 1) / h.n_tg + 31) / 32 * 32);
+  if ((int64_t)p.cs_cols * h.n_tg < h.Ppad) return fail(PLSPM_ERR_UNSUPPORTED, "column-sum partition too small");
+  p.G = (gp.n_chunks > 1) ? Gpart : G;
+  p.colsum = (gp.n_chunks > 1) ? cspart : colsum;
+  CK(cudaFuncSetAttribute(gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gp.smem));
+  const int64_t grid = gp.n_groups * gp.n_chunks;
+  if (grid > 0x7fffffff) return fail(PLSPM_ERR_UNSUPPORTED, "batch too large for one launch");
+  d->timer.begin(ST_GRAM, st);
+  gram_kernel<<<(unsigned)grid, GRAM_THREADS, gp.smem, st>>>(p);
+  d->timer.end(st);
+  CK(cudaGetLastError());
+  if (gp.n_chunks > 1) {
+    d->timer.begin(ST_REDUCE, st);
+    reduce_chunks_kernel<<<d->sm_count * 4, 256, 0, st>>>(Gpart, nb, gp.n_chunks, (int64_t)h.n_tiles * TILE, G);
+    d->timer.end(st);
+    d->timer.begin(ST_REDUCE, st);
+    reduce_chunks_kernel<<<d->sm_count, 256, 0, st>>>(cspart, nb, gp.n_chunks, h.Ppad, colsum);
+    d->timer.end(st);
+    CK(cudaGetLastError());
+  }
+  SolveBatch b;
+  b.M = m->dv;
+  b.G = G; b.g_stride = (int64_t)h.n_tiles * TILE;
+  b.colsum = colsum; b.cs_stride = h.Ppad;
+  b.mu = d->mu; b.N = (double)d->N; b.scheme = scheme; b.tol = tol; b.max_iter = max_iter;
+  b.ws = ws_solver;
+  b.out_rows = o.out_rows; b.out_stride = h.n_out();
+  b.weights = o.weights; b.loadings = o.loadings; b.r2 = o.r2; b.paths = o.paths; b.total = o.total;
+  b.crossloadings = o.crossloadings; b.score_coef = o.score_coef; b.score_shift = o.score_shift;
+  b.iters = o.iters; b.status = o.status;
+  const size_t smem = h.solver_smem_doubles() * sizeof(double);
+  if (smem > (size_t)d->max_smem) return fail(PLSPM_ERR_UNSUPPORTED, "model too large for the solver's shared memory");
+  CK(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  d->timer.begin(ST_SOLVE, st);
+  solve_kernel<<<(unsigned)nb, SOLVE_THREADS, smem, st>>>(b);
+  d->timer.end(st);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+static size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+
+int plspm_fit(const plspm_model* m, const plspm_data* dc, int32_t scheme, double tol, int32_t max_iter, double* weights,
+              double* loadings, double* r_squared, double* paths, double* total_effects, double* crossloadings,
+              double* scores, int32_t* iters, int32_t* status) {
+  if (!m || !dc || dc->model != m) return fail(PLSPM_ERR_INVALID, "model/data mismatch");
+  if (scheme < 0 || scheme > 2) return fail(PLSPM_ERR_INVALID, "unknown scheme");
+  plspm_data* d = const_cast<plspm_data*>(dc);
+  const HostModel& h = m->h;
+  const int64_t N = d->N;
+  GramPlan gp;
+  if (int rc = plan_gram(d, 1, gp)) return rc;
+  const size_t gsz = (size_t)h.n_tiles * TILE, L = h.L, P = h.P;
+  size_t off = 0;
+  auto take = [&](size_t doubles) { size_t o = off; off += align_up(doubles * 8); return o; };
+  const size_t o_G = take(gsz), o_Gp = take(gsz * gp.n_chunks), o_cs = take(h.Ppad), o_csp = take((size_t)h.Ppad * gp.n_chunks);
+  const size_t o_ws = take(h.ws_doubles), o_w = take(P), o_ld = take(P), o_r2 = take(L), o_pa = take(L * L);
+  const size_t o_to = take(L * L), o_cl = take(P * L), o_cf = take(h.Ppad), o_sh = take(L), o_it = take(2);
+  const size_t o_sc = take(scores ? (size_t)N * L : 1);
+  if (int rc = ws_reserve(d, off)) return rc;
+  char* base = (char*)d->ws.ptr;
+  auto D = [&](size_t o) { return (double*)(base + o); };
+  cudaStream_t st = d->stream;
+  BatchOut o;
+  o.weights = D(o_w); o.loadings = D(o_ld); o.r2 = D(o_r2); o.paths = D(o_pa); o.total = D(o_to);
+  o.crossloadings = D(o_cl); o.score_coef = D(o_cf); o.score_shift = D(o_sh);
+  int* it_dev = (int*)D(o_it);
+  o.iters = it_dev; o.status = it_dev + 2;
+  if (int rc = run_batch(d, 1, nullptr, D(o_G), D(o_Gp), D(o_cs), D(o_csp), D(o_ws), scheme, tol, max_iter, gp, o)) return rc;
+  if (scores) {
+    d->timer.begin(ST_SCORES, st);
+    scores_kernel<<<d->sm_count * 8, 256, 0, st>>>(d->X, N, h.Ppad, h.L, m->dv.lv_off, m->dv.lv_k, o.score_coef,
+                                                   o.score_shift, D(o_sc));
+    d->timer.end(st);
+    CK(cudaGetLastError());
+  }
+  int host_is[4] = {0, 0, 0, 0};
+  CK(cudaMemcpyAsync(host_is, it_dev, sizeof(host_is), cudaMemcpyDeviceToHost, st));
+  if (weights) CK(cudaMemcpyAsync(weights, o.weights, P * 8, cudaMemcpyDeviceToHost, st));
+  if (loadings) CK(cudaMemcpyAsync(loadings, o.loadings, P * 8, cudaMemcpyDeviceToHost, st));
+  if (r_squared) CK(cudaMemcpyAsync(r_squared, o.r2, L * 8, cudaMemcpyDeviceToHost, st));
+  if (paths) CK(cudaMemcpyAsync(paths, o.paths, L * L * 8, cudaMemcpyDeviceToHost, st));
+  if (total_effects) CK(cudaMemcpyAsync(total_effects, o.total, L * L * 8, cudaMemcpyDeviceToHost, st));
+  if (crossloadings) CK(cudaMemcpyAsync(crossloadings, o.crossloadings, P * L * 8, cudaMemcpyDeviceToHost, st));
+  if (scores) CK(cudaMemcpyAsync(scores, D(o_sc), (size_t)N * L * 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  d->timer.collect();
+  if (iters) *iters = host_is[0];
+  if (status) *status = host_is[2];
+  return PLSPM_OK;
+}
+
+int plspm_bootstrap(const plspm_model* m, const plspm_data* dc, int32_t scheme, double tol, int32_t max_iter,
+                    int64_t rep_begin, int64_t rep_count, uint64_t seed, const int32_t* idx, double* out,
+                    int32_t out_is_device, int32_t* status, int32_t* iters) {
+  if (!m || !dc || dc->model != m) return fail(PLSPM_ERR_INVALID, "model/data mismatch");
+  if (scheme < 0 || scheme > 2) return fail(PLSPM_ERR_INVALID, "unknown scheme");
+  if (rep_count < 0 || !out) return fail(PLSPM_ERR_INVALID, "bad replicate range / null output");
+  if (rep_count == 0) return PLSPM_OK;
+  plspm_data* d = const_cast<plspm_data*>(dc);
+  const HostModel& h = m->h;
+  const int64_t N = d->N;
+  const size_t gsz = (size_t)h.n_tiles * TILE, n_out = h.n_out();
+  if (idx)
+    for (int64_t e = 0; e < rep_count * N; ++e)
+      if (idx[e] < 0 || idx[e] >= N) return fail(PLSPM_ERR_INVALID, "resample index out of range");
+  // batch size: bound the workspace (~1.5 GB) and keep the Gram grid a whole number of waves
+  const size_t per_rep = (size_t)N * 4 + (gsz + h.Ppad + h.ws_doubles + n_out) * 8 + (idx ? (size_t)N * 4 : 0) + 64;
+  int64_t nb_max = std::max<int64_t>(1, (int64_t)((size_t)1536 * 1024 * 1024 / per_rep));
+  nb_max = std::min<int64_t>(nb_max, rep_count);
+  const int64_t wave = (int64_t)d->sm_count * GRAM_WARPS;  // warp items per wave
+  if (nb_max * h.n_tg > wave) {
+    int64_t waves = nb_max * h.n_tg / wave;
+    nb_max = std::max<int64_t>(1, waves * wave / h.n_tg);
+  }
+  GramPlan gp;
+  if (int rc = plan_gram(d, nb_max, gp)) return rc;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return o; };
+  const size_t o_cnt = take((size_t)nb_max * N * 4), o_idx = take(idx ? (size_t)nb_max * N * 4 : 8);
+  const size_t o_G = take((size_t)nb_max * gsz * 8), o_Gp = take(gp.n_chunks > 1 ? (size_t)nb_max * gsz * gp.n_chunks * 8 : 8);
+  const size_t o_cs = take((size_t)nb_max * h.Ppad * 8), o_csp = take(gp.n_chunks > 1 ? (size_t)nb_max * h.Ppad * gp.n_chunks * 8 : 8);
+  const size_t o_ws = take((size_t)nb_max * h.ws_doubles * 8), o_out = take(out_is_device ? 8 : (size_t)nb_max * n_out * 8);
+  const size_t o_it = take((size_t)nb_max * 4), o_st = take((size_t)nb_max * 4);
+  if (int rc = ws_reserve(d, off)) return rc;
+  char* base = (char*)d->ws.ptr;
+  cudaStream_t st = d->stream;
+  for (int64_t b0 = 0; b0 < rep_count; b0 += nb_max) {
+    const int64_t nb = std::min(nb_max, rep_count - b0);
+    GramPlan g2 = gp;
+    if (nb != nb_max) {
+      if (int rc = plan_gram(d, nb, g2)) return rc;
+      if (g2.n_chunks > gp.n_chunks) { g2 = gp; g2.n_groups = (nb * h.n_tg + GRAM_WARPS - 1) / GRAM_WARPS; }
+    }
+    uint32_t* cnt = (uint32_t*)(base + o_cnt);
+    int32_t* idx_dev = nullptr;
+    CK(cudaMemsetAsync(cnt, 0, (size_t)nb * N * 4, st));
+    if (idx) {
+      idx_dev = (int32_t*)(base + o_idx);
+      CK(cudaMemcpyAsync(idx_dev, idx + b0 * N, (size_t)nb * N * 4, cudaMemcpyHostToDevice, st));
+    }
+    const int64_t threads = ((N + 3) / 4) * nb;
+    d->timer.begin(ST_COUNTS, st);
+    counts_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(cnt, idx_dev, N, nb, rep_begin + b0, seed);
+    d->timer.end(st);
+    CK(cudaGetLastError());
+    BatchOut o;
+    o.out_rows = out_is_device ? out + (size_t)b0 * n_out : (double*)(base + o_out);
+    o.iters = (int*)(base + o_it);
+    o.status = (int*)(base + o_st);
+    if (int rc = run_batch(d, nb, cnt, (double*)(base + o_G), (double*)(base + o_Gp), (double*)(base + o_cs),
+                           (double*)(base + o_csp), (double*)(base + o_ws), scheme, tol, max_iter, g2, o))
+      return rc;
+    if (!out_is_device)
+      CK(cudaMemcpyAsync(out + (size_t)b0 * n_out, o.out_rows, (size_t)nb * n_out * 8, cudaMemcpyDeviceToHost, st));
+    if (iters) CK(cudaMemcpyAsync(iters + b0, o.iters, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
+    if (status) CK(cudaMemcpyAsync(status + b0, o.status, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    d->timer.collect();
+  }
+  return PLSPM_OK;
+}
+
+int plspm_bootstrap_host(const plspm_model* m, const double* X, int64_t N, int64_t ld, int32_t scheme, double tol,
+                         int32_t max_iter, int64_t rep_begin, int64_t rep_count, uint64_t seed, const int32_t* idx,
+                         double* out, int32_t* status, int32_t* iters) {
+  plspm_data* d = nullptr;
+  int rc = plspm_data_create(m, X, N, ld, 0, &d);
+  if (rc) return rc;
+  rc = plspm_bootstrap(m, d, scheme, tol, max_iter, rep_begin, rep_count, seed, idx, out, 0, status, iters);
+  plspm_data_destroy(d);
+  return rc;
+}
+
+int plspm_resample_indices(uint64_t seed, int64_t replicate, int64_t N, int32_t* idx_out) {
+  if (!idx_out || N < 1 || N >= ((int64_t)1 << 32)) return fail(PLSPM_ERR_INVALID, "bad arguments");
+  int32_t* dev = nullptr;
+  CK(cudaMalloc((void**)&dev, (size_t)N * 4));
+  const int64_t groups = (N + 3) / 4;
+  indices_kernel<<<(unsigned)((groups + 255) / 256), 256>>>(dev, N, (uint64_t)replicate, seed);
+  cudaError_t e = cudaMemcpy(idx_out, dev, (size_t)N * 4, cudaMemcpyDeviceToHost);
+  cudaFree(dev);
+  if (e != cudaSuccess) return fail(PLSPM_ERR_CUDA, cudaGetErrorString(e));
+  return PLSPM_OK;
+}
+
+int plspm_profile_reset(void) {
+  std::lock_guard<std::mutex> lk(g_prof.mu);
+  for (int i = 0; i < ST_N; ++i) { g_prof.ms[i] = 0; g_prof.launches[i] = 0; }
+  return PLSPM_OK;
+}
+int plspm_profile_get(double* ms, int64_t* launches) {
+  std::lock_guard<std::mutex> lk(g_prof.mu);
+  for (int i = 0; i < ST_N; ++i) {
+    if (ms) ms[i] = g_prof.ms[i];
+    if (launches) launches[i] = g_prof.launches[i];
+  }
+  return PLSPM_OK;
+}
+
+int plspm_host_alloc(void** ptr, int64_t bytes) {
+  CK(cudaMallocHost(ptr, (size_t)bytes));
+  return PLSPM_OK;
+}
+int plspm_host_free(void* ptr) {
+  CK(cudaFreeHost(ptr));
+  return PLSPM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,82 @@
+// TEST INFRASTRUCTURE ONLY -- never loaded by the product package.
+//
+// Host emulation of the device pipeline (slot layout + global centring, resample counts,
+// weighted Gram tiles, per-replicate solver, scores) so that tests/ can check the solver
+// logic in csrc/solver_core.h against the oracle in a container without a GPU.  The Gram
+// tiles are produced here by a plain triple loop that writes the same tile layout the
+// sm_100a Gram kernel writes; the solver is the shipped source compiled for the host.
+#define PLSPM_HOST_EMUL 1
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../plspm-python_b200/csrc/plspm_model.h"
+#include "../../plspm-python_b200/csrc/solver_core.h"
+
+using namespace plspm;
+
+extern "C" int emul_model_info(int L, const int32_t* block_sizes, const int8_t* modes, const int8_t* path, int scaled,
+                               int tile_policy, int32_t* info /*[8]*/, int32_t* eff_from, int32_t* eff_to) {
+  HostModel m;
+  std::string err;
+  if (build_model(L, block_sizes, modes, path, scaled, tile_policy, m, err)) return 1;
+  info[0] = m.P; info[1] = m.Ppad; info[2] = m.n_tiles; info[3] = m.n_tg; info[4] = m.n_pairs;
+  info[5] = m.n_eff; info[6] = m.n_out(); info[7] = m.full;
+  if (eff_from)
+    for (int e = 0; e < m.n_eff; ++e) { eff_from[e] = m.eff_from[e]; eff_to[e] = m.eff_to[e]; }
+  return 0;
+}
+
+extern "C" int emul_fit(int L, const int32_t* block_sizes, const int8_t* modes, const int8_t* path, int scaled,
+                        int tile_policy, const double* X, int64_t N, const int32_t* idx, int scheme, double tol,
+                        int max_iter, double* out_row, double* weights, double* loadings, double* r2, double* paths,
+                        double* total, double* crossloadings, double* scores, int32_t* iters, int32_t* status) {
+  HostModel m;
+  std::string err;
+  if (build_model(L, block_sizes, modes, path, scaled, tile_policy, m, err)) return 1;
+  const int P = m.P, Pp = m.Ppad;
+  // upload-time layout: slot padded, globally centred
+  std::vector<double> mu(Pp, 0.0), Xs((size_t)N * Pp, 0.0);
+  for (int p = 0; p < P; ++p) {
+    double s = 0.0;
+    for (int64_t i = 0; i < N; ++i) s += X[i * P + p];
+    mu[m.src_col[p]] = s / (double)N;
+  }
+  for (int64_t i = 0; i < N; ++i)
+    for (int p = 0; p < P; ++p) Xs[i * Pp + m.src_col[p]] = X[i * P + p] - mu[m.src_col[p]];
+  std::vector<double> cnt(N, idx ? 0.0 : 1.0);
+  if (idx)
+    for (int64_t i = 0; i < N; ++i) cnt[idx[i]] += 1.0;
+  std::vector<double> G((size_t)m.n_tiles * TILE, 0.0), colsum(Pp, 0.0);
+  for (int64_t i = 0; i < N; ++i) {
+    if (cnt[i] == 0.0) continue;
+    const double* x = &Xs[i * Pp];
+    for (int p = 0; p < Pp; ++p) colsum[p] += cnt[i] * x[p];
+    for (int t = 0; t < m.n_tiles; ++t) {
+      const double* xa = x + m.tile_sa[t] * SLOT;
+      const double* xb = x + m.tile_sb[t] * SLOT;
+      double* g = &G[(size_t)t * TILE];
+      for (int r = 0; r < SLOT; ++r)
+        for (int c = 0; c < SLOT; ++c) g[r * SLOT + c] += xa[r] * (cnt[i] * xb[c]);
+    }
+  }
+  std::vector<double> smem(m.solver_smem_doubles(), 0.0), ws(m.ws_doubles, 0.0), coef(Pp, 0.0), shift(L, 0.0);
+  SolveArgs A;
+  std::memset(&A, 0, sizeof(A));
+  A.M = m.host_view();
+  A.G = G.data(); A.colsum = colsum.data(); A.mu = mu.data(); A.N = (double)N;
+  A.scheme = scheme; A.tol = tol; A.max_iter = max_iter; A.ext_votes = nullptr; A.ws = ws.data();
+  A.out_row = out_row; A.weights = weights; A.loadings = loadings; A.r2 = r2; A.paths = paths; A.total = total;
+  A.crossloadings = crossloadings; A.score_coef = coef.data(); A.score_shift = shift.data();
+  A.iters = iters; A.status = status;
+  solve_replicate(A, smem.data());
+  if (scores && !idx)
+    for (int64_t i = 0; i < N; ++i)
+      for (int l = 0; l < L; ++l) {
+        double s = 0.0;
+        for (int c = m.lv_off[l]; c < m.lv_off[l] + m.lv_k[l]; ++c) s += Xs[i * Pp + c] * coef[c];
+        scores[i * L + l] = s - shift[l];
+      }
+  return 0;
+}

@@ -1,0 +1,193 @@
+"""GPU parity tests: the CUDA path (through the C ABI, ctypes) vs the CPU oracle and the golden fixtures.
+Tolerance: 1e-6 relative on outer weights, LV scores and path coefficients (BASELINE.json north_star);
+iteration counts must be identical."""
+import numpy as np
+import pytest
+
+from oracle import plspm_oracle as orc
+from plspm_b200.synth import make_synthetic
+
+pytestmark = pytest.mark.gpu
+REL = 1e-6
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from plspm_b200 import engine
+    engine.load()
+    assert engine.device_count() > 0, "no CUDA device"
+    engine.set_device(0)
+    return engine
+
+
+def check_fit(got, ref, rel=REL):
+    assert got["status"] == 0
+    assert got["iterations"] == ref["iterations"]
+    np.testing.assert_allclose(got["weights"], ref["weights"], rtol=rel)
+    np.testing.assert_allclose(got["scores"], ref["scores"], rtol=rel, atol=1e-8)
+    np.testing.assert_allclose(got["path_coefficients"], ref["path_coefficients"], rtol=rel, atol=1e-9)
+    np.testing.assert_allclose(got["total_effects"], ref["total_effects"], rtol=rel, atol=1e-9)
+    np.testing.assert_allclose(got["r_squared"], ref["r_squared"], rtol=rel, atol=1e-9)
+    np.testing.assert_allclose(got["loadings"], ref["loadings"], rtol=rel, atol=1e-9)
+    np.testing.assert_allclose(got["crossloadings"], ref["crossloadings"], rtol=rel, atol=1e-8)
+
+
+@pytest.mark.parametrize("scheme", ("centroid", "factorial", "path"))
+@pytest.mark.parametrize("mode", (0, 1))
+@pytest.mark.parametrize("scaled", (False, True))
+def test_satisfaction_vs_oracle_and_reference(eng, sat, scheme, mode, scaled):
+    model = eng.Model(sat["block_sizes"], [mode] * 6, sat["path"], scaled)
+    data = eng.Data(model, sat["X"])
+    got = eng.fit(model, data, scheme)
+    ref = orc.fit(sat["X"], sat["block_sizes"], [mode] * 6, sat["path"], scheme, scaled)
+    check_fit(got, ref)
+    tag = "ref/%s/%s/%s/" % (scheme, "AB"[mode], "scaled" if scaled else "unscaled")
+    assert got["iterations"] == int(sat[tag + "iterations"])
+    np.testing.assert_allclose(got["weights"], sat[tag + "weights"], rtol=REL)
+    np.testing.assert_allclose(got["scores"], sat[tag + "scores"], rtol=REL, atol=1e-8)
+    np.testing.assert_allclose(got["path_coefficients"], sat[tag + "path_coefficients"], rtol=REL, atol=1e-9)
+
+
+def test_satisfaction_r_golden(eng, sat):
+    model = eng.Model(sat["block_sizes"], [0] * 6, sat["path"], False)
+    data = eng.Data(model, sat["X"])
+    got = eng.fit(model, data, "centroid")
+    assert got["iterations"] == 4
+    np.testing.assert_allclose(got["scores"], sat["R/scores"], rtol=REL, atol=1e-8)
+    np.testing.assert_allclose(got["weights"], sat["R/centroid/weight"], rtol=REL)
+    np.testing.assert_allclose(got["loadings"], sat["R/centroid/loading"], rtol=REL)
+    np.testing.assert_allclose(got["crossloadings"], sat["R/crossloadings"], rtol=REL, atol=1e-9)
+    lvs = list(sat["lvs"])
+    for f, t, d, tot in zip(sat["R/effects_from"], sat["R/effects_to"], sat["R/effects_direct"], sat["R/effects_total"]):
+        i, j = lvs.index(t), lvs.index(f)
+        np.testing.assert_allclose(got["path_coefficients"][i, j], d, rtol=REL, atol=1e-10)
+        np.testing.assert_allclose(got["total_effects"][i, j], tot, rtol=REL, atol=1e-10)
+    for scheme in ("path", "factorial"):
+        g = eng.fit(model, data, scheme)
+        np.testing.assert_allclose(g["weights"], sat["R/%s/weight" % scheme], rtol=REL)
+        np.testing.assert_allclose(g["loadings"], sat["R/%s/loading" % scheme], rtol=REL)
+
+
+@pytest.mark.parametrize("case", ("syn_a", "syn_b", "syn_c", "syn_d", "syn_e", "syn_f", "syn_g", "syn_h"))
+def test_synthetic_cases(eng, syn, case):
+    N, L, K, seed = (int(v) for v in syn[case + "/gen"])
+    X, path = make_synthetic(N, L, K, seed, reverse_blocks=tuple(int(v) for v in syn[case + "/reverse"]))
+    mode = 0 if str(syn[case + "/mode"]) == "A" else 1
+    scheme, scaled = str(syn[case + "/scheme"]), bool(syn[case + "/scaled"])
+    model = eng.Model([K] * L, [mode] * L, path, scaled)
+    data = eng.Data(model, X)
+    got = eng.fit(model, data, scheme)
+    check_fit(got, orc.fit(X, [K] * L, [mode] * L, path, scheme, scaled))
+    assert got["iterations"] == int(syn[case + "/iterations"])
+    np.testing.assert_allclose(got["weights"], syn[case + "/weights"], rtol=REL)
+    np.testing.assert_allclose(got["scores"], syn[case + "/scores"], rtol=REL, atol=1e-8)
+
+
+@pytest.mark.parametrize("case", ("centroid/A/unscaled", "path/B/scaled", "factorial/A/scaled"))
+def test_bootstrap_injected_indices_vs_reference(eng, sat, case):
+    scheme, mode, sc = case.split("/")
+    m = 0 if mode == "A" else 1
+    nrep = int(sat["boot/n_replicates"])
+    idx = np.random.default_rng(1234).integers(0, 250, (1000, 250), dtype=np.int32)
+    model = eng.Model(sat["block_sizes"], [m] * 6, sat["path"], sc == "scaled")
+    data = eng.Data(model, sat["X"])
+    rows, status, iters = eng.bootstrap(model, data, scheme, 0, 1000, idx=idx)
+    assert (status == 0).all()
+    tag = "boot/%s/" % case
+    np.testing.assert_array_equal(iters[:nrep], sat[tag + "iterations"])
+    w, r2, tot, direct, load = model.split_row(rows)
+    rel = REL if mode == "A" else 1e-5  # Mode B resamples of 250 rows are ill-conditioned
+    np.testing.assert_allclose(w[:nrep], sat[tag + "weights"], rtol=rel)
+    np.testing.assert_allclose(r2[:nrep], sat[tag + "r_squared"], rtol=rel, atol=1e-9)
+    np.testing.assert_allclose(load[:nrep], sat[tag + "loadings"], rtol=rel, atol=1e-9)
+    pc = np.array([[sat[tag + "path_coefficients"][b, t, f] for f, t in zip(model.effects_from, model.effects_to)]
+                   for b in range(nrep)])
+    te = np.array([[sat[tag + "total_effects"][b, t, f] for f, t in zip(model.effects_from, model.effects_to)]
+                   for b in range(nrep)])
+    np.testing.assert_allclose(direct[:nrep], pc, rtol=rel, atol=1e-9)
+    np.testing.assert_allclose(tot[:nrep], te, rtol=rel, atol=1e-9)
+    # all 1000 replicates (config C2) against the oracle
+    orows, oiters, ostatus = orc.bootstrap(sat["X"], idx, sat["block_sizes"], [m] * 6, sat["path"], scheme,
+                                           sc == "scaled")
+    np.testing.assert_array_equal(iters, oiters)
+    np.testing.assert_allclose(rows, orows, rtol=rel, atol=1e-9)
+
+
+def test_philox_stream_matches_oracle(eng):
+    for seed, rep, N in ((0, 0, 250), (7, 12345678901, 1001), (2**40 + 5, 3, 4099)):
+        np.testing.assert_array_equal(eng.resample_indices(seed, rep, N), orc.philox_indices(seed, rep, N))
+
+
+def test_bootstrap_generated_indices_match_injected(eng, sat):
+    model = eng.Model(sat["block_sizes"], [0] * 6, sat["path"], True)
+    data = eng.Data(model, sat["X"])
+    rows, status, iters = eng.bootstrap(model, data, "centroid", 40, 24, seed=99)
+    idx = np.stack([orc.philox_indices(99, 40 + b, 250) for b in range(24)])
+    rows2, status2, iters2 = eng.bootstrap(model, data, "centroid", 0, 24, idx=idx)
+    np.testing.assert_array_equal(rows, rows2)
+    np.testing.assert_array_equal(iters, iters2)
+    orows, oiters, _ = orc.bootstrap(sat["X"], idx, sat["block_sizes"], [0] * 6, sat["path"], "centroid", True)
+    np.testing.assert_allclose(rows, orows, rtol=REL, atol=1e-9)
+
+
+def test_ragged_blocks_mixed_modes(eng):
+    rng = np.random.default_rng(3)
+    sizes = [1, 9, 3, 17, 2]
+    L = len(sizes)
+    path = np.zeros((L, L), dtype=np.int8)
+    path[1, 0] = path[2, 0] = path[2, 1] = path[3, 2] = path[4, 1] = path[4, 3] = 1
+    eta = rng.standard_normal((3001, L))
+    for i in range(1, L):
+        eta[:, i] += eta[:, :i] @ (0.5 * path[i, :i])
+    X = np.concatenate([eta[:, [l]] * rng.uniform(0.5, 1.0, (1, k)) + 0.7 * rng.standard_normal((3001, k))
+                        for l, k in enumerate(sizes)], axis=1) * 3.0 + 10.0
+    modes = [0, 1, 0, 0, 1]
+    model = eng.Model(sizes, modes, path, True)
+    data = eng.Data(model, X)
+    for scheme in ("centroid", "factorial", "path"):
+        check_fit(eng.fit(model, data, scheme), orc.fit(X, sizes, modes, path, scheme, True))
+    idx = rng.integers(0, 3001, (5, 3001), dtype=np.int32)
+    rows, status, iters = eng.bootstrap(model, data, "path", 0, 5, idx=idx)
+    orows, oiters, _ = orc.bootstrap(X, idx, sizes, modes, path, "path", True)
+    np.testing.assert_array_equal(iters, oiters)
+    np.testing.assert_allclose(rows, orows, rtol=REL, atol=1e-9)
+
+
+def test_not_converged_and_edge_inputs(eng, sat):
+    model = eng.Model(sat["block_sizes"], [1] * 6, sat["path"], True)
+    data = eng.Data(model, sat["X"])
+    got = eng.fit(model, data, "centroid", tol=1e-30, max_iter=3)
+    assert got["status"] == eng.STATUS_NOT_CONVERGED and got["iterations"] == 4
+    rows, status, iters = eng.bootstrap(model, data, "centroid", 0, 0)
+    assert rows.shape == (0, model.n_out)
+    with pytest.raises(eng.EngineError):
+        eng.bootstrap(model, data, "centroid", 0, 1, idx=np.full((1, 250), 250, dtype=np.int32))
+    # a resample that repeats one row N times has zero variance: flagged, never a crash
+    rows, status, iters = eng.bootstrap(model, data, "centroid", 0, 1, idx=np.zeros((1, 250), dtype=np.int32))
+    assert status[0] != 0 or not np.isfinite(rows).all()
+
+
+def test_medium_size_properties(eng):
+    """N=20k, 16 LVs x 8 MVs: oracle parity on the fit, then size-independent properties of the bootstrap:
+    identity resample == original fit; row permutation invariance."""
+    N, L, K = 20000, 16, 8
+    X, path = make_synthetic(N, L, K, seed=1)
+    model = eng.Model([K] * L, [0] * L, path, True)
+    data = eng.Data(model, X)
+    got = eng.fit(model, data, "factorial")
+    check_fit(got, orc.fit(X, [K] * L, [0] * L, path, "factorial", True))
+    ident = np.arange(N, dtype=np.int32)[None, :]
+    perm = np.random.default_rng(5).permutation(N).astype(np.int32)[None, :]
+    rows, status, iters = eng.bootstrap(model, data, "factorial", 0, 2, idx=np.concatenate((ident, perm)))
+    w, r2, tot, direct, load = model.split_row(rows)
+    assert (status == 0).all() and (iters == got["iterations"]).all()
+    np.testing.assert_allclose(w[0], got["weights"], rtol=1e-10)
+    np.testing.assert_allclose(w[1], got["weights"], rtol=1e-10)
+    np.testing.assert_allclose(load[0], got["loadings"], rtol=1e-10)
+    np.testing.assert_allclose(r2[0], got["r_squared"], rtol=1e-9, atol=1e-12)
+    # generated replicates against the oracle on the same Philox indices
+    rows, status, iters = eng.bootstrap(model, data, "factorial", 5, 3, seed=11)
+    idx = np.stack([orc.philox_indices(11, 5 + b, N) for b in range(3)])
+    orows, oiters, _ = orc.bootstrap(X, idx, [K] * L, [0] * L, path, "factorial", True)
+    np.testing.assert_array_equal(iters, oiters)
+    np.testing.assert_allclose(rows, orows, rtol=REL, atol=1e-9)

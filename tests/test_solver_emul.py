@@ -1,0 +1,92 @@
+"""Solver logic (csrc/solver_core.h compiled for the host, tests/emul) vs the oracle.  CPU only.
+The GPU parity tests (tests/test_gpu_parity.py) run the same comparisons through the CUDA library."""
+import numpy as np
+import pytest
+
+from oracle import plspm_oracle as orc
+from plspm_b200.synth import make_synthetic
+from tests.emul import emul
+
+REL = 1e-6  # north_star tolerance; the covariance-domain solver is in practice ~1e-12
+
+
+def check(r, o, L, rel=1e-9):
+    assert r["status"] == 0
+    assert r["iterations"] == o["iterations"]
+    np.testing.assert_allclose(r["weights"], o["weights"], rtol=rel)
+    np.testing.assert_allclose(r["scores"], o["scores"], rtol=rel, atol=1e-10)
+    np.testing.assert_allclose(r["path_coefficients"], o["path_coefficients"], rtol=rel, atol=1e-11)
+    np.testing.assert_allclose(r["total_effects"], o["total_effects"], rtol=rel, atol=1e-11)
+    np.testing.assert_allclose(r["r_squared"], o["r_squared"], rtol=rel, atol=1e-11)
+    np.testing.assert_allclose(r["loadings"], o["loadings"], rtol=rel, atol=1e-11)
+    np.testing.assert_allclose(r["crossloadings"], o["crossloadings"], rtol=rel, atol=1e-10)
+
+
+@pytest.mark.parametrize("scheme", ("centroid", "factorial", "path"))
+@pytest.mark.parametrize("mode", (0, 1))
+@pytest.mark.parametrize("scaled", (False, True))
+def test_satisfaction(sat, scheme, mode, scaled):
+    L = 6
+    o = orc.fit(sat["X"], sat["block_sizes"], [mode] * L, sat["path"], scheme, scaled)
+    r = emul.fit(sat["X"], sat["block_sizes"], [mode] * L, sat["path"], scheme, scaled)
+    check(r, o, L, rel=1e-9 if mode == 0 else 1e-7)
+
+
+def test_satisfaction_golden_r(sat):
+    r = emul.fit(sat["X"], sat["block_sizes"], [0] * 6, sat["path"], "centroid", False)
+    assert r["iterations"] == 4
+    np.testing.assert_allclose(r["weights"], sat["R/centroid/weight"], rtol=REL)
+    np.testing.assert_allclose(r["scores"], sat["R/scores"], rtol=REL, atol=1e-9)
+    np.testing.assert_allclose(r["loadings"], sat["R/centroid/loading"], rtol=REL)
+
+
+@pytest.mark.parametrize("case", ("syn_a", "syn_b", "syn_c", "syn_d", "syn_e", "syn_f", "syn_g", "syn_h"))
+def test_synthetic_cases(syn, case):
+    N, L, K, seed = (int(v) for v in syn[case + "/gen"])
+    X, path = make_synthetic(N, L, K, seed, reverse_blocks=tuple(int(v) for v in syn[case + "/reverse"]))
+    mode = 0 if str(syn[case + "/mode"]) == "A" else 1
+    scheme, scaled = str(syn[case + "/scheme"]), bool(syn[case + "/scaled"])
+    o = orc.fit(X, [K] * L, [mode] * L, path, scheme, scaled)
+    r = emul.fit(X, [K] * L, [mode] * L, path, scheme, scaled)
+    check(r, o, L, rel=1e-8)
+    np.testing.assert_allclose(r["weights"], syn[case + "/weights"], rtol=REL)
+
+
+def test_bootstrap_rows(sat):
+    idx = np.random.default_rng(1234).integers(0, 250, (1000, 250), dtype=np.int32)[:12]
+    for scheme, mode, scaled in (("centroid", 0, False), ("path", 1, True)):
+        out, iters, status = orc.bootstrap(sat["X"], idx, sat["block_sizes"], [mode] * 6, sat["path"], scheme, scaled)
+        for b in range(idx.shape[0]):
+            r = emul.fit(sat["X"], sat["block_sizes"], [mode] * 6, sat["path"], scheme, scaled, idx=idx[b])
+            assert r["iterations"] == iters[b]
+            np.testing.assert_allclose(r["out_row"], out[b], rtol=1e-7, atol=1e-10)
+
+
+def test_ragged_blocks_and_mixed_modes():
+    rng = np.random.default_rng(3)
+    sizes = [1, 9, 3, 17, 2]
+    L = len(sizes)
+    path = np.zeros((L, L), dtype=np.int8)
+    path[1, 0] = path[2, 0] = path[2, 1] = path[3, 2] = path[4, 1] = path[4, 3] = 1
+    eta = rng.standard_normal((300, L))
+    for i in range(1, L):
+        eta[:, i] += eta[:, :i] @ (0.5 * path[i, :i])
+    X = np.concatenate([eta[:, [l]] * rng.uniform(0.5, 1.0, (1, k)) + 0.7 * rng.standard_normal((300, k))
+                        for l, k in enumerate(sizes)], axis=1) * 3.0 + 10.0
+    modes = [0, 1, 0, 0, 1]
+    for scheme in ("centroid", "factorial", "path"):
+        o = orc.fit(X, sizes, modes, path, scheme, True)
+        r = emul.fit(X, sizes, modes, path, scheme, True)
+        check(r, o, L, rel=1e-8)
+
+
+def test_not_converged_status(sat):
+    r = emul.fit(sat["X"], sat["block_sizes"], [1] * 6, sat["path"], "centroid", True, tol=1e-30, max_iter=3)
+    assert r["status"] == 1 and r["iterations"] == 4  # max_iter + 1 iterate calls (quirk Q4)
+
+
+def test_model_tables(sat):
+    info = emul.model_info(sat["block_sizes"], [0] * 6, sat["path"], 0)
+    assert info["P"] == 27 and info["Ppad"] == 48 and info["n_tiles"] == 21 and info["n_eff"] == 15
+    pairs = orc.effect_pairs(sat["path"])
+    assert [(int(f), int(t)) for f, t in zip(info["eff_from"], info["eff_to"])] == pairs
