@@ -1,0 +1,352 @@
+#!/usr/bin/env python3
+"""bench.py -- bootstrap PLS-PM fits/s of the B200 engine (BASELINE.json metric), one JSON line.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c2|c4|c5|c3f] [--impl reference]
+
+A *step* is one bootstrap batch on every rank: `replicates_per_gpu_per_step` independent PLS-PM fits
+to convergence (tol 1e-6, max 100 iterations) on resamples of the HBM-resident observation matrix,
+drawn from the Philox stream of their GLOBAL replicate ids; for N > 1 the step ends with the one
+all-gather of the per-replicate rows.  Weak scaling: per-GPU work is fixed.
+
+  value     fits/s over all ranks, inputs resident in HBM, result rows left on the device
+  e2e       the same step through plspm_bootstrap_host(): X starts in pinned HOST memory, is
+            uploaded inside the timed region, and the rows come back to host memory
+  roofline  the Gram kernel against the HBM roofline in SURVEY.md §8(d)'s algorithmic bytes,
+            (n_iter + 2) * N * P * 8 per fit, divided by the kernel's CUDA-event duration
+  cpu_baseline / --impl reference
+            the oracle port (oracle/plspm_oracle.py, a NumPy restatement of the reference's
+            algorithm) on the box's host cores, one process per core, on a bounded sample
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "plspm-python_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+WORKLOADS = {
+    # name: (N, L, K, mode, scheme, replicates per GPU per step, description)
+    "c3": (100_000, 32, 8, 0, "centroid", 1184,
+           "synthetic N=100k, 32 LVs x 8 MVs (P=256), Mode A, centroid, bootstrap (north-star headline config)"),
+    "c3f": (100_000, 32, 8, 0, "factorial", 1184, "synthetic N=100k, 32 LVs x 8 MVs, Mode A, factorial, bootstrap"),
+    "c4": (100_000, 32, 8, 1, "path", 1184, "synthetic N=100k, 32 LVs x 8 MVs, Mode B, path scheme, bootstrap"),
+    "c5": (1_000_000, 64, 16, 0, "centroid", 16, "synthetic N=1M, 64 LVs x 16 MVs (P=1024), Mode A, centroid, bootstrap"),
+    "c2": (250, 6, 0, 0, "centroid", 1000, "satisfaction 250x27, 6 LVs, Mode A, centroid, 1000 resamples (latency-bound)"),
+}
+HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+
+
+def load_workload(name):
+    from plspm_b200.synth import make_synthetic
+    N, L, K, mode, scheme, reps, desc = WORKLOADS[name]
+    if name == "c2":
+        g = np.load(os.path.join(ROOT, "tests", "golden", "satisfaction.npz"))
+        return dict(X=np.ascontiguousarray(g["X"]), path=g["path"], blocks=[int(v) for v in g["block_sizes"]],
+                    modes=[0] * 6, scheme=scheme, reps=reps, desc=desc, scaled=False)
+    X, path = make_synthetic(N, L, K, seed=0)
+    return dict(X=X, path=path, blocks=[K] * L, modes=[mode] * L, scheme=scheme, reps=reps, desc=desc, scaled=True)
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            for key in ("hbm_gbs", "hbm_gb_s", "hbm_GBs"):
+                if key in d:
+                    return float(d[key]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on all host cores
+# ------------------------------------------------------------------------------------------------
+_CPU = {}
+
+
+def _cpu_one(rep):
+    from oracle import plspm_oracle as orc
+    w = _CPU["w"]
+    idx = orc.philox_indices(0, rep, w["X"].shape[0])
+    t = time.perf_counter()
+    row, iters, status = orc.replicate_row(w["X"], idx, w["blocks"], w["modes"], w["path"], w["scheme"], w["scaled"])
+    return time.perf_counter() - t, int(iters), int(status)
+
+
+def cpu_fits_per_sec(w, n_fits, cores):
+    """n_fits replicates of the same workload, one worker process per core (fork: X is shared)."""
+    import multiprocessing as mp
+    try:
+        from threadpoolctl import threadpool_limits
+        limiter = threadpool_limits(limits=1)
+    except Exception:
+        limiter = None
+    _CPU["w"] = w
+    ctx = mp.get_context("fork")
+    t0 = time.perf_counter()
+    with ctx.Pool(cores) as pool:
+        res = pool.map(_cpu_one, range(n_fits), chunksize=1)
+    dt = time.perf_counter() - t0
+    if limiter is not None:
+        limiter.unregister() if hasattr(limiter, "unregister") else None
+    assert all(r[2] == 0 for r in res)
+    return n_fits / dt, dt, float(np.mean([r[1] for r in res]))
+
+
+def cpu_sample_size(w, cores, budget_s):
+    """Sample size for ~budget_s seconds: time one fit first."""
+    _CPU["w"] = w
+    t1 = _cpu_one(0)[0]
+    per_round = max(t1, 1e-3)
+    rounds = max(1, int(budget_s / per_round))
+    return int(min(rounds * cores, 4096)), t1
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w = load_workload(args.workload)
+    cores = os.cpu_count() or 1
+    n_fits, t1 = cpu_sample_size(w, cores, budget_s=max(3.0, 60.0 / max(args.steps + args.warmup, 1)))
+    for _ in range(args.warmup):
+        cpu_fits_per_sec(w, max(cores, n_fits // 4), cores)
+    t0 = time.perf_counter()
+    total = 0
+    for _ in range(args.steps):
+        fps, dt, _ = cpu_fits_per_sec(w, n_fits, cores)
+        total += n_fits
+    el = time.perf_counter() - t0
+    value = total / el
+    sample = "%d bootstrap fits per step on %d worker processes (1 BLAS thread each), same data/config" % (n_fits, cores)
+    line = {
+        "impl": "reference", "metric": "bootstrap_fits_per_sec", "value": value, "unit": "fits/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.workload, w, n_fits),
+        "cpu_baseline": {"value": value, "unit": "fits/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "fits/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "oracle port of the reference algorithm (the Python reference itself cannot travel to the GPU box: "
+                "statsmodels is not installable offline); single fit %.3f s on one core" % t1,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(name, w, reps):
+    N, P = w["X"].shape
+    return {"workload": w["desc"], "name": name, "N": int(N), "P": int(P), "L": len(w["blocks"]),
+            "mode": "B" if w["modes"][0] else "A", "scheme": w["scheme"], "scaled": bool(w["scaled"]),
+            "tol": 1e-6, "max_iter": 100, "replicates_per_gpu_per_step": int(reps),
+            "l2": "inputs larger than L2: X (%.1f MB fp64) + %.1f MB of per-replicate resample counts + Gram "
+                  "workspace per step are streamed every step (L2 is 126 MB)" % (N * P * 8 / 1e6, reps * N * 4 / 1e6)}
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.file = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.file,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.file.flush()
+        rows = [r.split(",") for r in open(self.file.name).read().strip().splitlines() if r.count(",") >= 6]
+        os.unlink(self.file.name)
+        if not rows:
+            return out
+        sm = [float(r[0]) for r in rows if r[0].strip().replace(".", "").isdigit()]
+        out["sm_mhz"] = float(np.median(sm)) if sm else None
+        out["sm_max_mhz"] = float(rows[0][1]) if rows[0][1].strip().replace(".", "").isdigit() else None
+        try:
+            out["power_w_median"] = float(np.median([float(r[2]) for r in rows]))
+        except Exception:
+            pass
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for k, nme in enumerate(names):
+            if any("Active" in r[3 + k] and "Not" not in r[3 + k] for r in rows):
+                out["reasons"].append(nme)
+        out["samples"] = len(rows)
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    from plspm_b200 import engine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        torch.cuda.set_device(local)
+    engine.set_device(local)
+    dev = torch.device("cuda", local)
+
+    w = load_workload(args.workload)
+    X = w["X"]
+    N, P = X.shape
+    reps = args.replicates or w["reps"]
+    model = engine.Model(w["blocks"], w["modes"], w["path"], w["scaled"])
+    data = engine.Data(model, X)
+    n_out = model.n_out
+    rows_dev = torch.empty((reps, n_out), dtype=torch.float64, device=dev)
+    gathered = torch.empty((world * reps, n_out), dtype=torch.float64, device=dev) if world > 1 else None
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    step_id = [0]
+
+    def step():
+        # global replicate ids: step-major, then rank: never reused, independent of world size
+        begin = (step_id[0] * world + rank) * reps
+        step_id[0] += 1
+        _, status, iters = engine.bootstrap(model, data, w["scheme"], begin, reps, seed=0,
+                                            out_device_ptr=rows_dev.data_ptr())
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, rows_dev)
+            torch.cuda.synchronize()
+        return status, iters
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    engine.profile_reset()
+    sampler = ClockSampler(local) if rank == 0 else None
+    t0 = time.perf_counter()
+    iters_all, bad = [], 0
+    for _ in range(args.steps):
+        status, iters = step()
+        iters_all.append(iters.astype(np.float64))
+        bad += int((status != 0).sum())
+    barrier()
+    elapsed = time.perf_counter() - t0
+    clocks = sampler.stop() if sampler else None
+    prof = engine.profile_get()
+    el_t = torch.tensor([elapsed], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(el_t, op=dist.ReduceOp.MAX)
+    elapsed_max = float(el_t.item())
+    value = world * reps * args.steps / elapsed_max
+    iters_cat = np.concatenate(iters_all)
+
+    # ---- end to end: host X (pinned) -> upload -> bootstrap -> rows back on the host ---------
+    Xp = engine.pinned_empty(X.shape)
+    Xp[...] = X
+    out_host = engine.pinned_empty((reps, n_out))
+    e2e_steps = max(1, min(args.steps, 3))
+    engine.bootstrap_host(model, Xp, w["scheme"], 0, reps, seed=1, out=out_host)  # warm-up
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(e2e_steps):
+        engine.bootstrap_host(model, Xp, w["scheme"], (10_000 + s * world + rank) * reps, reps, seed=0, out=out_host)
+    barrier()
+    e2e_el = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_el, op=dist.ReduceOp.MAX)
+    e2e_value = world * reps * e2e_steps / float(e2e_el.item())
+
+    if rank == 0:
+        gram_ms, gram_n = prof["gram"]
+        alg_bytes = float((iters_cat + 2.0).sum()) * N * P * 8.0           # all fits of the timed region, this rank
+        peak, peak_src = hbm_peak()
+        achieved = alg_bytes / 1e9 / (gram_ms / 1e3) if gram_ms > 0 else 0.0
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "gram_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get(args.workload)
+            except Exception:
+                traffic = None
+        launches = int(sum(v[1] for v in prof.values()))
+        line = {
+            "metric": "bootstrap_fits_per_sec", "value": value, "unit": "fits/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * elapsed_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args.workload, w, reps),
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "fits/s", "h2d_bytes_per_step": int(N * P * 8),
+                    "d2h_bytes_per_step": int(reps * (n_out * 8 + 8)), "steps": e2e_steps},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "kernel": "gram_kernel",
+                         "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes / max(gram_n, 1),
+                         "launch_ms": gram_ms / max(gram_n, 1), "launches": gram_n,
+                         "note": "algorithmic bytes = (n_iter+2)*N*P*8 per fit (SURVEY 8d). The engine reads X once per "
+                                 "wave of replicates instead of (n_iter+2) times per replicate (covariance-domain "
+                                 "solver), so frac may exceed 1; the kernel itself is bound by the fp64 FMA pipe"},
+            "stages_ms_per_step": {k: v[0] / args.steps for k, v in prof.items() if v[1]},
+            "mean_iterations": float(iters_cat.mean()), "failed_replicates": bad,
+        }
+        if world == 1 and not args.no_cpu:
+            cores = os.cpu_count() or 1
+            n_fits, t1 = cpu_sample_size(w, cores, budget_s=args.cpu_seconds)
+            fps, dt, mean_it = cpu_fits_per_sec(w, n_fits, cores)
+            line["cpu_baseline"] = {"value": fps, "unit": "fits/s", "cores": cores, "kind": "port",
+                                    "sample": "%d bootstrap fits of the same workload in %.1f s on %d worker processes "
+                                              "(oracle port, 1 BLAS thread each)" % (n_fits, dt, cores)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=("b200", "reference"))
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--replicates", type=int, default=0, help="replicates per GPU per step (default: per workload)")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

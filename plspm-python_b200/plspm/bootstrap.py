@@ -1,0 +1,99 @@
+"""Bootstrap (reference plspm/bootstrap.py): row-resampling bootstrap of the whole estimation.
+
+Reference: p forked processes x (iterations // p) replicates, each a full host-side fit, results
+pickled through a Queue (bootstrap.py:83-113).  Here the replicates are the batch dimension of the
+CUDA kernels on the HBM-resident data; with torch.distributed initialised (one process per GPU)
+the global replicate ids are split across ranks and one all-gather returns every row to every
+rank.  `num_processes` is kept for signature compatibility and ignored.
+
+Differences that are deliberate: replicates are independent draws keyed
+by (seed, global replicate id) -- the reference's forked workers share one RNG state and repeat
+each other's resamples; failed replicates are dropped like the reference's bare `except: pass`.
+"""
+import numpy as np
+import pandas as pd
+
+from plspm_b200 import distributed as pdist
+
+
+def _create_summary(data: pd.DataFrame, original) -> pd.DataFrame:
+    """original / mean / std.error / perc.025 / perc.975 / t stat. per column (bootstrap.py:24-32)."""
+    sd = data.std(axis=0)
+    summary = pd.DataFrame({"original": pd.Series(original).reindex(data.columns).astype(float),
+                            "mean": data.mean(axis=0), "std.error": sd, "perc.025": data.quantile(0.025, axis=0),
+                            "perc.975": data.quantile(0.975, axis=0)}, index=data.columns)
+    summary["t stat."] = summary["original"] / sd
+    return summary
+
+
+class Bootstrap:
+    """Bootstrap validation results; returned by :meth:`plspm.Plspm.bootstrap`."""
+
+    def __init__(self, config, data: pd.DataFrame, inner_model, outer_model, calculator, iterations: int,
+                 num_processes: int = 1, seed: int = None, indices: np.ndarray = None):
+        session = calculator.session(data)
+        model = session.model
+        rank, world = pdist.rank_world()
+        if seed is None:
+            seed = int(np.random.randint(0, 2 ** 31 - 1))
+        seed = pdist.broadcast_int(seed)
+        begin, count = pdist.shard_range(iterations, rank, world)
+        idx = None if indices is None else np.ascontiguousarray(indices[begin:begin + count], dtype=np.int32)
+        scheme, tol, its = calculator.scheme(), calculator.tolerance(), calculator.iterations()
+        buf = pdist.send_buffer(iterations, model.n_out)
+        if buf is not None:  # NCCL: the solver writes its rows straight into the all-gather send buffer
+            _, status, iters = session.bootstrap(scheme, tol, its, begin, count, seed, idx,
+                                                 out_device_ptr=buf.data_ptr())
+            rows = None
+        else:
+            rows, status, iters = session.bootstrap(scheme, tol, its, begin, count, seed, idx)
+        rows, status, iters = pdist.allgather_rows(rows, status, iters, iterations, model.n_out, device_buffer=buf)
+        self._status, self._iterations, self._seed = status, iters, seed
+        rows = rows[status == 0]  # bootstrap.py:67-68
+        w, r2, total, direct, load = model.split_row(rows)
+        lvs, mvs = session.lvs, session.mvs
+        cols = list(data.columns)
+        weights = pd.DataFrame(w, columns=mvs).loc[:, cols]
+        loadings = pd.DataFrame(load, columns=mvs).loc[:, cols]
+        r_squared = pd.DataFrame(r2, columns=lvs)
+        names = [lvs[f] + " -> " + lvs[t] for f, t in zip(model.effects_from, model.effects_to)]
+        eff_index = list(inner_model.effects().index)
+        total_effects = pd.DataFrame(total, columns=names).reindex(columns=eff_index)
+        paths = pd.DataFrame(direct, columns=names).reindex(columns=eff_index)
+        om = outer_model.model()
+        self._weights = _create_summary(weights, om.loc[:, "weight"])
+        self._r_squared = _create_summary(r_squared, inner_model.r_squared()).loc[inner_model.endogenous(), :]
+        self._total_effects = _create_summary(total_effects, inner_model.effects().loc[:, "total"])
+        self._paths = _create_summary(paths, inner_model.effects().loc[:, "direct"])
+        self._loading = _create_summary(loadings, om.loc[:, "loading"])
+        self._samples = dict(weights=weights, r_squared=r_squared, total_effects=total_effects, paths=paths,
+                             loadings=loadings)
+
+    def weights(self) -> pd.DataFrame:
+        """Outer weights calculated from bootstrap validation."""
+        return self._weights
+
+    def r_squared(self) -> pd.DataFrame:
+        """R squared for latent variables calculated from bootstrap validation."""
+        return self._r_squared
+
+    def total_effects(self) -> pd.DataFrame:
+        """Total effects for paths calculated from bootstrap validation."""
+        return self._total_effects
+
+    def paths(self) -> pd.DataFrame:
+        """Direct effects for paths calculated from bootstrap validation."""
+        return self._paths[self._paths["mean"] != 0]
+
+    def loading(self) -> pd.DataFrame:
+        """Loadings of manifest variables calculated from bootstrap validation."""
+        return self._loading
+
+    # extras (not in the reference)
+    def samples(self) -> dict:
+        """Per-replicate values behind the summaries (DataFrames keyed weights / r_squared / ...)."""
+        return self._samples
+
+    def replicate_status(self):
+        """(status, iterations) per global replicate id; status 0 = converged."""
+        return self._status, self._iterations

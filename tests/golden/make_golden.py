@@ -48,7 +48,7 @@ def _stage_reference():
 
 
 _stage_reference()
-sys.path.insert(0, os.path.join(ROOT, "plspm-python_b200"))
+sys.path.append(os.path.join(ROOT, "plspm-python_b200"))  # after the staged reference: only plspm_b200.synth is used
 
 import plspm.config as c  # noqa: E402  (the REFERENCE package, from the staged copy)
 import plspm.weights as ref_weights  # noqa: E402
@@ -203,6 +203,10 @@ def main():
     for col in ("r_squared", "block_communality", "mean_redundancy"):
         store["R/modeb/inner_summary/" + col] = isb[col].values.astype(np.float64)
     store["R/gof"] = np.float64(0.609741624338411)  # test_regression_metric.py:80
+    uni = pd.read_csv(os.path.join(tdata, "satisfaction_unidim.csv"), index_col=0).loc[lvs]
+    for col in ("mvs", "cronbach_alpha", "dillon_goldstein_rho", "eig_1st", "eig_2nd"):
+        store["R/unidim/" + col] = uni[col].values.astype(np.float64)
+    store["index"] = np.array([str(v) for v in sat.index])
     for tag in ("weights", "loadings", "paths", "rsquared", "total_effects"):
         bt = pd.read_csv(os.path.join(tdata, "satisfaction_boot_%s.csv" % tag), index_col=0)
         store["R/boot/%s/index" % tag] = np.array(list(bt.index))

@@ -1,0 +1,162 @@
+"""The drop-in host API (plspm.Plspm / Config / Scheme / Mode / bootstrap) on the GPU, written the way
+the reference's own tests use it (reference tests/test_regression_metric.py, test_regression_bootstrap.py),
+against the R golden values and the reference outputs in tests/golden/."""
+import numpy as np
+import pandas as pd
+import pytest
+
+import plspm.config as c
+from plspm.mode import Mode
+from plspm.plspm import Plspm
+from plspm.scheme import Scheme
+
+pytestmark = pytest.mark.gpu
+
+
+def satisfaction_frame(sat):
+    df = pd.DataFrame(sat["X"], columns=[str(v) for v in sat["mvs"]], index=[str(v) for v in sat["index"]])
+    df["gender"] = "x"  # a column the model does not use (dropped by Config.filter)
+    return df
+
+
+def satisfaction_path_matrix():
+    s = c.Structure()
+    s.add_path(["IMAG"], ["EXPE", "SAT", "LOY"])
+    s.add_path(["EXPE"], ["QUAL", "VAL", "SAT"])
+    s.add_path(["QUAL"], ["VAL", "SAT"])
+    s.add_path(["VAL"], ["SAT"])
+    s.add_path(["SAT"], ["LOY"])
+    return s.path()
+
+
+def make_config(df, mode=Mode.A, scaled=False, order=("IMAG", "EXPE", "VAL", "QUAL", "SAT", "LOY")):
+    config = c.Config(satisfaction_path_matrix(), scaled=scaled)
+    for lv in order:
+        config.add_lv_with_columns_named(lv, mode, df, lv.lower())
+    return config
+
+
+def test_plspm_satisfaction(sat):
+    df = satisfaction_frame(sat)
+    lvs, mvs = [str(v) for v in sat["lvs"]], [str(v) for v in sat["mvs"]]
+    calc = Plspm(df, make_config(df))
+    assert calc.iterations() == 4
+    assert list(calc.scores().index) == list(df.index)
+    np.testing.assert_allclose(calc.scores().loc[:, lvs].values, sat["R/scores"], rtol=1e-6, atol=1e-9)
+    im = calc.inner_model()
+    rows = im[im["to"] == "SAT"].set_index("from").loc[[str(v) for v in sat["R/inner_model_SAT_from"]]]
+    np.testing.assert_allclose(rows[["estimate", "std error", "t", "p>|t|"]].values, sat["R/inner_model_SAT"], rtol=1e-6)
+    om = calc.outer_model()
+    assert list(om.columns) == ["weight", "loading", "communality", "redundancy"]
+    for col in om.columns:
+        np.testing.assert_allclose(om.loc[mvs, col].values, sat["R/centroid/" + col], rtol=1e-6, atol=1e-12)
+    np.testing.assert_allclose(calc.crossloadings().loc[mvs, lvs].values, sat["R/crossloadings"], rtol=1e-6, atol=1e-9)
+    isum = calc.inner_summary()
+    for col in ("r_squared", "block_communality", "mean_redundancy", "ave"):
+        np.testing.assert_allclose(isum.loc[lvs, col].values, sat["R/inner_summary/" + col], rtol=1e-6, atol=1e-12)
+    assert list(isum.loc[lvs, "type"]) == ["Exogenous"] + ["Endogenous"] * 5
+    eff = calc.effects()
+    assert list(eff["from"]) == [str(v) for v in sat["R/effects_from"]]
+    for col in ("direct", "indirect", "total"):
+        np.testing.assert_allclose(eff[col].values, sat["R/effects_" + col], rtol=1e-6, atol=1e-11)
+    np.testing.assert_allclose(calc.path_coefficients().loc[lvs, lvs].values,
+                               sat["ref/centroid/A/unscaled/path_coefficients"], rtol=1e-6, atol=1e-11)
+    assert abs(calc.goodness_of_fit() - float(sat["R/gof"])) < 1e-7
+    uni = calc.unidimensionality()
+    for col in ("cronbach_alpha", "dillon_goldstein_rho", "eig_1st", "eig_2nd"):
+        np.testing.assert_allclose(uni.loc[lvs, col].values.astype(float), sat["R/unidim/" + col], rtol=1e-6)
+    for scheme, tag in ((Scheme.PATH, "path"), (Scheme.FACTORIAL, "factorial")):
+        other = Plspm(df, make_config(df), scheme).outer_model()
+        for col in ("weight", "loading", "communality", "redundancy"):
+            np.testing.assert_allclose(other.loc[mvs, col].values, sat["R/%s/%s" % (tag, col)], rtol=1e-6, atol=1e-12)
+
+
+def test_plspm_mode_b_and_scaled(sat):
+    df = satisfaction_frame(sat)
+    lvs, mvs = [str(v) for v in sat["lvs"]], [str(v) for v in sat["mvs"]]
+    calc = Plspm(df, make_config(df, Mode.B), Scheme.CENTROID)
+    isum = calc.inner_summary()
+    for col in ("r_squared", "block_communality", "mean_redundancy"):
+        np.testing.assert_allclose(isum.loc[lvs, col].values, sat["R/modeb/inner_summary/" + col], rtol=1e-6, atol=1e-11)
+    calc = Plspm(df, make_config(df, Mode.B, scaled=True), Scheme.PATH)
+    tag = "ref/path/B/scaled/"
+    assert calc.iterations() == int(sat[tag + "iterations"])
+    np.testing.assert_allclose(calc.outer_model().loc[mvs, "weight"].values, sat[tag + "weights"], rtol=1e-6)
+    np.testing.assert_allclose(calc.scores().loc[:, lvs].values, sat[tag + "scores"], rtol=1e-6, atol=1e-8)
+
+
+def test_single_item_constructs(sat):
+    df = satisfaction_frame(sat)
+    config = c.Config(satisfaction_path_matrix())
+    for lv in ("QUAL", "VAL", "SAT", "LOY", "IMAG", "EXPE"):
+        config.add_lv(lv, Mode.A, c.MV(lv.lower() + "1"))
+    calc = Plspm(df, config, Scheme.CENTROID)
+    with pytest.raises(ValueError):
+        calc.goodness_of_fit()
+    np.testing.assert_allclose(np.abs(calc.outer_model()["loading"].values), 1.0, rtol=1e-9)
+
+
+def test_bootstrap_metric_like_the_reference_test(sat):
+    """Statistical agreement with the R bootstrap summaries (reference test_regression_bootstrap.py:17-48:
+    same loose tolerances, because the reference's resampling is unseeded)."""
+    df = satisfaction_frame(sat)
+    config = make_config(df, order=("IMAG", "EXPE", "QUAL", "VAL", "SAT", "LOY"))
+    calc = Plspm(df, config, bootstrap=True, bootstrap_iterations=1000, processes=4, bootstrap_seed=7)
+    boot = calc.bootstrap()
+    drop = ["t stat."]
+    for getter, tag, atol in ((boot.weights, "weights", 0.05), (boot.r_squared, "rsquared", 0.1),
+                              (boot.total_effects, "total_effects", 0.1), (boot.paths, "paths", 0.1),
+                              (boot.loading, "loadings", 0.15)):
+        got = getter().drop(columns=drop)
+        exp = pd.DataFrame(sat["R/boot/%s/values" % tag], index=[str(v) for v in sat["R/boot/%s/index" % tag]],
+                           columns=[str(v) for v in sat["R/boot/%s/columns" % tag]])
+        assert sorted(got.index) == sorted(exp.index), tag
+        np.testing.assert_allclose(got.loc[exp.index, sorted(got.columns)].values, exp.loc[:, sorted(exp.columns)].values,
+                                   atol=atol, err_msg=tag)
+    status, iters = boot.replicate_status()
+    assert (status == 0).all() and len(status) == 1000
+
+
+def test_bootstrap_injected_indices_reproduce_reference_replicates(sat):
+    df = satisfaction_frame(sat)
+    idx = np.random.default_rng(1234).integers(0, 250, (1000, 250), dtype=np.int32)[:48]
+    calc = Plspm(df, make_config(df), bootstrap=True, bootstrap_iterations=48, processes=1, bootstrap_indices=idx)
+    w = calc.bootstrap().samples()["weights"]
+    mvs = [str(v) for v in sat["mvs"]]
+    np.testing.assert_allclose(w.loc[:, mvs].values, sat["boot/centroid/A/unscaled/weights"], rtol=1e-6)
+    summ = calc.bootstrap().weights()
+    np.testing.assert_allclose(summ.loc[mvs, "mean"].values, sat["boot/centroid/A/unscaled/weights"].mean(axis=0),
+                               rtol=1e-6)
+    np.testing.assert_allclose(summ.loc[mvs, "original"].values, sat["R/centroid/weight"], rtol=1e-6)
+
+
+def test_argument_rules_and_errors(sat):
+    df = satisfaction_frame(sat)
+    with pytest.raises(AssertionError):
+        Plspm(df, make_config(df), tolerance=0)
+    with pytest.raises(AssertionError):
+        Plspm(df, make_config(df), bootstrap_iterations=100, processes=3)
+    with pytest.raises(Exception, match="To perform bootstrap validation"):
+        Plspm(df, make_config(df)).bootstrap()
+    with pytest.raises(Exception, match="at least 10 observations"):
+        Plspm(df.iloc[:9], make_config(df), bootstrap=True)
+    with pytest.raises(Exception, match="Could not converge after 101 iterations"):
+        Plspm(df, make_config(df, Mode.B, scaled=True), tolerance=1e-300)
+    from plspm.scale import Scale
+    nonmetric = c.Config(satisfaction_path_matrix(), default_scale=Scale.NUM)
+    for lv in ("IMAG", "EXPE", "QUAL", "VAL", "SAT", "LOY"):
+        nonmetric.add_lv_with_columns_named(lv, Mode.A, df, lv.lower())
+    with pytest.raises(NotImplementedError):
+        Plspm(df, nonmetric)
+
+
+def test_missing_values_single_fit_is_mean_imputed(sat):
+    from oracle import plspm_oracle as orc
+    df = satisfaction_frame(sat)
+    df.loc[df.index[3], "imag2"] = np.nan
+    df.loc[df.index[10], "sat1"] = np.nan
+    calc = Plspm(df, make_config(df))
+    X = df[[str(v) for v in sat["mvs"]]].values
+    ref = orc.fit(X, sat["block_sizes"], [0] * 6, sat["path"], "centroid", False)
+    np.testing.assert_allclose(calc.outer_model().loc[[str(v) for v in sat["mvs"]], "weight"].values, ref["weights"],
+                               rtol=1e-6)
