@@ -20,6 +20,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -47,7 +48,7 @@ static int fail(int code, const std::string& msg) {
                   std::string(#expr) + ": " + cudaGetErrorString(e_));                             \
   } while (0)
 
-enum { ST_COUNTS = 0, ST_GRAM = 1, ST_REDUCE = 2, ST_SOLVE = 3, ST_SCORES = 4, ST_UPLOAD = 5, ST_N = 8 };
+enum { ST_COUNTS = 0, ST_GRAM = 1, ST_REDUCE = 2, ST_SOLVE = 3, ST_SCORES = 4, ST_UPLOAD = 5, ST_COLSUM = 6, ST_N = 8 };
 struct Profile {
   std::mutex mu;
   double ms[ST_N] = {0};
@@ -253,23 +254,34 @@ __global__ void relayout_kernel(const double* __restrict__ X, int64_t N, int64_t
 // ------------------------------------------------------------------------------------------------
 constexpr int GRAM_WARPS = 8;    // consumer warps per CTA, each = one (replicate, tile group) item
 constexpr int GRAM_THREADS = GRAM_WARPS * 32;  // 2 warps per SM sub-partition: up to 255 registers per thread
-constexpr int GRAM_MAX_STAGES = 4;
-constexpr int GRAM_CS = 8;       // column-sum accumulators per lane
+constexpr int GRAM_MAX_STAGES = 8;
 
 struct GramParams {
   const double* X;          // [N][Ppad]
   const uint32_t* counts;   // [nrep][N] or null (every row once)
   int64_t N;
   int Ppad, n_tiles, n_tg;
-  const int *tile_sa, *tile_sb;
+  const int *tile_sa, *tile_sb, *lane_tile;
   int64_t n_items;          // nrep * n_tg
   int n_chunks;
   int64_t chunk_rows;       // multiple of RT
   int RT, stages;
-  int cs_cols;              // columns per tile group for the column sums (<= 32*GRAM_CS)
   double* G;                // [nrep][n_chunks][n_tiles*64]
-  double* colsum;           // [nrep][n_chunks][Ppad]
 };
+
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(done)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return done != 0;
+}
 
 __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const GramParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -297,86 +309,151 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const GramParams 
 
   // ---- producer duty: lane 0 of warp 0 feeds the ring through the TMA engine ------------------
   // (a ninth warp would put three warps on one SM sub-partition and cap every thread at 168
-  // registers; the 8x8 fp64 accumulator tile alone needs 128)
-  auto issue_tile = [&](int tn) {
-    const int s = tn % p.stages;
-    const uint32_t use = (uint32_t)(tn / p.stages);
-    if (use > 0) mbar_wait(&empty_bar[s], (use - 1) & 1);
-    const int64_t row = r0 + (int64_t)tn * p.RT;
-    const uint32_t rows = (uint32_t)min((int64_t)p.RT, r1 - row);
-    const uint32_t bytes = rows * (uint32_t)p.Ppad * 8u;
-    mbar_arrive_expect_tx(&full_bar[s], bytes);
-    bulk_g2s(tiles + (size_t)s * stage_doubles, p.X + row * p.Ppad, bytes, &full_bar[s]);
-  };
+  // registers; the 8x8 fp64 accumulator tile alone needs 128).  Tiles are issued as early as a
+  // stage is free (non-blocking probe), and at the latest -- blocking -- right before warp 0
+  // itself needs them, so the other warps never wait on warp 0's own arithmetic.
   const bool producer = (threadIdx.x == 0);
-  if (producer)
-    for (int tn = 0; tn < p.stages - 1 && tn < n_rt; ++tn) issue_tile(tn);
+  int tn = 0, tn_stage = 0;      // next row tile to issue and its ring stage (producer only)
+  uint32_t tn_use = 0;           // how many times that stage has been filled before
+  auto feed = [&](int t_cur) {   // t_cur: the tile warp 0 is about to consume / is consuming
+    while (tn < n_rt && tn < t_cur + p.stages) {
+      if (tn_use > 0) {
+        if (tn <= t_cur) mbar_wait(&empty_bar[tn_stage], (tn_use - 1) & 1);
+        else if (!mbar_test(&empty_bar[tn_stage], (tn_use - 1) & 1)) break;
+      }
+      const int64_t row = r0 + (int64_t)tn * p.RT;
+      const uint32_t rows = (uint32_t)min((int64_t)p.RT, r1 - row);
+      const uint32_t bytes = rows * (uint32_t)p.Ppad * 8u;
+      mbar_arrive_expect_tx(&full_bar[tn_stage], bytes);
+      bulk_g2s(tiles + (size_t)tn_stage * stage_doubles, p.X + row * p.Ppad, bytes, &full_bar[tn_stage]);
+      ++tn;
+      if (++tn_stage == p.stages) { tn_stage = 0; ++tn_use; }
+    }
+  };
+  if (producer) feed(0);
   if (warp >= n_active) return;
 
   // ---- consumer warp: one (replicate, tile group); lane = one 8x8 tile ------------------------
   const int64_t item = item0 + warp;
   const int64_t rep = item / p.n_tg;
   const int tg = (int)(item - rep * p.n_tg);
-  const int tile = tg * 32 + lane;
-  const bool tile_ok = tile < p.n_tiles;
+  const int tile = p.lane_tile[tg * 32 + lane];
+  const bool tile_ok = tile >= 0;
   const int sa = tile_ok ? p.tile_sa[tile] : 0, sb = tile_ok ? p.tile_sb[tile] : 0;
   // 16-byte chunks of a slot are read in a lane-dependent rotated order so that the 32 LDS.128 of
   // a warp spread over all bank quads (slot stride 64 B would otherwise be a 16-way conflict)
-  const int rot_a = (sa >> 1) & 3, rot_b = (sb >> 1) & 3;
+  // (the row operand xa is a broadcast within a packed tile group and needs no rotation)
+  const int rot_a = 0, rot_b = (sb >> 1) & 3;
   int off_a[4], off_b[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     off_a[k] = sa * SLOT + 2 * ((k + rot_a) & 3);
     off_b[k] = sb * SLOT + 2 * ((k + rot_b) & 3);
   }
-  const int cs0 = tg * p.cs_cols, cs1 = min(cs0 + p.cs_cols, p.Ppad);
-  const int ncs = (cs1 - cs0 + 31) / 32;  // warp-uniform
-
   double acc[8][8];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
-  double cs[GRAM_CS];
-#pragma unroll
-  for (int k = 0; k < GRAM_CS; ++k) cs[k] = 0.0;
 
   const uint32_t* cnt_row = p.counts ? p.counts + rep * p.N : nullptr;
+  auto load_counts = [&](int t_load) -> uint32_t {
+    const int64_t row = r0 + (int64_t)t_load * p.RT;
+    const int rows = (int)min((int64_t)p.RT, r1 - row);
+    if (lane >= rows) return 0u;
+    return cnt_row ? __ldg(cnt_row + row + lane) : 1u;
+  };
+  // shared-memory byte addresses of the lane's 2 x 4 16-byte operand chunks within a row
+  uint32_t boff_a[4], boff_b[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    boff_a[k] = (uint32_t)off_a[k] * 8u;
+    boff_b[k] = (uint32_t)off_b[k] * 8u;
+  }
+  auto lds128 = [](uint32_t addr, double& x, double& y) {
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "r"(addr));
+  };
+  auto load_row = [&](uint32_t row_addr, double (&xa)[8], double (&xb)[8]) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      lds128(row_addr + boff_a[k], xa[2 * k], xa[2 * k + 1]);
+      lds128(row_addr + boff_b[k], xb[2 * k], xb[2 * k + 1]);
+    }
+  };
+  // The scaling and the 64 FMAs of a row are emitted as volatile asm so that the compiler keeps
+  // them AFTER the (volatile) shared-memory loads of the NEXT row in program order: without this
+  // the loads get sunk below the FMA block to save registers and the software pipeline is lost
+  // (measured: 6.5 % of all issue slots stalled on the first DMUL of every row).
+  auto accumulate = [&](double (&xa)[8], double (&xb)[8], double c) {
+    asm volatile(
+        "mul.f64 %0, %0, %8;\n\tmul.f64 %1, %1, %8;\n\tmul.f64 %2, %2, %8;\n\tmul.f64 %3, %3, %8;\n\t"
+        "mul.f64 %4, %4, %8;\n\tmul.f64 %5, %5, %8;\n\tmul.f64 %6, %6, %8;\n\tmul.f64 %7, %7, %8;"
+        : "+d"(xb[0]), "+d"(xb[1]), "+d"(xb[2]), "+d"(xb[3]), "+d"(xb[4]), "+d"(xb[5]), "+d"(xb[6]), "+d"(xb[7])
+        : "d"(c));
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      asm volatile(
+          "fma.rn.f64 %0, %8, %9, %0;\n\tfma.rn.f64 %1, %8, %10, %1;\n\tfma.rn.f64 %2, %8, %11, %2;\n\t"
+          "fma.rn.f64 %3, %8, %12, %3;\n\tfma.rn.f64 %4, %8, %13, %4;\n\tfma.rn.f64 %5, %8, %14, %5;\n\t"
+          "fma.rn.f64 %6, %8, %15, %6;\n\tfma.rn.f64 %7, %8, %16, %7;"
+          : "+d"(acc[i][0]), "+d"(acc[i][1]), "+d"(acc[i][2]), "+d"(acc[i][3]), "+d"(acc[i][4]), "+d"(acc[i][5]),
+            "+d"(acc[i][6]), "+d"(acc[i][7])
+          : "d"(xa[i]), "d"(xb[0]), "d"(xb[1]), "d"(xb[2]), "d"(xb[3]), "d"(xb[4]), "d"(xb[5]), "d"(xb[6]),
+            "d"(xb[7]));
+  };
+  // per-warp list of the tile's non-zero rows: {row byte offset in the stage, multiplicity as fp64},
+  // built once per tile by all lanes, so that the row loop is a plain counted loop
+  __shared__ __align__(16) double2 row_list[GRAM_WARPS][36];  // 32 rows + 4 zero-multiplicity pads
+  double2* my_list = row_list[warp];
+  const uint32_t list_addr = smem_u32(my_list);
+  const uint32_t tiles_addr = smem_u32(tiles);
+  const uint32_t row_bytes = (uint32_t)p.Ppad * 8u;
+  auto load_entry = [&](int k, uint32_t& off, double& c) {
+    double o;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(o), "=d"(c) : "r"(list_addr + 16u * (uint32_t)k));
+    off = (uint32_t)__double_as_longlong(o);
+  };
+  uint32_t cnt_next = load_counts(0);
 
   for (int t = 0; t < n_rt; ++t) {
-    if (producer && t + p.stages - 1 < n_rt) issue_tile(t + p.stages - 1);  // refills the stage of tile t-1
+    if (producer) feed(t);
     const int s = t % p.stages;
     const uint32_t use = (uint32_t)(t / p.stages);
-    const int64_t row = r0 + (int64_t)t * p.RT;
-    const int rows = (int)min((int64_t)p.RT, r1 - row);
-    uint32_t cnt = 0;
-    if (lane < rows) cnt = cnt_row ? __ldg(cnt_row + row + lane) : 1u;
-    uint32_t mask = __ballot_sync(0xffffffffu, cnt != 0);
+    const uint32_t cnt = cnt_next;
+    if (t + 1 < n_rt) cnt_next = load_counts(t + 1);  // prefetch: hides the global-load latency
+    const uint32_t mask = __ballot_sync(0xffffffffu, cnt != 0);
+    const int n_nz = __popc(mask);
+    if (cnt != 0) {
+      const int pos = __popc(mask & ((1u << lane) - 1u));
+      my_list[pos] = make_double2(__longlong_as_double((long long)((uint32_t)lane * row_bytes)), (double)cnt);
+    }
+    // pads: multiplicity 0 on row 0 of the stage, so the pipelined loop below needs no branches
+    if (lane < 4) my_list[n_nz + lane] = make_double2(__longlong_as_double(0ll), 0.0);
+    __syncwarp();
     mbar_wait(&full_bar[s], use & 1);
-    const double* base = tiles + (size_t)s * stage_doubles;
-    while (mask) {
-      const int r = __ffs(mask) - 1;
-      mask &= mask - 1;
-      const double c = (double)__shfl_sync(0xffffffffu, cnt, r);
-      const double* xr = base + (size_t)r * p.Ppad;
-      double xa[8], xb[8];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const double2 va = *reinterpret_cast<const double2*>(xr + off_a[k]);
-        const double2 vb = *reinterpret_cast<const double2*>(xr + off_b[k]);
-        xa[2 * k] = va.x; xa[2 * k + 1] = va.y;
-        xb[2 * k] = vb.x * c; xb[2 * k + 1] = vb.y * c;
+    const uint32_t base = tiles_addr + (uint32_t)s * (uint32_t)(stage_doubles * 8);
+    if (n_nz > 0) {
+      // Software pipeline over the non-zero rows, two rows per trip, straight-line body: the
+      // operands of row k+1 are in flight (LDS) while the 64 FMAs of row k issue, and the list
+      // entries of rows k+2 / k+3 are already in registers.  An odd row count runs one padded row
+      // with multiplicity 0 (adds exact zeros; ~2.5 % extra FMAs, no branch in the body).
+      double xa0[8], xb0[8], xa1[8], xb1[8], c0, c1, ce0, ce1;
+      uint32_t oe0, oe1;
+      load_entry(0, oe0, ce0);
+      load_entry(1, oe1, ce1);
+      load_row(base + oe0, xa0, xb0);
+      c0 = ce0;
+      for (int k = 0; k < n_nz; k += 2) {
+        load_row(base + oe1, xa1, xb1);
+        c1 = ce1;
+        load_entry(k + 2, oe0, ce0);
+        accumulate(xa0, xb0, c0);
+        load_row(base + oe0, xa0, xb0);
+        c0 = ce0;
+        load_entry(k + 3, oe1, ce1);
+        accumulate(xa1, xb1, c1);
+        if (producer && (k & 6) == 6) feed(t);  // opportunistic refill while the tile is being consumed
       }
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = fma(xa[i], xb[j], acc[i][j]);
-#pragma unroll
-      for (int k = 0; k < GRAM_CS; ++k)
-        if (k < ncs) {
-          const int col = cs0 + lane + 32 * k;
-          if (col < cs1) cs[k] = fma(c, xr[col], cs[k]);
-        }
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty_bar[s]);
@@ -396,13 +473,58 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const GramParams 
       }
     }
   }
-  double* co = p.colsum + slab * p.Ppad;
-#pragma unroll
-  for (int k = 0; k < GRAM_CS; ++k)
-    if (k < ncs) {
-      const int col = cs0 + lane + 32 * k;
-      if (col < cs1) co[col] = cs[k];
+}
+
+// Weighted column sums colsum[b][p] = sum_i c_bi x~_ip  (a skinny fp64 GEMM, counts x X~).
+// CTA = 32 replicates x 64 columns over one row chunk; thread (i, j) of a 16 x 16 grid owns
+// replicates {2i, 2i+1} x columns {4j..4j+3}.  ~1 % of the Gram kernel's FMAs.
+constexpr int CS_REPS = 32, CS_COLS = 64, CS_ROWS = 32;
+__global__ void __launch_bounds__(256) colsum_kernel(const double* __restrict__ X, const uint32_t* __restrict__ counts,
+                                                     int64_t N, int Ppad, int64_t nrep, int n_chunks,
+                                                     int64_t chunk_rows, double* __restrict__ out) {
+  __shared__ __align__(16) double xs[CS_ROWS][CS_COLS];
+  __shared__ __align__(16) double cw[CS_ROWS][CS_REPS];
+  const int col0 = blockIdx.x * CS_COLS;
+  const int64_t rep0 = (int64_t)blockIdx.y * CS_REPS;
+  const int chunk = blockIdx.z;
+  const int64_t r0 = (int64_t)chunk * chunk_rows, r1 = min(r0 + chunk_rows, N);
+  const int ti = threadIdx.x >> 4, tj = threadIdx.x & 15;
+  double acc[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+  for (int64_t row = r0; row < r1; row += CS_ROWS) {
+    const int rows = (int)min((int64_t)CS_ROWS, r1 - row);
+    for (int e = threadIdx.x; e < CS_ROWS * CS_COLS; e += 256) {
+      const int r = e / CS_COLS, c = e - r * CS_COLS;
+      xs[r][c] = (r < rows && col0 + c < Ppad) ? X[(row + r) * Ppad + col0 + c] : 0.0;
     }
+    for (int e = threadIdx.x; e < CS_ROWS * CS_REPS; e += 256) {
+      const int b = e / CS_ROWS, r = e - b * CS_ROWS;  // consecutive threads: consecutive rows of one replicate
+      double v = 0.0;
+      if (r < rows && rep0 + b < nrep) v = counts ? (double)counts[(rep0 + b) * N + row + r] : 1.0;
+      cw[r][b] = v;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int r = 0; r < CS_ROWS; ++r) {
+      const double2 c2 = *reinterpret_cast<const double2*>(&cw[r][2 * ti]);
+      const double2 x01 = *reinterpret_cast<const double2*>(&xs[r][4 * tj]);
+      const double2 x23 = *reinterpret_cast<const double2*>(&xs[r][4 * tj + 2]);
+      acc[0][0] = fma(c2.x, x01.x, acc[0][0]); acc[0][1] = fma(c2.x, x01.y, acc[0][1]);
+      acc[0][2] = fma(c2.x, x23.x, acc[0][2]); acc[0][3] = fma(c2.x, x23.y, acc[0][3]);
+      acc[1][0] = fma(c2.y, x01.x, acc[1][0]); acc[1][1] = fma(c2.y, x01.y, acc[1][1]);
+      acc[1][2] = fma(c2.y, x23.x, acc[1][2]); acc[1][3] = fma(c2.y, x23.y, acc[1][3]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int64_t b = rep0 + 2 * ti + u;
+    if (b >= nrep) continue;
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const int c = col0 + 4 * tj + v;
+      if (c < Ppad) out[(b * n_chunks + chunk) * Ppad + c] = acc[u][v];
+    }
+  }
 }
 
 // sum of the per-chunk partials in chunk order (deterministic)
@@ -525,6 +647,7 @@ int plspm_model_create(int32_t L, const int32_t* block_sizes, const int8_t* mode
   rc |= upload_vec(m, h.tile_sa, &v.tile_sa);
   rc |= upload_vec(m, h.tile_sb, &v.tile_sb);
   rc |= upload_vec(m, h.tile_of, &v.tile_of);
+  rc |= upload_vec(m, h.lane_tile, &v.lane_tile);
   rc |= upload_vec(m, h.pair_l, &v.pair_l);
   rc |= upload_vec(m, h.pair_j, &v.pair_j);
   rc |= upload_vec(m, h.pair_voff, &v.pair_voff);
@@ -656,15 +779,32 @@ struct GramPlan {
   int RT, stages, n_chunks;
   int64_t chunk_rows, n_groups;
   size_t smem;
+  int cs_chunks;          // row chunks of the column-sum kernel
+  int64_t cs_chunk_rows;
 };
+static void plan_colsum(const plspm_data* d, int64_t nb, int max_chunks, GramPlan& g) {
+  const HostModel& h = d->model->h;
+  const int64_t blocks_xy = (int64_t)((h.Ppad + CS_COLS - 1) / CS_COLS) * ((nb + CS_REPS - 1) / CS_REPS);
+  const int64_t want = (int64_t)d->sm_count * 8;
+  int64_t chunks = std::max<int64_t>(1, (want + blocks_xy - 1) / blocks_xy);
+  chunks = std::min<int64_t>(chunks, std::max<int64_t>(1, d->N / (CS_ROWS * 8)));
+  chunks = std::min<int64_t>(chunks, 65535);
+  if (max_chunks > 0) chunks = std::min<int64_t>(chunks, max_chunks);
+  int64_t rows = ((d->N + chunks - 1) / chunks + CS_ROWS - 1) / CS_ROWS * CS_ROWS;
+  g.cs_chunk_rows = rows;
+  g.cs_chunks = (int)((d->N + rows - 1) / rows);
+}
 static int plan_gram(const plspm_data* d, int64_t nb, GramPlan& g) {
   const HostModel& h = d->model->h;
   const size_t row_bytes = (size_t)h.Ppad * 8;
-  int RT = 32;
-  while (RT > 1 && RT * row_bytes > 48 * 1024) RT >>= 1;
+  // ring geometry: stages of <= 64 KB / 32 rows (env PLSPM_GRAM_STAGE_KB) and as many as fit (<= 8);
+  // measured on c3: 32-row stages beat 16-row stages by 10 % (per-tile handshakes amortise)
+  static const int stage_kb = getenv("PLSPM_GRAM_STAGE_KB") ? atoi(getenv("PLSPM_GRAM_STAGE_KB")) : 64;
+  static const int max_stages = getenv("PLSPM_GRAM_STAGES") ? atoi(getenv("PLSPM_GRAM_STAGES")) : GRAM_MAX_STAGES;
+  int RT = (int)std::min<size_t>(32, std::max<size_t>(1, (size_t)stage_kb * 1024 / row_bytes));
   const size_t stage_bytes = RT * row_bytes;
-  const size_t budget = (size_t)d->max_smem - 1024;
-  int stages = (int)std::min<size_t>(GRAM_MAX_STAGES, budget / stage_bytes);
+  const size_t budget = (size_t)d->max_smem - 8 * 1024;  // static shared memory (barriers, row lists) + slack
+  int stages = (int)std::min<size_t>(std::min(max_stages, GRAM_MAX_STAGES), budget / stage_bytes);
   if (stages < 2) return fail(PLSPM_ERR_UNSUPPORTED, "manifest rows too wide for the shared-memory ring");
   const int64_t n_tiles_rt = (d->N + RT - 1) / RT;
   stages = (int)std::min<int64_t>(stages, std::max<int64_t>(2, n_tiles_rt));
@@ -679,6 +819,7 @@ static int plan_gram(const plspm_data* d, int64_t nb, GramPlan& g) {
   n_chunks = (d->N + chunk_rows - 1) / chunk_rows;
   g.RT = RT; g.stages = stages; g.n_chunks = (int)n_chunks; g.chunk_rows = chunk_rows; g.n_groups = n_groups;
   g.smem = (size_t)stages * stage_bytes;
+  plan_colsum(d, nb, 0, g);
   return 0;
 }
 
@@ -698,12 +839,9 @@ static int run_batch(plspm_data* d, int64_t nb, const uint32_t* counts_dev, doub
   cudaStream_t st = d->stream;
   GramParams p;
   p.X = d->X; p.counts = counts_dev; p.N = d->N; p.Ppad = h.Ppad; p.n_tiles = h.n_tiles; p.n_tg = h.n_tg;
-  p.tile_sa = m->dv.tile_sa; p.tile_sb = m->dv.tile_sb;
+  p.tile_sa = m->dv.tile_sa; p.tile_sb = m->dv.tile_sb; p.lane_tile = m->dv.lane_tile;
   p.n_items = nb * h.n_tg; p.n_chunks = gp.n_chunks; p.chunk_rows = gp.chunk_rows; p.RT = gp.RT; p.stages = gp.stages;
-  p.cs_cols = std::min(32 * GRAM_CS, ((h.Ppad + h.n_tg - 1) / h.n_tg + 31) / 32 * 32);
-  if ((int64_t)p.cs_cols * h.n_tg < h.Ppad) return fail(PLSPM_ERR_UNSUPPORTED, "column-sum partition too small");
   p.G = (gp.n_chunks > 1) ? Gpart : G;
-  p.colsum = (gp.n_chunks > 1) ? cspart : colsum;
   CK(cudaFuncSetAttribute(gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gp.smem));
   const int64_t grid = gp.n_groups * gp.n_chunks;
   if (grid > 0x7fffffff) return fail(PLSPM_ERR_UNSUPPORTED, "batch too large for one launch");
@@ -715,9 +853,19 @@ static int run_batch(plspm_data* d, int64_t nb, const uint32_t* counts_dev, doub
     d->timer.begin(ST_REDUCE, st);
     reduce_chunks_kernel<<<d->sm_count * 4, 256, 0, st>>>(Gpart, nb, gp.n_chunks, (int64_t)h.n_tiles * TILE, G);
     d->timer.end(st);
-    d->timer.begin(ST_REDUCE, st);
-    reduce_chunks_kernel<<<d->sm_count, 256, 0, st>>>(cspart, nb, gp.n_chunks, h.Ppad, colsum);
+    CK(cudaGetLastError());
+  }
+  {
+    dim3 grid_cs((h.Ppad + CS_COLS - 1) / CS_COLS, (unsigned)((nb + CS_REPS - 1) / CS_REPS), gp.cs_chunks);
+    d->timer.begin(ST_COLSUM, st);
+    colsum_kernel<<<grid_cs, 256, 0, st>>>(d->X, counts_dev, d->N, h.Ppad, nb, gp.cs_chunks, gp.cs_chunk_rows,
+                                            gp.cs_chunks > 1 ? cspart : colsum);
     d->timer.end(st);
+    if (gp.cs_chunks > 1) {
+      d->timer.begin(ST_REDUCE, st);
+      reduce_chunks_kernel<<<d->sm_count, 256, 0, st>>>(cspart, nb, gp.cs_chunks, h.Ppad, colsum);
+      d->timer.end(st);
+    }
     CK(cudaGetLastError());
   }
   SolveBatch b;
@@ -755,7 +903,7 @@ int plspm_fit(const plspm_model* m, const plspm_data* dc, int32_t scheme, double
   const size_t gsz = (size_t)h.n_tiles * TILE, L = h.L, P = h.P;
   size_t off = 0;
   auto take = [&](size_t doubles) { size_t o = off; off += align_up(doubles * 8); return o; };
-  const size_t o_G = take(gsz), o_Gp = take(gsz * gp.n_chunks), o_cs = take(h.Ppad), o_csp = take((size_t)h.Ppad * gp.n_chunks);
+  const size_t o_G = take(gsz), o_Gp = take(gsz * gp.n_chunks), o_cs = take(h.Ppad), o_csp = take((size_t)h.Ppad * gp.cs_chunks);
   const size_t o_ws = take(h.ws_doubles), o_w = take(P), o_ld = take(P), o_r2 = take(L), o_pa = take(L * L);
   const size_t o_to = take(L * L), o_cl = take(P * L), o_cf = take(h.Ppad), o_sh = take(L), o_it = take(2);
   const size_t o_sc = take(scores ? (size_t)N * L : 1);
@@ -821,7 +969,7 @@ int plspm_bootstrap(const plspm_model* m, const plspm_data* dc, int32_t scheme, 
   auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return o; };
   const size_t o_cnt = take((size_t)nb_max * N * 4), o_idx = take(idx ? (size_t)nb_max * N * 4 : 8);
   const size_t o_G = take((size_t)nb_max * gsz * 8), o_Gp = take(gp.n_chunks > 1 ? (size_t)nb_max * gsz * gp.n_chunks * 8 : 8);
-  const size_t o_cs = take((size_t)nb_max * h.Ppad * 8), o_csp = take(gp.n_chunks > 1 ? (size_t)nb_max * h.Ppad * gp.n_chunks * 8 : 8);
+  const size_t o_cs = take((size_t)nb_max * h.Ppad * 8), o_csp = take((size_t)nb_max * h.Ppad * gp.cs_chunks * 8);
   const size_t o_ws = take((size_t)nb_max * h.ws_doubles * 8), o_out = take(out_is_device ? 8 : (size_t)nb_max * n_out * 8);
   const size_t o_it = take((size_t)nb_max * 4), o_st = take((size_t)nb_max * 4);
   if (int rc = ws_reserve(d, off)) return rc;
@@ -832,7 +980,14 @@ int plspm_bootstrap(const plspm_model* m, const plspm_data* dc, int32_t scheme, 
     GramPlan g2 = gp;
     if (nb != nb_max) {
       if (int rc = plan_gram(d, nb, g2)) return rc;
-      if (g2.n_chunks > gp.n_chunks) { g2 = gp; g2.n_groups = (nb * h.n_tg + GRAM_WARPS - 1) / GRAM_WARPS; }
+      if (g2.n_chunks > gp.n_chunks) {
+        GramPlan keep = g2;
+        g2 = gp;
+        g2.n_groups = (nb * h.n_tg + GRAM_WARPS - 1) / GRAM_WARPS;
+        g2.cs_chunks = keep.cs_chunks; g2.cs_chunk_rows = keep.cs_chunk_rows;
+      }
+      const int64_t cap = std::max<int64_t>(1, nb_max * gp.cs_chunks / nb);  // cspart was sized for (nb_max, gp)
+      if (g2.cs_chunks > cap) plan_colsum(d, nb, (int)cap, g2);
     }
     uint32_t* cnt = (uint32_t*)(base + o_cnt);
     int32_t* idx_dev = nullptr;

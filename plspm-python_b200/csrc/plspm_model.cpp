@@ -2,6 +2,7 @@
 #include "plspm_model.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <set>
 #include <utility>
 
@@ -15,6 +16,7 @@ ModelView HostModel::host_view() const {
   v.lv_off = lv_off.data(); v.lv_k = lv_k.data(); v.lv_mode = lv_mode.data();
   v.col_lv = col_lv.data(); v.col_src = col_src.data(); v.path = path.data();
   v.tile_sa = tile_sa.data(); v.tile_sb = tile_sb.data(); v.tile_of = tile_of.data();
+  v.lane_tile = lane_tile.data(); v.tile_owner = tile_owner.data();
   v.pair_l = pair_l.data(); v.pair_j = pair_j.data(); v.pair_voff = pair_voff.data();
   v.lv_pair_begin = lv_pair_begin.data();
   v.eff_from = eff_from.data(); v.eff_to = eff_to.data(); v.chol_b_off = chol_b_off.data();
@@ -142,7 +144,45 @@ int build_model(int L, const int32_t* block_sizes, const int8_t* modes, const in
     if (t.first != t.second) m.tile_of[(size_t)t.second * m.ns + t.first] = -(id + 2);
   }
   m.n_tiles = (int)m.tile_sa.size();
-  m.n_tg = (m.n_tiles + 31) / 32;
+  m.tile_owner.assign(m.n_tiles, 0);
+  for (int sl = 0; sl < m.ns; ++sl) {
+    int best = -1;
+    for (int t = 0; t < m.n_tiles; ++t)
+      if (m.tile_sb[t] == sl && (best < 0 || m.tile_sa[t] > m.tile_sa[best])) best = t;
+    m.tile_owner[best] = 1;
+  }
+  // pack tiles into warps (tile groups of 32 lanes): chunks of one row slot, first-fit decreasing
+  {
+    std::vector<std::vector<int>> chunks;
+    for (int t = 0; t < m.n_tiles;) {
+      int e = t;
+      while (e < m.n_tiles && m.tile_sa[e] == m.tile_sa[t] && e - t < 32) ++e;
+      chunks.emplace_back();
+      for (int k = t; k < e; ++k) chunks.back().push_back(k);
+      t = e;
+    }
+    const bool pack = !(getenv("PLSPM_TILE_PACK") && atoi(getenv("PLSPM_TILE_PACK")) == 0);
+    if (!pack) {  // natural order, 32 consecutive tiles per group (experiment switch)
+      chunks.clear();
+      for (int t = 0; t < m.n_tiles; t += 32) {
+        chunks.emplace_back();
+        for (int k = t; k < std::min(t + 32, m.n_tiles); ++k) chunks.back().push_back(k);
+      }
+    }
+    std::stable_sort(chunks.begin(), chunks.end(),
+                     [](const std::vector<int>& a, const std::vector<int>& b) { return a.size() > b.size(); });
+    std::vector<std::vector<int>> bins;
+    for (auto& ch : chunks) {
+      bool placed = false;
+      for (auto& b : bins)
+        if (b.size() + ch.size() <= 32) { b.insert(b.end(), ch.begin(), ch.end()); placed = true; break; }
+      if (!placed) bins.push_back(ch);
+    }
+    m.n_tg = (int)bins.size();
+    m.lane_tile.assign((size_t)m.n_tg * 32, -1);
+    for (int g = 0; g < m.n_tg; ++g)
+      for (size_t k = 0; k < bins[g].size(); ++k) m.lane_tile[(size_t)g * 32 + k] = bins[g][k];
+  }
 
   // effect rows: (from, to) with a directed path from -> to, reference row order
   std::vector<char> reach((size_t)L * L, 0);  // reach[to*L+from]

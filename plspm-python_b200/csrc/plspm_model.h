@@ -27,6 +27,8 @@ struct ModelView {
   const int *lv_off, *lv_k, *lv_mode, *col_lv, *col_src;
   const int8_t* path;                       // [L*L] path[i*L+j]==1 : j -> i
   const int *tile_sa, *tile_sb, *tile_of;   // tile list and ns*ns lookup (see tile_of encoding)
+  const int* lane_tile;                     // [n_tg*32] tile id handled by lane (or -1)
+  const int* tile_owner;                    // [n_tiles] 1: this tile's lane accumulates the column sums of slot sb
   const int *pair_l, *pair_j, *pair_voff, *lv_pair_begin;
   const int *eff_from, *eff_to;
   const int *chol_b_off;
@@ -44,6 +46,12 @@ struct HostModel {
   // sum_i c_i x[i, 8*sa+r] x[i, 8*sb+c].  tile_of[a*ns+b] = t if stored as (a,b), -(t+2) if stored
   // transposed, -1 if the slot pair is not computed.
   std::vector<int> tile_sa, tile_sb, tile_of;
+  // Tile -> (tile group, lane) packing: tiles of one row slot stay in one warp so that the row
+  // operand is a shared-memory broadcast; lane_tile[g*32+lane] = tile id or -1.
+  std::vector<int> lane_tile;
+  // tile_owner[t] = 1 for exactly one tile per slot s (sb == s, largest sa): its lane also sums the
+  // slot's columns (the replicate's weighted column sums) from registers it has loaded anyway.
+  std::vector<int> tile_owner;
   // directed LV pairs (l <- j) whose block covariance the iteration needs; sorted by l, the
   // diagonal pair (l <- l) first.  V[pair_voff[d] + r], r < K_l, receives (S_lj w_j)[r].
   std::vector<int> pair_l, pair_j, pair_voff, lv_pair_begin;
