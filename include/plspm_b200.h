@@ -97,7 +97,8 @@ int plspm_resample_indices(uint64_t seed, int64_t replicate, int64_t N, int32_t*
 
 /* Instrumentation of the library's own stream since the last reset: device milliseconds per
  * stage measured with CUDA events around every launch, and kernel launch counts.
- * ms[8] / launches[8]: 0 counts, 1 gram, 2 chunk reduce, 3 solve, 4 scores, 5 upload kernels, 6 column sums. */
+ * ms[8] / launches[8]: 0 counts, 1 gram, 2 chunk reduce, 3 solve, 4 scores, 5 upload kernels, 6 column sums,
+ * 7 cross moments (sparse tile sets). */
 int plspm_profile_reset(void);
 int plspm_profile_get(double* ms, int64_t* launches);
 

@@ -48,7 +48,7 @@ static int fail(int code, const std::string& msg) {
                   std::string(#expr) + ": " + cudaGetErrorString(e_));                             \
   } while (0)
 
-enum { ST_COUNTS = 0, ST_GRAM = 1, ST_REDUCE = 2, ST_SOLVE = 3, ST_SCORES = 4, ST_UPLOAD = 5, ST_COLSUM = 6, ST_N = 8 };
+enum { ST_COUNTS = 0, ST_GRAM = 1, ST_REDUCE = 2, ST_SOLVE = 3, ST_SCORES = 4, ST_UPLOAD = 5, ST_COLSUM = 6, ST_CROSS = 7, ST_N = 8 };
 struct Profile {
   std::mutex mu;
   double ms[ST_N] = {0};
@@ -267,6 +267,11 @@ struct GramParams {
   int64_t chunk_rows;       // multiple of RT
   int RT, stages;
   double* G;                // [nrep][n_chunks][n_tiles*64]
+  // cross-moment mode (template CROSS): tiles are (slot sa, LV group g) in natural order, the
+  // column operand is the row's LV scores x~_i . wf_l times the multiplicity (per-warp scratch)
+  int L, ng;
+  const int *lv_off, *lv_k;
+  const double* wf;         // [nrep][Ppad] final weights of every replicate
 };
 
 __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
@@ -283,6 +288,7 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
   return done != 0;
 }
 
+template <bool CROSS>
 __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const GramParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[GRAM_MAX_STAGES], empty_bar[GRAM_MAX_STAGES];
@@ -337,13 +343,25 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const GramParams 
   const int64_t item = item0 + warp;
   const int64_t rep = item / p.n_tg;
   const int tg = (int)(item - rep * p.n_tg);
-  const int tile = p.lane_tile[tg * 32 + lane];
+  int tile, sa, sb;
+  if constexpr (CROSS) {
+    // LV-group-major order: a warp covers (almost always) ONE group of 8 LVs and 32 row slots, so it
+    // needs only that group's scores
+    tile = tg * 32 + lane;
+    if (tile >= p.n_tiles) tile = -1;
+    const int ns = p.Ppad / SLOT;
+    sb = tile >= 0 ? tile / ns : 0;          // LV group: "slot" sb of the score scratch row
+    sa = tile >= 0 ? tile - sb * ns : 0;
+  } else {
+    tile = p.lane_tile[tg * 32 + lane];
+    sa = tile >= 0 ? p.tile_sa[tile] : 0;
+    sb = tile >= 0 ? p.tile_sb[tile] : 0;
+  }
   const bool tile_ok = tile >= 0;
-  const int sa = tile_ok ? p.tile_sa[tile] : 0, sb = tile_ok ? p.tile_sb[tile] : 0;
   // 16-byte chunks of a slot are read in a lane-dependent rotated order so that the 32 LDS.128 of
-  // a warp spread over all bank quads (slot stride 64 B would otherwise be a 16-way conflict)
-  // (the row operand xa is a broadcast within a packed tile group and needs no rotation)
-  const int rot_a = 0, rot_b = (sb >> 1) & 3;
+  // a warp spread over all bank quads (slot stride 64 B would otherwise be a 16-way conflict).
+  // In Gram mode the row operand xa is a broadcast within a packed tile group: no rotation.
+  const int rot_a = CROSS ? ((sa >> 1) & 3) : 0, rot_b = CROSS ? 0 : ((sb >> 1) & 3);
   int off_a[4], off_b[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
@@ -373,11 +391,11 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const GramParams 
   auto lds128 = [](uint32_t addr, double& x, double& y) {
     asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "r"(addr));
   };
-  auto load_row = [&](uint32_t row_addr, double (&xa)[8], double (&xb)[8]) {
+  auto load_row = [&](uint32_t row_addr, uint32_t b_addr, double (&xa)[8], double (&xb)[8]) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       lds128(row_addr + boff_a[k], xa[2 * k], xa[2 * k + 1]);
-      lds128(row_addr + boff_b[k], xb[2 * k], xb[2 * k + 1]);
+      lds128(b_addr + boff_b[k], xb[2 * k], xb[2 * k + 1]);
     }
   };
   // The scaling and the 64 FMAs of a row are emitted as volatile asm so that the compiler keeps
@@ -385,6 +403,7 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const GramParams 
   // the loads get sunk below the FMA block to save registers and the software pipeline is lost
   // (measured: 6.5 % of all issue slots stalled on the first DMUL of every row).
   auto accumulate = [&](double (&xa)[8], double (&xb)[8], double c) {
+    if constexpr (!CROSS)  // (the score scratch is already multiplied by the multiplicity)
     asm volatile(
         "mul.f64 %0, %0, %8;\n\tmul.f64 %1, %1, %8;\n\tmul.f64 %2, %2, %8;\n\tmul.f64 %3, %3, %8;\n\t"
         "mul.f64 %4, %4, %8;\n\tmul.f64 %5, %5, %8;\n\tmul.f64 %6, %6, %8;\n\tmul.f64 %7, %7, %8;"
@@ -403,7 +422,7 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const GramParams 
   };
   // per-warp list of the tile's non-zero rows: {row byte offset in the stage, multiplicity as fp64},
   // built once per tile by all lanes, so that the row loop is a plain counted loop
-  __shared__ __align__(16) double2 row_list[GRAM_WARPS][36];  // 32 rows + 4 zero-multiplicity pads
+  __shared__ __align__(16) double2 row_list[GRAM_WARPS][40];  // 32 rows + 8 zero-multiplicity pads
   double2* my_list = row_list[warp];
   const uint32_t list_addr = smem_u32(my_list);
   const uint32_t tiles_addr = smem_u32(tiles);
@@ -413,6 +432,16 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const GramParams 
     asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(o), "=d"(c) : "r"(list_addr + 16u * (uint32_t)k));
     off = (uint32_t)__double_as_longlong(o);
   };
+  // cross mode: per-warp scratch of (RT + 8) rows x Lpad scores behind the ring
+  const int Lpad = p.ng * SLOT;
+  double* my_scores = tiles + (size_t)p.stages * stage_doubles + (size_t)warp * (p.RT + 8) * Lpad;
+  const uint32_t sc_addr = smem_u32(my_scores);
+  const uint32_t sc_row_bytes = (uint32_t)Lpad * 8u;
+  const double* wf_rep = CROSS ? p.wf + rep * p.Ppad : nullptr;
+  if constexpr (CROSS) {
+    for (int e = lane; e < (p.RT + 8) * Lpad; e += 32) my_scores[e] = 0.0;
+    __syncwarp();
+  }
   uint32_t cnt_next = load_counts(0);
 
   for (int t = 0; t < n_rt; ++t) {
@@ -428,10 +457,40 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const GramParams 
       my_list[pos] = make_double2(__longlong_as_double((long long)((uint32_t)lane * row_bytes)), (double)cnt);
     }
     // pads: multiplicity 0 on row 0 of the stage, so the pipelined loop below needs no branches
-    if (lane < 4) my_list[n_nz + lane] = make_double2(__longlong_as_double(0ll), 0.0);
+    if (lane < 8) my_list[n_nz + lane] = make_double2(__longlong_as_double(0ll), 0.0);
     __syncwarp();
     mbar_wait(&full_bar[s], use & 1);
     const uint32_t base = tiles_addr + (uint32_t)s * (uint32_t)(stage_doubles * 8);
+    if constexpr (CROSS) {
+      // scores of the tile's non-zero rows for the LVs this warp's tiles touch, one (row, LV) pair
+      // per lane:  scratch[k][l] = c_k * sum_{q in block l} x~[row_k][q] wf[q]   (pad rows: c = 0)
+      if (n_nz > 0) {
+        const int ns = p.Ppad / SLOT;
+        const int lv_lo = ((tg * 32) / ns) * SLOT;
+        const int lv_hi = min(p.L, (min(p.n_tiles - 1, tg * 32 + 31) / ns) * SLOT + SLOT);
+        const int nlw = lv_hi - lv_lo;
+        for (int e = lane; e < nlw * (n_nz + 2); e += 32) {
+          const int k = e / nlw, lv = lv_lo + (e - k * nlw);
+          const int slot0 = p.lv_off[lv] >> 3, nsl = (p.lv_k[lv] + SLOT - 1) >> 3;
+          const int rot = (slot0 >> 1) & 3;
+          uint32_t o;
+          double cc, sc = 0.0;
+          load_entry(k, o, cc);
+          for (int sl = 0; sl < nsl; ++sl)
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {
+              const int col = (slot0 + sl) * SLOT + 2 * ((ch + rot) & 3);
+              const double2 w2 = __ldg(reinterpret_cast<const double2*>(wf_rep + col));
+              double x0, x1;
+              lds128(base + o + (uint32_t)col * 8u, x0, x1);
+              sc = fma(x0, w2.x, sc);
+              sc = fma(x1, w2.y, sc);
+            }
+          my_scores[(size_t)k * Lpad + lv] = cc * sc;
+        }
+      }
+      __syncwarp();
+    }
     if (n_nz > 0) {
       // Software pipeline over the non-zero rows, two rows per trip, straight-line body: the
       // operands of row k+1 are in flight (LDS) while the 64 FMAs of row k issue, and the list
@@ -439,20 +498,22 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const GramParams 
       // with multiplicity 0 (adds exact zeros; ~2.5 % extra FMAs, no branch in the body).
       double xa0[8], xb0[8], xa1[8], xb1[8], c0, c1, ce0, ce1;
       uint32_t oe0, oe1;
+      // column operand: the same X row (Gram) or the row's scratch scores (cross)
+      uint32_t bsrc = sc_addr;
       load_entry(0, oe0, ce0);
       load_entry(1, oe1, ce1);
-      load_row(base + oe0, xa0, xb0);
+      load_row(base + oe0, CROSS ? bsrc : base + oe0, xa0, xb0);
       c0 = ce0;
       for (int k = 0; k < n_nz; k += 2) {
-        load_row(base + oe1, xa1, xb1);
+        load_row(base + oe1, CROSS ? bsrc + sc_row_bytes : base + oe1, xa1, xb1);
         c1 = ce1;
         load_entry(k + 2, oe0, ce0);
         accumulate(xa0, xb0, c0);
-        load_row(base + oe0, xa0, xb0);
+        bsrc += 2 * sc_row_bytes;
+        load_row(base + oe0, CROSS ? bsrc : base + oe0, xa0, xb0);
         c0 = ce0;
         load_entry(k + 3, oe1, ce1);
         accumulate(xa1, xb1, c1);
-        if (producer && (k & 6) == 6) feed(t);  // opportunistic refill while the tile is being consumed
       }
     }
     __syncwarp();
@@ -462,7 +523,8 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const GramParams 
   // ---- write the partial tile (undo the chunk rotation) and the column sums --------------------
   const size_t slab = (size_t)rep * p.n_chunks + chunk;
   if (tile_ok) {
-    double* g = p.G + (slab * p.n_tiles + tile) * TILE;
+    const int store_tile = CROSS ? sa * p.ng + sb : tile;
+    double* g = p.G + (slab * p.n_tiles + store_tile) * TILE;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int ra = 2 * (((i >> 1) + rot_a) & 3) + (i & 1);
@@ -551,6 +613,9 @@ struct SolveBatch {
   double N;
   int scheme; double tol; int max_iter;
   double* ws;
+  int phase;                             // see SolveArgs::phase
+  double* wf;                            // [nrep][Ppad] (sparse tile sets)
+  const double* cross; int64_t cross_stride;
   double* out_rows; int64_t out_stride;  // may be null
   double *weights, *loadings, *r2, *paths, *total, *crossloadings, *score_coef, *score_shift;  // single fit
   int *iters, *status;
@@ -571,6 +636,9 @@ __global__ void __launch_bounds__(SOLVE_THREADS) solve_kernel(const SolveBatch b
   A.tol = b.tol;
   A.max_iter = b.max_iter;
   A.ext_votes = nullptr;
+  A.phase = b.phase;
+  A.wf_out = b.wf ? b.wf + rep * b.M.Ppad : nullptr;
+  A.cross = b.cross ? b.cross + rep * b.cross_stride : nullptr;
   A.ws = b.ws + rep * (int64_t)b.M.ws_doubles;
   A.out_row = b.out_rows ? b.out_rows + rep * b.out_stride : nullptr;
   A.weights = b.weights; A.loadings = b.loadings; A.r2 = b.r2; A.paths = b.paths; A.total = b.total;
@@ -625,10 +693,6 @@ int plspm_model_create(int32_t L, const int32_t* block_sizes, const int8_t* mode
   if (build_model(L, block_sizes, modes, path, scaled, tile_policy, m->h, err)) {
     delete m;
     return fail(PLSPM_ERR_INVALID, err);
-  }
-  if (!m->h.full) {
-    delete m;
-    return fail(PLSPM_ERR_UNSUPPORTED, "sparse tile sets need the cross-moment sign pass (not built yet)");
   }
   if ((size_t)m->h.Ppad * 8 > 64 * 1024) {
     delete m;
@@ -774,41 +838,56 @@ void plspm_data_destroy(plspm_data* d) {
   delete d;
 }
 
-// Launch plan of the Gram kernel for nb replicates.
-struct GramPlan {
-  int RT, stages, n_chunks;
-  int64_t chunk_rows, n_groups;
-  size_t smem;
-  int cs_chunks;          // row chunks of the column-sum kernel
-  int64_t cs_chunk_rows;
+// ------------------------------------------------------------------------------------------------
+// launch plans, workspace layout, batch driver
+// ------------------------------------------------------------------------------------------------
+struct StreamPlan {  // one streaming pass over X (Gram tiles or cross-moment tiles)
+  int RT = 0, stages = 0, n_chunks = 1;
+  int64_t chunk_rows = 0, n_groups = 0;
+  size_t smem = 0;
 };
-static void plan_colsum(const plspm_data* d, int64_t nb, int max_chunks, GramPlan& g) {
+struct BatchPlan {
+  StreamPlan gram, cross;
+  int cs_chunks = 1;  // row chunks of the column-sum kernel
+  int64_t cs_chunk_rows = 0;
+};
+
+static void plan_colsum(const plspm_data* d, int64_t nb, BatchPlan& g) {
   const HostModel& h = d->model->h;
   const int64_t blocks_xy = (int64_t)((h.Ppad + CS_COLS - 1) / CS_COLS) * ((nb + CS_REPS - 1) / CS_REPS);
   const int64_t want = (int64_t)d->sm_count * 8;
   int64_t chunks = std::max<int64_t>(1, (want + blocks_xy - 1) / blocks_xy);
   chunks = std::min<int64_t>(chunks, std::max<int64_t>(1, d->N / (CS_ROWS * 8)));
   chunks = std::min<int64_t>(chunks, 65535);
-  if (max_chunks > 0) chunks = std::min<int64_t>(chunks, max_chunks);
   int64_t rows = ((d->N + chunks - 1) / chunks + CS_ROWS - 1) / CS_ROWS * CS_ROWS;
   g.cs_chunk_rows = rows;
   g.cs_chunks = (int)((d->N + rows - 1) / rows);
 }
-static int plan_gram(const plspm_data* d, int64_t nb, GramPlan& g) {
+
+// Ring geometry + row chunking of a streaming pass.  extra_row_bytes / extra_fixed_bytes: per-CTA
+// shared memory the kernel needs per ring row and in total besides the ring (cross mode scratch).
+static int plan_stream(const plspm_data* d, int64_t n_items, size_t extra_row_bytes, size_t extra_fixed_bytes,
+                       StreamPlan& g) {
   const HostModel& h = d->model->h;
   const size_t row_bytes = (size_t)h.Ppad * 8;
-  // ring geometry: stages of <= 64 KB / 32 rows (env PLSPM_GRAM_STAGE_KB) and as many as fit (<= 8);
-  // measured on c3: 32-row stages beat 16-row stages by 10 % (per-tile handshakes amortise)
+  // stages of <= 64 KB / 32 rows; measured on c3: 32-row stages beat 16-row stages by 10 % (per-tile
+  // handshakes amortise), three stages are enough once the producer refills opportunistically
   static const int stage_kb = getenv("PLSPM_GRAM_STAGE_KB") ? atoi(getenv("PLSPM_GRAM_STAGE_KB")) : 64;
-  static const int max_stages = getenv("PLSPM_GRAM_STAGES") ? atoi(getenv("PLSPM_GRAM_STAGES")) : GRAM_MAX_STAGES;
-  int RT = (int)std::min<size_t>(32, std::max<size_t>(1, (size_t)stage_kb * 1024 / row_bytes));
-  const size_t stage_bytes = RT * row_bytes;
+  static const int want_stages = getenv("PLSPM_GRAM_STAGES") ? atoi(getenv("PLSPM_GRAM_STAGES")) : 3;
   const size_t budget = (size_t)d->max_smem - 8 * 1024;  // static shared memory (barriers, row lists) + slack
-  int stages = (int)std::min<size_t>(std::min(max_stages, GRAM_MAX_STAGES), budget / stage_bytes);
-  if (stages < 2) return fail(PLSPM_ERR_UNSUPPORTED, "manifest rows too wide for the shared-memory ring");
+  if (budget < extra_fixed_bytes + 2 * (row_bytes + extra_row_bytes))
+    return fail(PLSPM_ERR_UNSUPPORTED, "manifest rows too wide for the shared-memory ring");
+  int stages = std::max(2, std::min(want_stages, GRAM_MAX_STAGES));
+  int64_t RT = 0;
+  for (; stages >= 2; --stages) {
+    RT = (int64_t)((budget - extra_fixed_bytes) / ((size_t)stages * row_bytes + extra_row_bytes));
+    RT = std::min<int64_t>(RT, std::max<int64_t>(1, (int64_t)((size_t)stage_kb * 1024 / row_bytes)));
+    RT = std::min<int64_t>(RT, 32);
+    if (RT >= 4 || stages == 2) break;
+  }
+  if (RT < 1) return fail(PLSPM_ERR_UNSUPPORTED, "manifest rows too wide for the shared-memory ring");
   const int64_t n_tiles_rt = (d->N + RT - 1) / RT;
   stages = (int)std::min<int64_t>(stages, std::max<int64_t>(2, n_tiles_rt));
-  const int64_t n_items = nb * h.n_tg;
   const int64_t n_groups = (n_items + GRAM_WARPS - 1) / GRAM_WARPS;
   // split rows only when there are too few (replicate, tile group) items to fill the chip
   int64_t n_chunks = 1;
@@ -817,78 +896,153 @@ static int plan_gram(const plspm_data* d, int64_t nb, GramPlan& g) {
   n_chunks = std::max<int64_t>(1, std::min<int64_t>(n_chunks, n_tiles_rt / 4 > 0 ? n_tiles_rt / 4 : 1));
   int64_t chunk_rows = ((n_tiles_rt + n_chunks - 1) / n_chunks) * RT;
   n_chunks = (d->N + chunk_rows - 1) / chunk_rows;
-  g.RT = RT; g.stages = stages; g.n_chunks = (int)n_chunks; g.chunk_rows = chunk_rows; g.n_groups = n_groups;
-  g.smem = (size_t)stages * stage_bytes;
-  plan_colsum(d, nb, 0, g);
+  g.RT = (int)RT; g.stages = stages; g.n_chunks = (int)n_chunks; g.chunk_rows = chunk_rows; g.n_groups = n_groups;
+  g.smem = (size_t)stages * RT * row_bytes + extra_fixed_bytes + (size_t)RT * extra_row_bytes;
   return 0;
 }
 
-// Shared implementation of fit (counts == null, one "replicate") and bootstrap batches.
-struct BatchOut {
-  double* out_rows = nullptr;  // device [nb][n_out] or null
-  double *weights = nullptr, *loadings = nullptr, *r2 = nullptr, *paths = nullptr, *total = nullptr,
-         *crossloadings = nullptr, *score_coef = nullptr, *score_shift = nullptr;  // device, single fit
-  int *iters = nullptr, *status = nullptr;  // device [nb]
-};
+static int plan_batch(const plspm_data* d, int64_t nb, BatchPlan& bp) {
+  const HostModel& h = d->model->h;
+  if (int rc = plan_stream(d, nb * h.n_tg, 0, 0, bp.gram)) return rc;
+  if (!h.full) {
+    const size_t per_row = (size_t)GRAM_WARPS * h.ng * SLOT * 8;  // score scratch row of every warp
+    if (int rc = plan_stream(d, nb * h.n_tg_cross, per_row, 8 * per_row, bp.cross)) return rc;
+  }
+  plan_colsum(d, nb, bp);
+  return 0;
+}
 
-static int run_batch(plspm_data* d, int64_t nb, const uint32_t* counts_dev, double* G, double* Gpart, double* colsum,
-                     double* cspart, double* ws_solver, int scheme, double tol, int max_iter, const GramPlan& gp,
-                     const BatchOut& o) {
+static size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+
+// Device workspace of one batch of up to nb replicates (offsets into plspm_data::ws).
+struct BatchBuffers {
+  size_t total = 0;
+  size_t counts, idx, G, Gpart, colsum, cspart, ws, out, iters, status, wf, CG, CGpart;
+  // single-fit outputs
+  size_t weights, loadings, r2, paths, totalfx, crossl, coef, shift, scores;
+};
+static BatchBuffers layout_batch(const plspm_data* d, int64_t nb, const BatchPlan& bp, bool with_counts, bool with_idx,
+                                 bool rows_on_device_of_caller, bool single_fit, bool want_scores) {
+  const HostModel& h = d->model->h;
+  BatchBuffers b;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += align_up(std::max<size_t>(bytes, 8)); return o; };
+  const size_t gsz = (size_t)h.n_tiles * TILE * 8, csz = (size_t)h.n_cross * TILE * 8;
+  b.counts = take(with_counts ? (size_t)nb * d->N * 4 : 0);
+  b.idx = take(with_idx ? (size_t)nb * d->N * 4 : 0);
+  b.G = take((size_t)nb * gsz);
+  b.Gpart = take(bp.gram.n_chunks > 1 ? (size_t)nb * gsz * bp.gram.n_chunks : 0);
+  b.colsum = take((size_t)nb * h.Ppad * 8);
+  b.cspart = take(bp.cs_chunks > 1 ? (size_t)nb * h.Ppad * 8 * bp.cs_chunks : 0);
+  b.ws = take((size_t)nb * h.ws_doubles * 8);
+  b.out = take(rows_on_device_of_caller || single_fit ? 0 : (size_t)nb * h.n_out() * 8);
+  b.iters = take((size_t)nb * 4);
+  b.status = take((size_t)nb * 4);
+  b.wf = take(h.full ? 0 : (size_t)nb * h.Ppad * 8);
+  b.CG = take(h.full ? 0 : (size_t)nb * csz);
+  b.CGpart = take(!h.full && bp.cross.n_chunks > 1 ? (size_t)nb * csz * bp.cross.n_chunks : 0);
+  if (single_fit) {
+    const size_t L = h.L, P = h.P;
+    b.weights = take(P * 8); b.loadings = take(P * 8); b.r2 = take(L * 8); b.paths = take(L * L * 8);
+    b.totalfx = take(L * L * 8); b.crossl = take(P * L * 8); b.coef = take((size_t)h.Ppad * 8); b.shift = take(L * 8);
+    b.scores = take(want_scores ? (size_t)d->N * L * 8 : 0);
+  }
+  b.total = off;
+  return b;
+}
+
+static int launch_stream(plspm_data* d, bool cross, int64_t nb, const uint32_t* counts_dev, const StreamPlan& sp,
+                         double* out_tiles, double* part_tiles, const double* wf) {
   const plspm_model* m = d->model;
   const HostModel& h = m->h;
   cudaStream_t st = d->stream;
   GramParams p;
-  p.X = d->X; p.counts = counts_dev; p.N = d->N; p.Ppad = h.Ppad; p.n_tiles = h.n_tiles; p.n_tg = h.n_tg;
+  p.X = d->X; p.counts = counts_dev; p.N = d->N; p.Ppad = h.Ppad;
+  p.n_tiles = cross ? h.n_cross : h.n_tiles;
+  p.n_tg = cross ? h.n_tg_cross : h.n_tg;
   p.tile_sa = m->dv.tile_sa; p.tile_sb = m->dv.tile_sb; p.lane_tile = m->dv.lane_tile;
-  p.n_items = nb * h.n_tg; p.n_chunks = gp.n_chunks; p.chunk_rows = gp.chunk_rows; p.RT = gp.RT; p.stages = gp.stages;
-  p.G = (gp.n_chunks > 1) ? Gpart : G;
-  CK(cudaFuncSetAttribute(gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gp.smem));
-  const int64_t grid = gp.n_groups * gp.n_chunks;
+  p.n_items = nb * p.n_tg; p.n_chunks = sp.n_chunks; p.chunk_rows = sp.chunk_rows; p.RT = sp.RT; p.stages = sp.stages;
+  p.G = (sp.n_chunks > 1) ? part_tiles : out_tiles;
+  p.L = h.L; p.ng = h.ng; p.lv_off = m->dv.lv_off; p.lv_k = m->dv.lv_k; p.wf = wf;
+  const int64_t n_groups = (p.n_items + GRAM_WARPS - 1) / GRAM_WARPS;
+  const int64_t grid = n_groups * sp.n_chunks;
   if (grid > 0x7fffffff) return fail(PLSPM_ERR_UNSUPPORTED, "batch too large for one launch");
-  d->timer.begin(ST_GRAM, st);
-  gram_kernel<<<(unsigned)grid, GRAM_THREADS, gp.smem, st>>>(p);
+  d->timer.begin(cross ? ST_CROSS : ST_GRAM, st);
+  if (cross) {
+    CK(cudaFuncSetAttribute(gram_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp.smem));
+    gram_kernel<true><<<(unsigned)grid, GRAM_THREADS, sp.smem, st>>>(p);
+  } else {
+    CK(cudaFuncSetAttribute(gram_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp.smem));
+    gram_kernel<false><<<(unsigned)grid, GRAM_THREADS, sp.smem, st>>>(p);
+  }
   d->timer.end(st);
   CK(cudaGetLastError());
-  if (gp.n_chunks > 1) {
+  if (sp.n_chunks > 1) {
     d->timer.begin(ST_REDUCE, st);
-    reduce_chunks_kernel<<<d->sm_count * 4, 256, 0, st>>>(Gpart, nb, gp.n_chunks, (int64_t)h.n_tiles * TILE, G);
+    reduce_chunks_kernel<<<d->sm_count * 4, 256, 0, st>>>(part_tiles, nb, sp.n_chunks, (int64_t)p.n_tiles * TILE,
+                                                          out_tiles);
     d->timer.end(st);
     CK(cudaGetLastError());
   }
+  return 0;
+}
+
+// Shared implementation of fit (counts == null, one "replicate") and bootstrap batches.
+static int run_batch(plspm_data* d, int64_t nb, const uint32_t* counts_dev, const BatchBuffers& bb, int scheme,
+                     double tol, int max_iter, const BatchPlan& bp, double* out_rows, bool single_fit) {
+  const plspm_model* m = d->model;
+  const HostModel& h = m->h;
+  cudaStream_t st = d->stream;
+  char* base = (char*)d->ws.ptr;
+  auto D = [&](size_t o) { return (double*)(base + o); };
+  if (int rc = launch_stream(d, false, nb, counts_dev, bp.gram, D(bb.G), D(bb.Gpart), nullptr)) return rc;
   {
-    dim3 grid_cs((h.Ppad + CS_COLS - 1) / CS_COLS, (unsigned)((nb + CS_REPS - 1) / CS_REPS), gp.cs_chunks);
+    dim3 grid_cs((h.Ppad + CS_COLS - 1) / CS_COLS, (unsigned)((nb + CS_REPS - 1) / CS_REPS), bp.cs_chunks);
     d->timer.begin(ST_COLSUM, st);
-    colsum_kernel<<<grid_cs, 256, 0, st>>>(d->X, counts_dev, d->N, h.Ppad, nb, gp.cs_chunks, gp.cs_chunk_rows,
-                                            gp.cs_chunks > 1 ? cspart : colsum);
+    colsum_kernel<<<grid_cs, 256, 0, st>>>(d->X, counts_dev, d->N, h.Ppad, nb, bp.cs_chunks, bp.cs_chunk_rows,
+                                            bp.cs_chunks > 1 ? D(bb.cspart) : D(bb.colsum));
     d->timer.end(st);
-    if (gp.cs_chunks > 1) {
+    if (bp.cs_chunks > 1) {
       d->timer.begin(ST_REDUCE, st);
-      reduce_chunks_kernel<<<d->sm_count, 256, 0, st>>>(cspart, nb, gp.cs_chunks, h.Ppad, colsum);
+      reduce_chunks_kernel<<<d->sm_count, 256, 0, st>>>(D(bb.cspart), nb, bp.cs_chunks, h.Ppad, D(bb.colsum));
       d->timer.end(st);
     }
     CK(cudaGetLastError());
   }
   SolveBatch b;
+  std::memset(&b, 0, sizeof(b));
   b.M = m->dv;
-  b.G = G; b.g_stride = (int64_t)h.n_tiles * TILE;
-  b.colsum = colsum; b.cs_stride = h.Ppad;
+  b.G = D(bb.G); b.g_stride = (int64_t)h.n_tiles * TILE;
+  b.colsum = D(bb.colsum); b.cs_stride = h.Ppad;
   b.mu = d->mu; b.N = (double)d->N; b.scheme = scheme; b.tol = tol; b.max_iter = max_iter;
-  b.ws = ws_solver;
-  b.out_rows = o.out_rows; b.out_stride = h.n_out();
-  b.weights = o.weights; b.loadings = o.loadings; b.r2 = o.r2; b.paths = o.paths; b.total = o.total;
-  b.crossloadings = o.crossloadings; b.score_coef = o.score_coef; b.score_shift = o.score_shift;
-  b.iters = o.iters; b.status = o.status;
+  b.ws = D(bb.ws);
+  b.iters = (int*)(base + bb.iters); b.status = (int*)(base + bb.status);
+  b.wf = h.full ? nullptr : D(bb.wf);
+  b.cross = h.full ? nullptr : D(bb.CG); b.cross_stride = (int64_t)h.n_cross * TILE;
   const size_t smem = h.solver_smem_doubles() * sizeof(double);
   if (smem > (size_t)d->max_smem) return fail(PLSPM_ERR_UNSUPPORTED, "model too large for the solver's shared memory");
   CK(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (!h.full) {
+    // sparse tile set: final weights first, then the P x L cross-moment pass for the sign vote
+    b.phase = 1;
+    d->timer.begin(ST_SOLVE, st);
+    solve_kernel<<<(unsigned)nb, SOLVE_THREADS, smem, st>>>(b);
+    d->timer.end(st);
+    CK(cudaGetLastError());
+    if (int rc = launch_stream(d, true, nb, counts_dev, bp.cross, D(bb.CG), D(bb.CGpart), D(bb.wf))) return rc;
+  }
+  b.phase = h.full ? 0 : 2;
+  b.out_rows = out_rows; b.out_stride = h.n_out();
+  if (single_fit) {
+    b.weights = D(bb.weights); b.loadings = D(bb.loadings); b.r2 = D(bb.r2); b.paths = D(bb.paths);
+    b.total = D(bb.totalfx); b.crossloadings = D(bb.crossl); b.score_coef = D(bb.coef); b.score_shift = D(bb.shift);
+  }
   d->timer.begin(ST_SOLVE, st);
   solve_kernel<<<(unsigned)nb, SOLVE_THREADS, smem, st>>>(b);
   d->timer.end(st);
   CK(cudaGetLastError());
   return 0;
 }
-
-static size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 
 int plspm_fit(const plspm_model* m, const plspm_data* dc, int32_t scheme, double tol, int32_t max_iter, double* weights,
               double* loadings, double* r_squared, double* paths, double* total_effects, double* crossloadings,
@@ -898,45 +1052,36 @@ int plspm_fit(const plspm_model* m, const plspm_data* dc, int32_t scheme, double
   plspm_data* d = const_cast<plspm_data*>(dc);
   const HostModel& h = m->h;
   const int64_t N = d->N;
-  GramPlan gp;
-  if (int rc = plan_gram(d, 1, gp)) return rc;
-  const size_t gsz = (size_t)h.n_tiles * TILE, L = h.L, P = h.P;
-  size_t off = 0;
-  auto take = [&](size_t doubles) { size_t o = off; off += align_up(doubles * 8); return o; };
-  const size_t o_G = take(gsz), o_Gp = take(gsz * gp.n_chunks), o_cs = take(h.Ppad), o_csp = take((size_t)h.Ppad * gp.cs_chunks);
-  const size_t o_ws = take(h.ws_doubles), o_w = take(P), o_ld = take(P), o_r2 = take(L), o_pa = take(L * L);
-  const size_t o_to = take(L * L), o_cl = take(P * L), o_cf = take(h.Ppad), o_sh = take(L), o_it = take(2);
-  const size_t o_sc = take(scores ? (size_t)N * L : 1);
-  if (int rc = ws_reserve(d, off)) return rc;
+  const size_t L = h.L, P = h.P;
+  BatchPlan bp;
+  if (int rc = plan_batch(d, 1, bp)) return rc;
+  const BatchBuffers bb = layout_batch(d, 1, bp, false, false, false, true, scores != nullptr);
+  if (int rc = ws_reserve(d, bb.total)) return rc;
   char* base = (char*)d->ws.ptr;
   auto D = [&](size_t o) { return (double*)(base + o); };
   cudaStream_t st = d->stream;
-  BatchOut o;
-  o.weights = D(o_w); o.loadings = D(o_ld); o.r2 = D(o_r2); o.paths = D(o_pa); o.total = D(o_to);
-  o.crossloadings = D(o_cl); o.score_coef = D(o_cf); o.score_shift = D(o_sh);
-  int* it_dev = (int*)D(o_it);
-  o.iters = it_dev; o.status = it_dev + 2;
-  if (int rc = run_batch(d, 1, nullptr, D(o_G), D(o_Gp), D(o_cs), D(o_csp), D(o_ws), scheme, tol, max_iter, gp, o)) return rc;
+  if (int rc = run_batch(d, 1, nullptr, bb, scheme, tol, max_iter, bp, nullptr, true)) return rc;
   if (scores) {
     d->timer.begin(ST_SCORES, st);
-    scores_kernel<<<d->sm_count * 8, 256, 0, st>>>(d->X, N, h.Ppad, h.L, m->dv.lv_off, m->dv.lv_k, o.score_coef,
-                                                   o.score_shift, D(o_sc));
+    scores_kernel<<<d->sm_count * 8, 256, 0, st>>>(d->X, N, h.Ppad, h.L, m->dv.lv_off, m->dv.lv_k, D(bb.coef),
+                                                   D(bb.shift), D(bb.scores));
     d->timer.end(st);
     CK(cudaGetLastError());
   }
-  int host_is[4] = {0, 0, 0, 0};
-  CK(cudaMemcpyAsync(host_is, it_dev, sizeof(host_is), cudaMemcpyDeviceToHost, st));
-  if (weights) CK(cudaMemcpyAsync(weights, o.weights, P * 8, cudaMemcpyDeviceToHost, st));
-  if (loadings) CK(cudaMemcpyAsync(loadings, o.loadings, P * 8, cudaMemcpyDeviceToHost, st));
-  if (r_squared) CK(cudaMemcpyAsync(r_squared, o.r2, L * 8, cudaMemcpyDeviceToHost, st));
-  if (paths) CK(cudaMemcpyAsync(paths, o.paths, L * L * 8, cudaMemcpyDeviceToHost, st));
-  if (total_effects) CK(cudaMemcpyAsync(total_effects, o.total, L * L * 8, cudaMemcpyDeviceToHost, st));
-  if (crossloadings) CK(cudaMemcpyAsync(crossloadings, o.crossloadings, P * L * 8, cudaMemcpyDeviceToHost, st));
-  if (scores) CK(cudaMemcpyAsync(scores, D(o_sc), (size_t)N * L * 8, cudaMemcpyDeviceToHost, st));
+  int host_it = 0, host_st = 0;
+  CK(cudaMemcpyAsync(&host_it, base + bb.iters, 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(&host_st, base + bb.status, 4, cudaMemcpyDeviceToHost, st));
+  if (weights) CK(cudaMemcpyAsync(weights, D(bb.weights), P * 8, cudaMemcpyDeviceToHost, st));
+  if (loadings) CK(cudaMemcpyAsync(loadings, D(bb.loadings), P * 8, cudaMemcpyDeviceToHost, st));
+  if (r_squared) CK(cudaMemcpyAsync(r_squared, D(bb.r2), L * 8, cudaMemcpyDeviceToHost, st));
+  if (paths) CK(cudaMemcpyAsync(paths, D(bb.paths), L * L * 8, cudaMemcpyDeviceToHost, st));
+  if (total_effects) CK(cudaMemcpyAsync(total_effects, D(bb.totalfx), L * L * 8, cudaMemcpyDeviceToHost, st));
+  if (crossloadings) CK(cudaMemcpyAsync(crossloadings, D(bb.crossl), P * L * 8, cudaMemcpyDeviceToHost, st));
+  if (scores) CK(cudaMemcpyAsync(scores, D(bb.scores), (size_t)N * L * 8, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   d->timer.collect();
-  if (iters) *iters = host_is[0];
-  if (status) *status = host_is[2];
+  if (iters) *iters = host_it;
+  if (status) *status = host_st;
   return PLSPM_OK;
 }
 
@@ -950,50 +1095,35 @@ int plspm_bootstrap(const plspm_model* m, const plspm_data* dc, int32_t scheme, 
   plspm_data* d = const_cast<plspm_data*>(dc);
   const HostModel& h = m->h;
   const int64_t N = d->N;
-  const size_t gsz = (size_t)h.n_tiles * TILE, n_out = h.n_out();
+  const size_t n_out = h.n_out();
   if (idx)
     for (int64_t e = 0; e < rep_count * N; ++e)
       if (idx[e] < 0 || idx[e] >= N) return fail(PLSPM_ERR_INVALID, "resample index out of range");
   // batch size: bound the workspace (~1.5 GB) and keep the Gram grid a whole number of waves
-  const size_t per_rep = (size_t)N * 4 + (gsz + h.Ppad + h.ws_doubles + n_out) * 8 + (idx ? (size_t)N * 4 : 0) + 64;
+  const size_t per_rep = (size_t)N * 4 + ((size_t)h.n_tiles * TILE + (h.full ? 0 : (size_t)h.n_cross * TILE) +
+                                          2 * h.Ppad + h.ws_doubles + n_out) * 8 + (idx ? (size_t)N * 4 : 0) + 64;
   int64_t nb_max = std::max<int64_t>(1, (int64_t)((size_t)1536 * 1024 * 1024 / per_rep));
   nb_max = std::min<int64_t>(nb_max, rep_count);
   const int64_t wave = (int64_t)d->sm_count * GRAM_WARPS;  // warp items per wave
-  if (nb_max * h.n_tg > wave) {
-    int64_t waves = nb_max * h.n_tg / wave;
-    nb_max = std::max<int64_t>(1, waves * wave / h.n_tg);
+  const int64_t items_per_rep = h.full ? h.n_tg : std::max(h.n_tg, h.n_tg_cross);
+  if (nb_max * items_per_rep > wave) {
+    int64_t waves = nb_max * items_per_rep / wave;
+    nb_max = std::max<int64_t>(1, waves * wave / items_per_rep);
   }
-  GramPlan gp;
-  if (int rc = plan_gram(d, nb_max, gp)) return rc;
-  size_t off = 0;
-  auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return o; };
-  const size_t o_cnt = take((size_t)nb_max * N * 4), o_idx = take(idx ? (size_t)nb_max * N * 4 : 8);
-  const size_t o_G = take((size_t)nb_max * gsz * 8), o_Gp = take(gp.n_chunks > 1 ? (size_t)nb_max * gsz * gp.n_chunks * 8 : 8);
-  const size_t o_cs = take((size_t)nb_max * h.Ppad * 8), o_csp = take((size_t)nb_max * h.Ppad * gp.cs_chunks * 8);
-  const size_t o_ws = take((size_t)nb_max * h.ws_doubles * 8), o_out = take(out_is_device ? 8 : (size_t)nb_max * n_out * 8);
-  const size_t o_it = take((size_t)nb_max * 4), o_st = take((size_t)nb_max * 4);
-  if (int rc = ws_reserve(d, off)) return rc;
+  BatchPlan bp;
+  if (int rc = plan_batch(d, nb_max, bp)) return rc;
+  const BatchBuffers bb = layout_batch(d, nb_max, bp, true, idx != nullptr, out_is_device != 0, false, false);
+  if (int rc = ws_reserve(d, bb.total)) return rc;
   char* base = (char*)d->ws.ptr;
   cudaStream_t st = d->stream;
   for (int64_t b0 = 0; b0 < rep_count; b0 += nb_max) {
     const int64_t nb = std::min(nb_max, rep_count - b0);
-    GramPlan g2 = gp;
-    if (nb != nb_max) {
-      if (int rc = plan_gram(d, nb, g2)) return rc;
-      if (g2.n_chunks > gp.n_chunks) {
-        GramPlan keep = g2;
-        g2 = gp;
-        g2.n_groups = (nb * h.n_tg + GRAM_WARPS - 1) / GRAM_WARPS;
-        g2.cs_chunks = keep.cs_chunks; g2.cs_chunk_rows = keep.cs_chunk_rows;
-      }
-      const int64_t cap = std::max<int64_t>(1, nb_max * gp.cs_chunks / nb);  // cspart was sized for (nb_max, gp)
-      if (g2.cs_chunks > cap) plan_colsum(d, nb, (int)cap, g2);
-    }
-    uint32_t* cnt = (uint32_t*)(base + o_cnt);
+    // a short last batch reuses the plan (and therefore the workspace layout) of a full one
+    uint32_t* cnt = (uint32_t*)(base + bb.counts);
     int32_t* idx_dev = nullptr;
     CK(cudaMemsetAsync(cnt, 0, (size_t)nb * N * 4, st));
     if (idx) {
-      idx_dev = (int32_t*)(base + o_idx);
+      idx_dev = (int32_t*)(base + bb.idx);
       CK(cudaMemcpyAsync(idx_dev, idx + b0 * N, (size_t)nb * N * 4, cudaMemcpyHostToDevice, st));
     }
     const int64_t threads = ((N + 3) / 4) * nb;
@@ -1001,17 +1131,12 @@ int plspm_bootstrap(const plspm_model* m, const plspm_data* dc, int32_t scheme, 
     counts_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(cnt, idx_dev, N, nb, rep_begin + b0, seed);
     d->timer.end(st);
     CK(cudaGetLastError());
-    BatchOut o;
-    o.out_rows = out_is_device ? out + (size_t)b0 * n_out : (double*)(base + o_out);
-    o.iters = (int*)(base + o_it);
-    o.status = (int*)(base + o_st);
-    if (int rc = run_batch(d, nb, cnt, (double*)(base + o_G), (double*)(base + o_Gp), (double*)(base + o_cs),
-                           (double*)(base + o_csp), (double*)(base + o_ws), scheme, tol, max_iter, g2, o))
-      return rc;
+    double* rows = out_is_device ? out + (size_t)b0 * n_out : (double*)(base + bb.out);
+    if (int rc = run_batch(d, nb, cnt, bb, scheme, tol, max_iter, bp, rows, false)) return rc;
     if (!out_is_device)
-      CK(cudaMemcpyAsync(out + (size_t)b0 * n_out, o.out_rows, (size_t)nb * n_out * 8, cudaMemcpyDeviceToHost, st));
-    if (iters) CK(cudaMemcpyAsync(iters + b0, o.iters, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
-    if (status) CK(cudaMemcpyAsync(status + b0, o.status, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(out + (size_t)b0 * n_out, rows, (size_t)nb * n_out * 8, cudaMemcpyDeviceToHost, st));
+    if (iters) CK(cudaMemcpyAsync(iters + b0, base + bb.iters, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
+    if (status) CK(cudaMemcpyAsync(status + b0, base + bb.status, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     d->timer.collect();
   }

@@ -13,6 +13,7 @@ ModelView HostModel::host_view() const {
   v.L = L; v.P = P; v.Ppad = Ppad; v.ns = ns; v.scaled = scaled; v.full = full;
   v.n_tiles = n_tiles; v.n_tg = n_tg; v.n_pairs = n_pairs; v.n_v = n_v; v.n_eff = n_eff;
   v.max_deg = max_deg; v.ws_doubles = ws_doubles; v.kmax = kmax;
+  v.ng = ng; v.n_cross = n_cross; v.n_tg_cross = n_tg_cross;
   v.lv_off = lv_off.data(); v.lv_k = lv_k.data(); v.lv_mode = lv_mode.data();
   v.col_lv = col_lv.data(); v.col_src = col_src.data(); v.path = path.data();
   v.tile_sa = tile_sa.data(); v.tile_sb = tile_sb.data(); v.tile_of = tile_of.data();
@@ -119,22 +120,31 @@ int build_model(int L, const int32_t* block_sizes, const int8_t* modes, const in
   m.n_pairs = (int)m.pair_l.size();
   m.n_v = voff;
 
-  // Gram tiles
-  bool full = (tile_policy != TILES_SPARSE);  // TILES_AUTO == full until the sparse sign pass exists
+  // Gram tiles.  Sparse = only the slot pairs of LV pairs the iteration touches, plus a P x L
+  // cross-moment pass for the sign vote; AUTO picks whichever costs fewer fp64 FMAs per row.
+  m.ng = (L + SLOT - 1) / SLOT;
+  m.n_cross = m.ns * m.ng;
+  m.n_tg_cross = (m.n_cross + 31) / 32;
+  std::set<std::pair<int, int>> sparse_tiles, tiles;  // (sa, sb) with sa >= sb
+  {
+    auto add_lv_pair = [&](int l, int j) {
+      for (int a = m.lv_off[l] / SLOT; a < m.lv_off[l + 1] / SLOT; ++a)
+        for (int b = m.lv_off[j] / SLOT; b < m.lv_off[j + 1] / SLOT; ++b)
+          sparse_tiles.insert({std::max(a, b), std::min(a, b)});
+    };
+    for (int l = 0; l < L; ++l) add_lv_pair(l, l);
+    for (auto& pr : und) add_lv_pair(pr.first, pr.second);
+  }
+  const double cost_full = 0.5 * m.ns * (m.ns + 1);
+  const double cost_sparse = (double)sparse_tiles.size() + 1.15 * m.n_cross;
+  bool full = (tile_policy == TILES_FULL) || (tile_policy == TILES_AUTO && cost_sparse > 0.8 * cost_full);
   m.full = full ? 1 : 0;
   m.tile_of.assign((size_t)m.ns * m.ns, -1);
-  std::set<std::pair<int, int>> tiles;  // (sa, sb) with sa >= sb
   if (full) {
     for (int a = 0; a < m.ns; ++a)
       for (int b = 0; b <= a; ++b) tiles.insert({a, b});
   } else {
-    auto add_lv_pair = [&](int l, int j) {
-      for (int a = m.lv_off[l] / SLOT; a < m.lv_off[l + 1] / SLOT; ++a)
-        for (int b = m.lv_off[j] / SLOT; b < m.lv_off[j + 1] / SLOT; ++b)
-          tiles.insert({std::max(a, b), std::min(a, b)});
-    };
-    for (int l = 0; l < L; ++l) add_lv_pair(l, l);
-    for (auto& pr : und) add_lv_pair(pr.first, pr.second);
+    tiles = sparse_tiles;
   }
   for (auto& t : tiles) {
     int id = (int)m.tile_sa.size();

@@ -24,6 +24,7 @@ enum TilePolicy { TILES_AUTO = 0, TILES_FULL = 1, TILES_SPARSE = 2 };
 // pointers in the emulation.
 struct ModelView {
   int L, P, Ppad, ns, scaled, full, n_tiles, n_tg, n_pairs, n_v, n_eff, max_deg, ws_doubles, kmax;
+  int ng, n_cross, n_tg_cross;              // cross-moment tiles: ns x ng tiles of 8 MVs x 8 LVs (sparse tile sets)
   const int *lv_off, *lv_k, *lv_mode, *col_lv, *col_src;
   const int8_t* path;                       // [L*L] path[i*L+j]==1 : j -> i
   const int *tile_sa, *tile_sb, *tile_of;   // tile list and ns*ns lookup (see tile_of encoding)
@@ -38,6 +39,10 @@ struct ModelView {
 struct HostModel {
   int L = 0, P = 0, Ppad = 0, ns = 0, scaled = 0, full = 0;
   int n_tiles = 0, n_tg = 0, n_pairs = 0, n_v = 0, n_eff = 0, max_deg = 0, ws_doubles = 0, kmax = 0;
+  // Sparse tile sets do not hold cov(x_p, score_l) for every (p, l), which the sign vote needs
+  // (quirk Q6); a second streaming pass accumulates those P x L cross moments in tiles of
+  // 8 MVs x 8 LVs: tile c = sa * ng + g covers slot sa and LVs 8g..8g+7.
+  int ng = 0, n_cross = 0, n_tg_cross = 0;
   std::vector<int> lv_off, lv_k, lv_mode;   // [L+1] padded column offset, [L] block size, [L] mode
   std::vector<int> col_lv, col_src;         // [Ppad] LV of a padded column (-1 = padding), source column
   std::vector<int> src_col;                 // [P] padded column of source column p

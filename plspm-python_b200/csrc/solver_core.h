@@ -48,7 +48,11 @@ struct SolveArgs {
   int scheme;
   double tol;
   int max_iter;
-  const int* ext_votes;  // [L] sign votes computed elsewhere (sparse tile sets), or null
+  const int* ext_votes;  // unused (kept for layout compatibility)
+  int phase;             // 0: everything (full tile set); 1: stop after the final weights (writes wf_out);
+                         // 2: everything, cov(x_p, score_l) taken from the cross-moment tiles
+  const double* cross;   // [n_cross*64] raw sum_i c_i x~_ip (x~_i . wf_l) tiles (phase 2)
+  double* wf_out;        // [Ppad] final normalised weights, padded layout (phase 1)
   double* ws;            // [M.ws_doubles] global scratch private to this CTA
   // outputs; any pointer may be null
   double* out_row;        // [2P+L+2n_eff] weights | r_squared | total effects | direct effects | loadings
@@ -325,21 +329,36 @@ PL_HD void solve_replicate(const SolveArgs& A, double* smem) {
     u[p] = (l >= 0) ? w[p] * dinv[l] : 0.0;  // wf: scores have unit population variance
   }
   for (int l = tid; l < L; l += nt) votes[l] = 0;
-  PL_SYNC();
-  if (A.ext_votes) {
-    for (int l = tid; l < L; l += nt) votes[l] = A.ext_votes[l];
-  } else {
-    // cov(x_p, score_l) for ALL (p, l): every manifest variable votes on every LV (quirk Q6)
-    for (int t = tid; t < Ppad * L; t += nt) {
-      int p = t / L, l = t - p * L;
-      if (M.col_lv[p] < 0) continue;
-      int o = M.lv_off[l];
-      double acc = 0.0;
-      for (int c = 0; c < M.lv_k[l]; ++c) acc += PL_S(p, o + c) * u[o + c];
-      if (A.crossloadings) A.crossloadings[(size_t)M.col_src[p] * L + l] = acc / sqrt(PL_S(p, p));
-      // copysign(1, cor): +1 for cor >= +0, -1 for cor < 0 or -0 (weights.py:63-64); NaN does not vote
-      if (acc == acc) vote_add(votes, l, signbit(acc) ? -1 : 1);
+  if (A.phase == 1) {  // sparse tile set, first pass: hand the weights to the cross-moment kernel
+    for (int p = tid; p < Ppad; p += nt) A.wf_out[p] = u[p];
+    if (tid == 0) {
+      if (A.iters) *A.iters = iteration;
+      if (A.status) *A.status = status;
     }
+    return;
+  }
+  if (A.phase == 2)  // mean of the un-centred score: sum_q m_q wf_q (bsum is free after the init)
+    for (int l = tid; l < L; l += nt) {
+      double sh = 0.0;
+      for (int r = 0; r < M.lv_k[l]; ++r) sh += m[M.lv_off[l] + r] * u[M.lv_off[l] + r];
+      bsum[l] = sh;
+    }
+  PL_SYNC();
+  // cov(x_p, score_l) for ALL (p, l): every manifest variable votes on every LV (quirk Q6)
+  for (int t = tid; t < Ppad * L; t += nt) {
+    int p = t / L, l = t - p * L;
+    if (M.col_lv[p] < 0) continue;
+    double acc = 0.0;
+    if (A.phase == 2) {
+      const double raw = A.cross[((size_t)(p >> 3) * M.ng + (l >> 3)) * TILE + (p & 7) * SLOT + (l & 7)];
+      acc = (raw * invN - m[p] * bsum[l]) * iss;
+    } else {
+      int o = M.lv_off[l];
+      for (int c = 0; c < M.lv_k[l]; ++c) acc += PL_S(p, o + c) * u[o + c];
+    }
+    if (A.crossloadings) A.crossloadings[(size_t)M.col_src[p] * L + l] = acc / sqrt(PL_S(p, p));
+    // copysign(1, cor): +1 for cor >= +0, -1 for cor < 0 or -0 (weights.py:63-64); NaN does not vote
+    if (acc == acc) vote_add(votes, l, signbit(acc) ? -1 : 1);
   }
   PL_SYNC();
   for (int l = tid; l < L; l += nt) sgn[l] = (votes[l] < 0) ? -1.0 : 1.0;
@@ -423,7 +442,7 @@ PL_HD void solve_replicate(const SolveArgs& A, double* smem) {
     if (A.paths) A.paths[e] = Bm[e];
     if (A.total) A.total[e] = T[e];
   }
-  if (A.crossloadings && !A.ext_votes) {
+  if (A.crossloadings) {
     PL_SYNC();
     for (int t = tid; t < P * L; t += nt) A.crossloadings[t] *= sgn[t % L];
   }

@@ -228,7 +228,7 @@ def resample_indices(seed: int, replicate: int, N: int) -> np.ndarray:
     return out
 
 
-STAGES = ("counts", "gram", "reduce", "solve", "scores", "upload", "colsum")
+STAGES = ("counts", "gram", "reduce", "solve", "scores", "upload", "colsum", "cross")
 
 
 def profile_reset():

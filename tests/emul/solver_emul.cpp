@@ -70,7 +70,29 @@ extern "C" int emul_fit(int L, const int32_t* block_sizes, const int8_t* modes, 
   A.out_row = out_row; A.weights = weights; A.loadings = loadings; A.r2 = r2; A.paths = paths; A.total = total;
   A.crossloadings = crossloadings; A.score_coef = coef.data(); A.score_shift = shift.data();
   A.iters = iters; A.status = status;
-  solve_replicate(A, smem.data());
+  std::vector<double> wf(Pp, 0.0), cross((size_t)m.n_cross * TILE, 0.0);
+  if (m.full) {
+    A.phase = 0;
+    solve_replicate(A, smem.data());
+  } else {
+    // sparse tile set: weights first, then the P x L cross-moment pass, then the full solve
+    A.phase = 1; A.wf_out = wf.data();
+    solve_replicate(A, smem.data());
+    for (int64_t i = 0; i < N; ++i) {
+      if (cnt[i] == 0.0) continue;
+      const double* x = &Xs[i * Pp];
+      for (int l = 0; l < L; ++l) {
+        double sc = 0.0;
+        for (int c = m.lv_off[l]; c < m.lv_off[l + 1]; ++c) sc += x[c] * wf[c];
+        sc *= cnt[i];
+        for (int p = 0; p < Pp; ++p)
+          cross[((size_t)(p >> 3) * m.ng + (l >> 3)) * TILE + (p & 7) * SLOT + (l & 7)] += x[p] * sc;
+      }
+    }
+    std::fill(smem.begin(), smem.end(), 0.0);
+    A.phase = 2; A.cross = cross.data();
+    solve_replicate(A, smem.data());
+  }
   if (scores && !idx)
     for (int64_t i = 0; i < N; ++i)
       for (int l = 0; l < L; ++l) {

@@ -191,3 +191,68 @@ def test_medium_size_properties(eng):
     orows, oiters, _ = orc.bootstrap(X, idx, [K] * L, [0] * L, path, "factorial", True)
     np.testing.assert_array_equal(iters, oiters)
     np.testing.assert_allclose(rows, orows, rtol=REL, atol=1e-9)
+
+
+@pytest.mark.parametrize("case", ("syn_a", "syn_b", "syn_d", "syn_e", "syn_f", "syn_g"))
+def test_sparse_tile_policy_synthetic(eng, syn, case):
+    """TILES_SPARSE: only the Gram tiles the iteration needs + the P x L cross-moment pass (sign vote)."""
+    N, L, K, seed = (int(v) for v in syn[case + "/gen"])
+    X, path = make_synthetic(N, L, K, seed, reverse_blocks=tuple(int(v) for v in syn[case + "/reverse"]))
+    mode = 0 if str(syn[case + "/mode"]) == "A" else 1
+    scheme, scaled = str(syn[case + "/scheme"]), bool(syn[case + "/scaled"])
+    model = eng.Model([K] * L, [mode] * L, path, scaled, tile_policy=2)
+    assert not model.full_tiles
+    data = eng.Data(model, X)
+    got = eng.fit(model, data, scheme)
+    check_fit(got, orc.fit(X, [K] * L, [mode] * L, path, scheme, scaled))
+    np.testing.assert_allclose(got["weights"], syn[case + "/weights"], rtol=REL)
+    idx = np.random.default_rng(3).integers(0, N, (9, N), dtype=np.int32)
+    rows, status, iters = eng.bootstrap(model, data, scheme, 0, 9, idx=idx)
+    orows, oiters, _ = orc.bootstrap(X, idx, [K] * L, [mode] * L, path, scheme, scaled)
+    np.testing.assert_array_equal(iters, oiters)
+    np.testing.assert_allclose(rows, orows, rtol=REL, atol=1e-9)
+
+
+def test_sparse_equals_full_on_medium_model(eng):
+    """N=30k, 24 LVs x 8 MVs with two reverse-coded blocks: the sparse and the full tile sets must give the
+    same replicates (same Philox stream), and AUTO must pick the sparse set for this chain model."""
+    N, L, K = 30000, 24, 8
+    X, path = make_synthetic(N, L, K, seed=2, reverse_blocks=(5, 17))
+    outs = {}
+    for policy in (0, 1, 2):
+        model = eng.Model([K] * L, [0] * L, path, True, tile_policy=policy)
+        data = eng.Data(model, X)
+        outs[policy] = (model.full_tiles, eng.fit(model, data, "centroid"),
+                        eng.bootstrap(model, data, "centroid", 100, 40, seed=3))
+    assert outs[1][0] and not outs[2][0] and not outs[0][0]
+    check_fit(outs[2][1], orc.fit(X, [K] * L, [0] * L, path, "centroid", True))
+    for policy in (0, 2):
+        np.testing.assert_array_equal(outs[policy][2][2], outs[1][2][2])
+        np.testing.assert_allclose(outs[policy][2][0], outs[1][2][0], rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(outs[policy][1]["scores"], outs[1][1]["scores"], rtol=1e-9, atol=1e-11)
+        np.testing.assert_allclose(outs[policy][1]["crossloadings"], outs[1][1]["crossloadings"], rtol=1e-9, atol=1e-12)
+
+
+def test_sparse_ragged_mixed_modes(eng):
+    rng = np.random.default_rng(8)
+    sizes = [3, 12, 1, 9, 2, 5, 7, 20, 4]
+    L = len(sizes)
+    path = np.zeros((L, L), dtype=np.int8)
+    for i in range(1, L):
+        path[i, i - 1] = 1
+    path[6, 2] = 1
+    eta = rng.standard_normal((4000, L))
+    for i in range(1, L):
+        eta[:, i] += 0.7 * eta[:, i - 1]
+    X = np.concatenate([eta[:, [l]] * rng.uniform(0.5, 1.0, (1, k)) * (-1 if l == 3 else 1)
+                        + 0.6 * rng.standard_normal((4000, k)) for l, k in enumerate(sizes)], axis=1)
+    modes = [0, 1, 0, 0, 0, 1, 0, 0, 1]
+    model = eng.Model(sizes, modes, path, True, tile_policy=2)
+    data = eng.Data(model, X)
+    for scheme in ("centroid", "path", "factorial"):
+        check_fit(eng.fit(model, data, scheme), orc.fit(X, sizes, modes, path, scheme, True))
+    idx = rng.integers(0, 4000, (7, 4000), dtype=np.int32)
+    rows, status, iters = eng.bootstrap(model, data, "path", 0, 7, idx=idx)
+    orows, oiters, _ = orc.bootstrap(X, idx, sizes, modes, path, "path", True)
+    np.testing.assert_array_equal(iters, oiters)
+    np.testing.assert_allclose(rows, orows, rtol=REL, atol=1e-9)

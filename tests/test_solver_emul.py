@@ -90,3 +90,40 @@ def test_model_tables(sat):
     assert info["P"] == 27 and info["Ppad"] == 48 and info["n_tiles"] == 21 and info["n_eff"] == 15
     pairs = orc.effect_pairs(sat["path"])
     assert [(int(f), int(t)) for f, t in zip(info["eff_from"], info["eff_to"])] == pairs
+
+
+@pytest.mark.parametrize("case", ("syn_b", "syn_d", "syn_e", "syn_f"))
+def test_sparse_tile_set_matches_oracle(syn, case):
+    """TILES_SPARSE (policy 2): only the Gram tiles the iteration needs + the P x L cross-moment pass."""
+    N, L, K, seed = (int(v) for v in syn[case + "/gen"])
+    X, path = make_synthetic(N, L, K, seed, reverse_blocks=tuple(int(v) for v in syn[case + "/reverse"]))
+    mode = 0 if str(syn[case + "/mode"]) == "A" else 1
+    scheme, scaled = str(syn[case + "/scheme"]), bool(syn[case + "/scaled"])
+    r = emul.fit(X, [K] * L, [mode] * L, path, scheme, scaled, tile_policy=2)
+    assert r["info"]["full"] == 0
+    check(r, orc.fit(X, [K] * L, [mode] * L, path, scheme, scaled), L, rel=1e-8)
+    idx = np.random.default_rng(1).integers(0, N, N, dtype=np.int32)
+    rb = emul.fit(X, [K] * L, [mode] * L, path, scheme, scaled, idx=idx, tile_policy=2)
+    row, it, st = orc.replicate_row(X, idx, [K] * L, [mode] * L, path, scheme, scaled)
+    assert rb["iterations"] == it
+    np.testing.assert_allclose(rb["out_row"], row, rtol=1e-7, atol=1e-10)
+
+
+def test_sparse_ragged_blocks():
+    rng = np.random.default_rng(8)
+    sizes = [3, 12, 1, 9, 2, 5, 7]
+    L = len(sizes)
+    path = np.zeros((L, L), dtype=np.int8)
+    for i in range(1, L):
+        path[i, i - 1] = 1
+    path[6, 2] = 1
+    eta = rng.standard_normal((500, L))
+    for i in range(1, L):
+        eta[:, i] += 0.7 * eta[:, i - 1]
+    X = np.concatenate([eta[:, [l]] * rng.uniform(0.5, 1.0, (1, k)) * (-1 if l == 3 else 1)
+                        + 0.6 * rng.standard_normal((500, k)) for l, k in enumerate(sizes)], axis=1)
+    modes = [0, 1, 0, 0, 0, 1, 0]
+    for scheme in ("centroid", "path"):
+        r = emul.fit(X, sizes, modes, path, scheme, True, tile_policy=2)
+        assert r["info"]["full"] == 0
+        check(r, orc.fit(X, sizes, modes, path, scheme, True), L, rel=1e-8)

@@ -19,16 +19,17 @@ ap.add_argument("--B", type=int, default=1184)
 ap.add_argument("--scheme", default="centroid")
 ap.add_argument("--mode", type=int, default=0)
 ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--policy", type=int, default=0)
 a = ap.parse_args()
 
 engine.set_device(0)
 t0 = time.time()
 X, path = make_synthetic(a.N, a.L, a.K, seed=0)
 print("gen %.1fs" % (time.time() - t0), flush=True)
-model = engine.Model([a.K] * a.L, [a.mode] * a.L, path, True)
+model = engine.Model([a.K] * a.L, [a.mode] * a.L, path, True, a.policy)
 t0 = time.time()
 data = engine.Data(model, X)
-print("upload %.3fs  tiles=%d tile_groups=%d" % (time.time() - t0, model.n_tiles, model.n_tile_groups), flush=True)
+print("upload %.3fs  tiles=%d tile_groups=%d full=%s" % (time.time() - t0, model.n_tiles, model.n_tile_groups, model.full_tiles), flush=True)
 t0 = time.time()
 f = engine.fit(model, data, a.scheme)
 print("fit %.4fs iters=%d status=%d" % (time.time() - t0, f["iterations"], f["status"]), flush=True)
