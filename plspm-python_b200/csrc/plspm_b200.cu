@@ -56,6 +56,73 @@ struct Profile {
 };
 static Profile g_prof;
 
+// Process-wide cache of large device buffers (per device): plspm_bootstrap_host() creates and
+// destroys a data handle per call, and cudaMalloc/cudaFree of the 0.2-1.5 GB buffers would
+// otherwise dominate the end-to-end time of a call.
+struct DevPool {
+  struct Block { void* p; size_t bytes; int device; };
+  std::mutex mu;
+  std::vector<Block> free_blocks;
+  size_t cached = 0;
+  static constexpr size_t kMaxCached = (size_t)12 << 30;
+  cudaError_t alloc(void** out, size_t bytes) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      int best = -1;
+      for (int i = 0; i < (int)free_blocks.size(); ++i) {
+        const Block& b = free_blocks[i];
+        if (b.device == dev && b.bytes >= bytes && b.bytes <= 2 * bytes + (1 << 20) &&
+            (best < 0 || b.bytes < free_blocks[best].bytes))
+          best = i;
+      }
+      if (best >= 0) {
+        *out = free_blocks[best].p;
+        cached -= free_blocks[best].bytes;
+        sizes.push_back({*out, free_blocks[best].bytes, dev});
+        free_blocks.erase(free_blocks.begin() + best);
+        return cudaSuccess;
+      }
+    }
+    cudaError_t e = cudaMalloc(out, bytes);
+    if (e != cudaSuccess) {  // release the cache and retry once
+      trim();
+      e = cudaMalloc(out, bytes);
+    }
+    if (e == cudaSuccess) {
+      std::lock_guard<std::mutex> lk(mu);
+      sizes.push_back({*out, bytes, dev});
+    }
+    return e;
+  }
+  void release(void* p) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(mu);
+    for (size_t i = 0; i < sizes.size(); ++i)
+      if (sizes[i].p == p) {
+        Block b = sizes[i];
+        sizes.erase(sizes.begin() + i);
+        if (cached + b.bytes <= kMaxCached) {
+          free_blocks.push_back(b);
+          cached += b.bytes;
+        } else {
+          cudaFree(p);
+        }
+        return;
+      }
+    cudaFree(p);
+  }
+  void trim() {
+    std::lock_guard<std::mutex> lk(mu);
+    for (auto& b : free_blocks) cudaFree(b.p);
+    free_blocks.clear();
+    cached = 0;
+  }
+  std::vector<Block> sizes;  // live blocks handed out
+};
+static DevPool g_pool;
+
 // A timed launch region: events on the launching stream; durations are collected when the
 // stream is synchronised at the end of the API call.
 struct StageTimer {
@@ -743,7 +810,7 @@ int plspm_model_query(const plspm_model* m, int32_t* info) {
   std::memset(info, 0, 16 * sizeof(int32_t));
   const HostModel& h = m->h;
   info[0] = h.L; info[1] = h.P; info[2] = h.Ppad; info[3] = h.n_tiles; info[4] = h.n_tg; info[5] = h.n_pairs;
-  info[6] = h.n_eff; info[7] = h.n_out(); info[8] = h.full; info[9] = h.scaled;
+  info[6] = h.n_eff; info[7] = h.n_out(); info[8] = h.full; info[9] = h.scaled; info[10] = h.n_cross;
   return PLSPM_OK;
 }
 
@@ -755,10 +822,10 @@ int plspm_model_effects(const plspm_model* m, int32_t* from, int32_t* to) {
 
 static int ws_reserve(plspm_data* d, size_t bytes) {
   if (d->ws.bytes >= bytes) return 0;
-  if (d->ws.ptr) CK(cudaFree(d->ws.ptr));
+  if (d->ws.ptr) g_pool.release(d->ws.ptr);
   d->ws.ptr = nullptr;
   d->ws.bytes = 0;
-  CK(cudaMalloc(&d->ws.ptr, bytes));
+  CK(g_pool.alloc(&d->ws.ptr, bytes));
   d->ws.bytes = bytes;
   return 0;
 }
@@ -789,11 +856,11 @@ int plspm_data_create(const plspm_model* m, const double* X, int64_t N, int64_t 
   const double* Xd = X;
   int rc = 0;
   auto body = [&]() -> int {
-    CK(cudaMalloc((void**)&d->X, (size_t)N * h.Ppad * sizeof(double)));
-    CK(cudaMalloc((void**)&d->mu, (size_t)h.Ppad * sizeof(double)));
+    CK(g_pool.alloc((void**)&d->X, (size_t)N * h.Ppad * sizeof(double)));
+    CK(g_pool.alloc((void**)&d->mu, (size_t)h.Ppad * sizeof(double)));
     CK(cudaMemsetAsync(d->mu, 0, (size_t)h.Ppad * sizeof(double), st));
     if (!x_is_device) {
-      CK(cudaMalloc((void**)&raw, (size_t)N * h.P * sizeof(double)));
+      CK(g_pool.alloc((void**)&raw, (size_t)N * h.P * sizeof(double)));
       CK(cudaMemcpy2DAsync(raw, (size_t)h.P * sizeof(double), X, (size_t)ld * sizeof(double),
                            (size_t)h.P * sizeof(double), (size_t)N, cudaMemcpyHostToDevice, st));
       Xd = raw;
@@ -802,9 +869,9 @@ int plspm_data_create(const plspm_model* m, const double* X, int64_t N, int64_t 
     const int nblocks = (int)std::min<int64_t>(1024, (N + 63) / 64);
     const int64_t rpb = (N + nblocks - 1) / nblocks;
     double* partial = nullptr;
-    CK(cudaMalloc((void**)&partial, (size_t)nblocks * h.P * sizeof(double)));
+    CK(g_pool.alloc((void**)&partial, (size_t)nblocks * h.P * sizeof(double)));
     int* src_col = nullptr;
-    CK(cudaMalloc((void**)&src_col, (size_t)h.P * sizeof(int)));
+    CK(g_pool.alloc((void**)&src_col, (size_t)h.P * sizeof(int)));
     CK(cudaMemcpyAsync(src_col, h.src_col.data(), (size_t)h.P * sizeof(int), cudaMemcpyHostToDevice, st));
     d->timer.begin(ST_UPLOAD, st);
     colsum_partial_kernel<<<nblocks, 256, 0, st>>>(Xd, N, ld, h.P, rpb, partial);
@@ -818,12 +885,12 @@ int plspm_data_create(const plspm_model* m, const double* X, int64_t N, int64_t 
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(st));
     d->timer.collect();
-    cudaFree(partial);
-    cudaFree(src_col);
+    g_pool.release(partial);
+    g_pool.release(src_col);
     return 0;
   };
   rc = body();
-  if (raw) cudaFree(raw);
+  if (raw) g_pool.release(raw);
   if (rc) return bail(rc);
   *out = d;
   return PLSPM_OK;
@@ -831,9 +898,9 @@ int plspm_data_create(const plspm_model* m, const double* X, int64_t N, int64_t 
 
 void plspm_data_destroy(plspm_data* d) {
   if (!d) return;
-  if (d->X) cudaFree(d->X);
-  if (d->mu) cudaFree(d->mu);
-  if (d->ws.ptr) cudaFree(d->ws.ptr);
+  if (d->X) g_pool.release(d->X);
+  if (d->mu) g_pool.release(d->mu);
+  if (d->ws.ptr) g_pool.release(d->ws.ptr);
   if (d->stream) cudaStreamDestroy(d->stream);
   delete d;
 }
