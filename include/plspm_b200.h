@@ -97,10 +97,15 @@ int plspm_resample_indices(uint64_t seed, int64_t replicate, int64_t N, int32_t*
 
 /* Instrumentation of the library's own stream since the last reset: device milliseconds per
  * stage measured with CUDA events around every launch, and kernel launch counts.
- * ms[8] / launches[8]: 0 counts, 1 gram, 2 chunk reduce, 3 solve, 4 scores, 5 upload kernels, 6 column sums,
- * 7 cross moments (sparse tile sets). */
+ * ms[12] / launches[12]: 0 counts, 1 gram, 2 chunk reduce, 3 solve, 4 scores, 5 upload kernels, 6 column
+ * sums, 7 cross moments (exact fp64 pass, or the fp16 GEMMs of the fast sign vote), 8 score generation
+ * for the fast sign vote. */
 int plspm_profile_reset(void);
 int plspm_profile_get(double* ms, int64_t* launches);
+
+/* Number of bootstrap replicates (since library load) whose low-precision tensor-core sign vote was
+ * undecided and which were therefore redone with exact fp64 cross moments. */
+int plspm_redo_count(int64_t* count);
 
 /* Pinned host memory for callers that want full-speed host<->device copies. */
 int plspm_host_alloc(void** ptr, int64_t bytes);

@@ -22,7 +22,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and up_to_date():
         return OUT
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SOURCES
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SOURCES + ["-lcublas"]
     subprocess.check_call(cmd)
     return OUT
 

@@ -15,6 +15,8 @@
 //   scores_kernel   single fit only: scores = X~ . coef - shift   (N x L, HBM-bound)
 //
 // Nothing here falls back to a CPU path: without a CUDA device every entry point fails.
+#include <cublas_v2.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -48,13 +50,14 @@ static int fail(int code, const std::string& msg) {
                   std::string(#expr) + ": " + cudaGetErrorString(e_));                             \
   } while (0)
 
-enum { ST_COUNTS = 0, ST_GRAM = 1, ST_REDUCE = 2, ST_SOLVE = 3, ST_SCORES = 4, ST_UPLOAD = 5, ST_COLSUM = 6, ST_CROSS = 7, ST_N = 8 };
+enum { ST_COUNTS = 0, ST_GRAM = 1, ST_REDUCE = 2, ST_SOLVE = 3, ST_SCORES = 4, ST_UPLOAD = 5, ST_COLSUM = 6, ST_CROSS = 7, ST_SCOREGEN = 8, ST_N = 12 };
 struct Profile {
   std::mutex mu;
   double ms[ST_N] = {0};
   int64_t launches[ST_N] = {0};
 };
 static Profile g_prof;
+static int64_t g_redo_count = 0;  // replicates redone exactly after an undecided low-precision vote
 
 // Process-wide cache of large device buffers (per device): plspm_bootstrap_host() creates and
 // destroys a data handle per call, and cudaMalloc/cudaFree of the 0.2-1.5 GB buffers would
@@ -178,6 +181,11 @@ struct plspm_data {
   int64_t N = 0;
   double* X = nullptr;   // [N][Ppad] slot layout, globally centred
   double* mu = nullptr;  // [Ppad]
+  // low-precision copy for the tensor-core sign vote (sparse tile sets): xh = x~ / sd (fp16)
+  __half* Xh = nullptr;      // [N][Ppad]
+  double* inv_sd = nullptr;  // [Ppad]
+  cublasHandle_t blas = nullptr;
+  bool fast_vote = false;    // the fp16 pass is worth trying on this data
   cudaStream_t stream = nullptr;
   Workspace ws;          // grown on demand, reused across calls
   StageTimer timer;
@@ -316,6 +324,102 @@ __global__ void relayout_kernel(const double* __restrict__ X, int64_t N, int64_t
   }
 }
 
+// column sums of squares of the centred slot-layout matrix -> 1/sd, and the fp16 copy xh = x~/sd
+__global__ void colsq_partial_kernel(const double* __restrict__ X, int64_t N, int Ppad, int64_t rows_per_block,
+                                     double* __restrict__ partial) {
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block, r1 = min(r0 + rows_per_block, N);
+  for (int p = threadIdx.x; p < Ppad; p += blockDim.x) {
+    double s = 0.0;
+    for (int64_t i = r0; i < r1; ++i) s = fma(X[i * Ppad + p], X[i * Ppad + p], s);
+    partial[(int64_t)blockIdx.x * Ppad + p] = s;
+  }
+}
+__global__ void inv_sd_kernel(const double* __restrict__ partial, int nblocks, int Ppad, int64_t N,
+                              double* __restrict__ inv_sd) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= Ppad) return;
+  double s = 0.0;
+  for (int b = 0; b < nblocks; ++b) s += partial[(int64_t)b * Ppad + p];
+  inv_sd[p] = s > 0.0 ? 1.0 / sqrt(s / (double)N) : 0.0;
+}
+__global__ void make_half_kernel(const double* __restrict__ X, int64_t N, int Ppad, const double* __restrict__ inv_sd,
+                                 __half* __restrict__ out) {
+  const int64_t total = N * Ppad;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x)
+    out[e] = __double2half(X[e] * inv_sd[e % Ppad]);
+}
+
+// Scores for the tensor-core sign vote (models whose blocks fit one slot, K <= 8):
+//   B[i - i0][b*L + l] = fp16( c_bi * (x~_i . wf_b,l - sh_b,l) )        rows [i0, i0 + rc) of one chunk.
+// Thread = (replicate lane, latent variable): it keeps the block weights of SG_RPT replicates in
+// registers and walks the rows of the CTA's tile, reading the row's block (8 doubles) once for all of
+// them.  t is computed in fp64; only the product with the multiplicity is rounded to fp16.
+constexpr int SG_ROWS = 32, SG_RPT = 4, SG_THREADS = 256;
+__global__ void __launch_bounds__(SG_THREADS) scoregen_kernel(const double* __restrict__ X,
+                                                              const uint32_t* __restrict__ counts,
+                                                              const double* __restrict__ wf,
+                                                              const double* __restrict__ sh, int64_t N, int Ppad, int L,
+                                                              const int* __restrict__ lv_off, int64_t nrep, int64_t i0,
+                                                              int rc, __half* __restrict__ B) {
+  extern __shared__ __align__(16) double sg_smem[];
+  double* xs = sg_smem;                                     // [SG_ROWS][Ppad]
+  float* cs = reinterpret_cast<float*>(xs + (size_t)SG_ROWS * Ppad);  // [reps_per_cta][SG_ROWS]
+  const int nbl = SG_THREADS / L;                           // replicate lanes per CTA
+  const int reps_per_cta = nbl * SG_RPT;
+  const int row0 = blockIdx.x * SG_ROWS;
+  const int64_t rep0 = (int64_t)blockIdx.y * reps_per_cta;
+  const int rows = min(SG_ROWS, rc - row0);
+  for (int e = threadIdx.x; e < SG_ROWS * Ppad; e += SG_THREADS) {
+    const int r = e / Ppad;
+    xs[e] = (r < rows) ? X[(i0 + row0) * Ppad + e] : 0.0;
+  }
+  for (int e = threadIdx.x; e < reps_per_cta * SG_ROWS; e += SG_THREADS) {
+    const int bl = e / SG_ROWS, r = e - bl * SG_ROWS;
+    const int64_t bb = rep0 + bl;
+    float c = 0.f;
+    if (r < rows && bb < nrep) c = counts ? (float)counts[bb * N + i0 + row0 + r] : 1.f;
+    cs[e] = c;
+  }
+  __syncthreads();
+  const int bl = threadIdx.x / L, l = threadIdx.x - bl * L;
+  if (bl >= nbl) return;
+  const int slot = lv_off[l] >> 3;
+  const int rot = (slot >> 1) & 3;  // rotated chunk order: the 64-byte slot stride would alias shared-memory banks
+  double w[SG_RPT][8], shv[SG_RPT];
+  bool ok[SG_RPT];
+#pragma unroll
+  for (int j = 0; j < SG_RPT; ++j) {
+    const int64_t bb = rep0 + bl * SG_RPT + j;
+    ok[j] = bb < nrep;
+    shv[j] = ok[j] ? sh[bb * L + l] : 0.0;
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) {
+      const int col = slot * SLOT + 2 * ((ch + rot) & 3);
+      w[j][2 * ch] = ok[j] ? wf[bb * Ppad + col] : 0.0;
+      w[j][2 * ch + 1] = ok[j] ? wf[bb * Ppad + col + 1] : 0.0;
+    }
+  }
+  const int64_t ldb = nrep * L;
+  for (int r = 0; r < rows; ++r) {
+    double x[8];
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) {
+      const double2 v = *reinterpret_cast<const double2*>(xs + (size_t)r * Ppad + slot * SLOT + 2 * ((ch + rot) & 3));
+      x[2 * ch] = v.x; x[2 * ch + 1] = v.y;
+    }
+#pragma unroll
+    for (int j = 0; j < SG_RPT; ++j) {
+      double t = -shv[j];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) t = fma(x[k], w[j][k], t);
+      if (ok[j]) {
+        const int64_t bb = rep0 + bl * SG_RPT + j;
+        B[(int64_t)(row0 + r) * ldb + bb * L + l] = __double2half((double)cs[(bl * SG_RPT + j) * SG_ROWS + r] * t);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // weighted Gram kernel
 // ------------------------------------------------------------------------------------------------
@@ -339,6 +443,7 @@ struct GramParams {
   int L, ng;
   const int *lv_off, *lv_k;
   const double* wf;         // [nrep][Ppad] final weights of every replicate
+  const int* rep_map;       // optional: item / n_tg -> replicate (exact redo of selected replicates)
 };
 
 __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
@@ -408,8 +513,9 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const GramParams 
 
   // ---- consumer warp: one (replicate, tile group); lane = one 8x8 tile ------------------------
   const int64_t item = item0 + warp;
-  const int64_t rep = item / p.n_tg;
-  const int tg = (int)(item - rep * p.n_tg);
+  const int64_t rep_pos = item / p.n_tg;
+  const int tg = (int)(item - rep_pos * p.n_tg);
+  const int64_t rep = p.rep_map ? (int64_t)p.rep_map[rep_pos] : rep_pos;
   int tile, sa, sb;
   if constexpr (CROSS) {
     // LV-group-major order: a warp covers (almost always) ONE group of 8 LVs and 32 row slots, so it
@@ -683,6 +789,9 @@ struct SolveBatch {
   int phase;                             // see SolveArgs::phase
   double* wf;                            // [nrep][Ppad] (sparse tile sets)
   const double* cross; int64_t cross_stride;
+  const float* fast_cross; const double* inv_sd; int64_t fast_nb;  // phase 3
+  double* sh;                            // [nrep][L] (phase 1 output)
+  const int* rep_map;                    // optional: block -> replicate
   double* out_rows; int64_t out_stride;  // may be null
   double *weights, *loadings, *r2, *paths, *total, *crossloadings, *score_coef, *score_shift;  // single fit
   int *iters, *status;
@@ -692,7 +801,7 @@ constexpr int SOLVE_THREADS = 128;
 
 __global__ void __launch_bounds__(SOLVE_THREADS) solve_kernel(const SolveBatch b) {
   extern __shared__ __align__(16) double solver_smem[];
-  const int64_t rep = blockIdx.x;
+  const int64_t rep = b.rep_map ? (int64_t)b.rep_map[blockIdx.x] : (int64_t)blockIdx.x;
   SolveArgs A;
   A.M = b.M;
   A.G = b.G + rep * b.g_stride;
@@ -706,6 +815,8 @@ __global__ void __launch_bounds__(SOLVE_THREADS) solve_kernel(const SolveBatch b
   A.phase = b.phase;
   A.wf_out = b.wf ? b.wf + rep * b.M.Ppad : nullptr;
   A.cross = b.cross ? b.cross + rep * b.cross_stride : nullptr;
+  A.fast_cross = b.fast_cross; A.inv_sd = b.inv_sd; A.fast_nb = b.fast_nb; A.fast_b = rep;
+  A.sh_out = b.sh ? b.sh + rep * b.M.L : nullptr;
   A.ws = b.ws + rep * (int64_t)b.M.ws_doubles;
   A.out_row = b.out_rows ? b.out_rows + rep * b.out_stride : nullptr;
   A.weights = b.weights; A.loadings = b.loadings; A.r2 = b.r2; A.paths = b.paths; A.total = b.total;
@@ -790,6 +901,7 @@ int plspm_model_create(int32_t L, const int32_t* block_sizes, const int8_t* mode
   rc |= upload_vec(m, h.pred_idx, &v.pred_idx);
   rc |= upload_vec(m, h.succ_begin, &v.succ_begin);
   rc |= upload_vec(m, h.succ_idx, &v.succ_idx);
+  rc |= upload_vec(m, h.omega, &v.omega);
   if (rc) {
     plspm_model_destroy(m);
     return PLSPM_ERR_CUDA;
@@ -883,6 +995,29 @@ int plspm_data_create(const plspm_model* m, const double* X, int64_t N, int64_t 
     relayout_kernel<<<d->sm_count * 8, 256, 0, st>>>(Xd, N, ld, h.Ppad, m->dv.col_src, d->mu, d->X);
     d->timer.end(st);
     CK(cudaGetLastError());
+    // fp16 copy for the tensor-core sign vote of sparse tile sets (PLSPM_VOTE=exact disables it)
+    static const bool vote_exact = getenv("PLSPM_VOTE") && std::string(getenv("PLSPM_VOTE")) == "exact";
+    if (!h.full && !vote_exact && N >= 4096 && h.kmax <= SLOT && h.L <= SG_THREADS) {
+      double* sq = nullptr;
+      CK(g_pool.alloc((void**)&sq, (size_t)nblocks * h.Ppad * sizeof(double)));
+      CK(g_pool.alloc((void**)&d->inv_sd, (size_t)h.Ppad * sizeof(double)));
+      CK(g_pool.alloc((void**)&d->Xh, (size_t)N * h.Ppad * sizeof(__half)));
+      d->timer.begin(ST_UPLOAD, st);
+      colsq_partial_kernel<<<nblocks, 256, 0, st>>>(d->X, N, h.Ppad, rpb, sq);
+      d->timer.end(st);
+      d->timer.begin(ST_UPLOAD, st);
+      inv_sd_kernel<<<(h.Ppad + 127) / 128, 128, 0, st>>>(sq, nblocks, h.Ppad, N, d->inv_sd);
+      d->timer.end(st);
+      d->timer.begin(ST_UPLOAD, st);
+      make_half_kernel<<<d->sm_count * 8, 256, 0, st>>>(d->X, N, h.Ppad, d->inv_sd, d->Xh);
+      d->timer.end(st);
+      CK(cudaGetLastError());
+      CK(cudaStreamSynchronize(st));
+      g_pool.release(sq);
+      if (cublasCreate(&d->blas) != CUBLAS_STATUS_SUCCESS) return fail(PLSPM_ERR_CUDA, "cublasCreate failed");
+      cublasSetStream(d->blas, st);
+      d->fast_vote = true;
+    }
     CK(cudaStreamSynchronize(st));
     d->timer.collect();
     g_pool.release(partial);
@@ -900,6 +1035,9 @@ void plspm_data_destroy(plspm_data* d) {
   if (!d) return;
   if (d->X) g_pool.release(d->X);
   if (d->mu) g_pool.release(d->mu);
+  if (d->Xh) g_pool.release(d->Xh);
+  if (d->inv_sd) g_pool.release(d->inv_sd);
+  if (d->blas) cublasDestroy(d->blas);
   if (d->ws.ptr) g_pool.release(d->ws.ptr);
   if (d->stream) cudaStreamDestroy(d->stream);
   delete d;
@@ -982,9 +1120,10 @@ static int plan_batch(const plspm_data* d, int64_t nb, BatchPlan& bp) {
 static size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 
 // Device workspace of one batch of up to nb replicates (offsets into plspm_data::ws).
+constexpr int FAST_RC = 4096;  // rows per tensor-core GEMM chunk (bounds the fp32 accumulation error)
 struct BatchBuffers {
   size_t total = 0;
-  size_t counts, idx, G, Gpart, colsum, cspart, ws, out, iters, status, wf, CG, CGpart;
+  size_t counts, idx, G, Gpart, colsum, cspart, ws, out, iters, status, wf, CG, CGpart, sh, BT, Cf, rep_map;
   // single-fit outputs
   size_t weights, loadings, r2, paths, totalfx, crossl, coef, shift, scores;
 };
@@ -1008,6 +1147,11 @@ static BatchBuffers layout_batch(const plspm_data* d, int64_t nb, const BatchPla
   b.wf = take(h.full ? 0 : (size_t)nb * h.Ppad * 8);
   b.CG = take(h.full ? 0 : (size_t)nb * csz);
   b.CGpart = take(!h.full && bp.cross.n_chunks > 1 ? (size_t)nb * csz * bp.cross.n_chunks : 0);
+  b.sh = take(h.full ? 0 : (size_t)nb * h.L * 8);
+  const bool fast = d->fast_vote && !single_fit;
+  b.BT = take(fast ? (size_t)nb * h.L * FAST_RC * sizeof(__half) : 0);
+  b.Cf = take(fast ? (size_t)nb * h.L * h.Ppad * sizeof(float) : 0);
+  b.rep_map = take((size_t)nb * 4);
   if (single_fit) {
     const size_t L = h.L, P = h.P;
     b.weights = take(P * 8); b.loadings = take(P * 8); b.r2 = take(L * 8); b.paths = take(L * L * 8);
@@ -1019,7 +1163,7 @@ static BatchBuffers layout_batch(const plspm_data* d, int64_t nb, const BatchPla
 }
 
 static int launch_stream(plspm_data* d, bool cross, int64_t nb, const uint32_t* counts_dev, const StreamPlan& sp,
-                         double* out_tiles, double* part_tiles, const double* wf) {
+                         double* out_tiles, double* part_tiles, const double* wf, const int* rep_map = nullptr) {
   const plspm_model* m = d->model;
   const HostModel& h = m->h;
   cudaStream_t st = d->stream;
@@ -1030,7 +1174,7 @@ static int launch_stream(plspm_data* d, bool cross, int64_t nb, const uint32_t* 
   p.tile_sa = m->dv.tile_sa; p.tile_sb = m->dv.tile_sb; p.lane_tile = m->dv.lane_tile;
   p.n_items = nb * p.n_tg; p.n_chunks = sp.n_chunks; p.chunk_rows = sp.chunk_rows; p.RT = sp.RT; p.stages = sp.stages;
   p.G = (sp.n_chunks > 1) ? part_tiles : out_tiles;
-  p.L = h.L; p.ng = h.ng; p.lv_off = m->dv.lv_off; p.lv_k = m->dv.lv_k; p.wf = wf;
+  p.L = h.L; p.ng = h.ng; p.lv_off = m->dv.lv_off; p.lv_k = m->dv.lv_k; p.wf = wf; p.rep_map = rep_map;
   const int64_t n_groups = (p.n_items + GRAM_WARPS - 1) / GRAM_WARPS;
   const int64_t grid = n_groups * sp.n_chunks;
   if (grid > 0x7fffffff) return fail(PLSPM_ERR_UNSUPPORTED, "batch too large for one launch");
@@ -1054,11 +1198,44 @@ static int launch_stream(plspm_data* d, bool cross, int64_t nb, const uint32_t* 
   return 0;
 }
 
+// Exact redo (fp64 cross moments) of the replicates the low-precision vote could not decide.
+static int redo_exact(plspm_data* d, int64_t n_list, const int* rep_map_dev, const uint32_t* counts_dev,
+                      const BatchBuffers& bb, int scheme, double tol, int max_iter, const BatchPlan& bp,
+                      double* out_rows) {
+  const plspm_model* m = d->model;
+  const HostModel& h = m->h;
+  cudaStream_t st = d->stream;
+  char* base = (char*)d->ws.ptr;
+  auto D = [&](size_t o) { return (double*)(base + o); };
+  StreamPlan sp = bp.cross;
+  sp.n_chunks = 1;  // partial buffers are laid out per replicate position; keep whole-row passes here
+  sp.chunk_rows = ((d->N + sp.RT - 1) / sp.RT) * sp.RT;
+  if (int rc = launch_stream(d, true, n_list, counts_dev, sp, D(bb.CG), D(bb.CGpart), D(bb.wf), rep_map_dev)) return rc;
+  SolveBatch b;
+  std::memset(&b, 0, sizeof(b));
+  b.M = m->dv;
+  b.G = D(bb.G); b.g_stride = (int64_t)h.n_tiles * TILE;
+  b.colsum = D(bb.colsum); b.cs_stride = h.Ppad;
+  b.mu = d->mu; b.N = (double)d->N; b.scheme = scheme; b.tol = tol; b.max_iter = max_iter;
+  b.ws = D(bb.ws);
+  b.iters = (int*)(base + bb.iters); b.status = (int*)(base + bb.status);
+  b.cross = D(bb.CG); b.cross_stride = (int64_t)h.n_cross * TILE;
+  b.phase = 2; b.rep_map = rep_map_dev;
+  b.out_rows = out_rows; b.out_stride = h.n_out();
+  const size_t smem = h.solver_smem_doubles() * sizeof(double);
+  d->timer.begin(ST_SOLVE, st);
+  solve_kernel<<<(unsigned)n_list, SOLVE_THREADS, smem, st>>>(b);
+  d->timer.end(st);
+  CK(cudaGetLastError());
+  return 0;
+}
+
 // Shared implementation of fit (counts == null, one "replicate") and bootstrap batches.
 static int run_batch(plspm_data* d, int64_t nb, const uint32_t* counts_dev, const BatchBuffers& bb, int scheme,
                      double tol, int max_iter, const BatchPlan& bp, double* out_rows, bool single_fit) {
   const plspm_model* m = d->model;
   const HostModel& h = m->h;
+  const bool use_fast = !h.full && d->fast_vote && !single_fit && (int64_t)nb * h.L < (1 << 30);
   cudaStream_t st = d->stream;
   char* base = (char*)d->ws.ptr;
   auto D = [&](size_t o) { return (double*)(base + o); };
@@ -1092,13 +1269,45 @@ static int run_batch(plspm_data* d, int64_t nb, const uint32_t* counts_dev, cons
   if (!h.full) {
     // sparse tile set: final weights first, then the P x L cross-moment pass for the sign vote
     b.phase = 1;
+    b.sh = D(bb.sh);
     d->timer.begin(ST_SOLVE, st);
     solve_kernel<<<(unsigned)nb, SOLVE_THREADS, smem, st>>>(b);
     d->timer.end(st);
     CK(cudaGetLastError());
-    if (int rc = launch_stream(d, true, nb, counts_dev, bp.cross, D(bb.CG), D(bb.CGpart), D(bb.wf))) return rc;
+    b.sh = nullptr;
+    if (use_fast) {
+      // tensor-core sign vote: E[p][b][l] = sum_i xh_ip * fp16(c_bi t_bil), fp32 accumulate, in chunks
+      // of FAST_RC rows (cuBLAS: a plain fp16 GEMM, m = nb*L, n = Ppad, k = rows of the chunk)
+      __half* BT = (__half*)(base + bb.BT);
+      float* Cf = (float*)(base + bb.Cf);
+      const int reps_per_cta = (SG_THREADS / h.L) * SG_RPT;
+      const size_t sg_smem = (size_t)SG_ROWS * h.Ppad * 8 + (size_t)reps_per_cta * SG_ROWS * 4;
+      CK(cudaFuncSetAttribute(scoregen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sg_smem));
+      const float one = 1.f, zero = 0.f;
+      for (int64_t i0 = 0; i0 < d->N; i0 += FAST_RC) {
+        const int rc = (int)std::min<int64_t>(FAST_RC, d->N - i0);
+        dim3 grid_sg((rc + SG_ROWS - 1) / SG_ROWS, (unsigned)((nb + reps_per_cta - 1) / reps_per_cta));
+        d->timer.begin(ST_SCOREGEN, st);
+        scoregen_kernel<<<grid_sg, SG_THREADS, sg_smem, st>>>(d->X, counts_dev, D(bb.wf), D(bb.sh), d->N, h.Ppad, h.L,
+                                                             m->dv.lv_off, nb, i0, rc, BT);
+        d->timer.end(st);
+        CK(cudaGetLastError());
+        // C[nb*L x Ppad] (+)= B^T-free NT product: A = scores stored [nb*L x rc] (column-major view of the
+        // row-major [rc][nb*L] buffer), B = xh chunk stored [Ppad x rc]
+        d->timer.begin(ST_CROSS, st);
+        cublasStatus_t cs = cublasGemmEx(d->blas, CUBLAS_OP_N, CUBLAS_OP_T, (int)(nb * h.L), h.Ppad, rc, &one, BT,
+                                         CUDA_R_16F, (int)(nb * h.L), d->Xh + i0 * h.Ppad, CUDA_R_16F, h.Ppad,
+                                         i0 == 0 ? &zero : &one, Cf, CUDA_R_32F, (int)(nb * h.L), CUBLAS_COMPUTE_32F,
+                                         CUBLAS_GEMM_DEFAULT);
+        d->timer.end(st);
+        if (cs != CUBLAS_STATUS_SUCCESS) return fail(PLSPM_ERR_CUDA, "cublasGemmEx failed: " + std::to_string((int)cs));
+      }
+      b.fast_cross = Cf; b.inv_sd = d->inv_sd; b.fast_nb = nb;
+    } else {
+      if (int rc = launch_stream(d, true, nb, counts_dev, bp.cross, D(bb.CG), D(bb.CGpart), D(bb.wf))) return rc;
+    }
   }
-  b.phase = h.full ? 0 : 2;
+  b.phase = h.full ? 0 : (use_fast ? 3 : 2);
   b.out_rows = out_rows; b.out_stride = h.n_out();
   if (single_fit) {
     b.weights = D(bb.weights); b.loadings = D(bb.loadings); b.r2 = D(bb.r2); b.paths = D(bb.paths);
@@ -1200,6 +1409,22 @@ int plspm_bootstrap(const plspm_model* m, const plspm_data* dc, int32_t scheme, 
     CK(cudaGetLastError());
     double* rows = out_is_device ? out + (size_t)b0 * n_out : (double*)(base + bb.out);
     if (int rc = run_batch(d, nb, cnt, bb, scheme, tol, max_iter, bp, rows, false)) return rc;
+    if (!h.full && d->fast_vote) {
+      // replicates whose low-precision sign vote was undecided are redone with exact fp64 cross moments
+      std::vector<int> st_host(nb);
+      CK(cudaMemcpyAsync(st_host.data(), base + bb.status, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      std::vector<int> redo;
+      for (int64_t r = 0; r < nb; ++r)
+        if (st_host[r] == STATUS_AMBIGUOUS) redo.push_back((int)r);
+      if (!redo.empty()) {
+        int* map_dev = (int*)(base + bb.rep_map);
+        CK(cudaMemcpyAsync(map_dev, redo.data(), redo.size() * 4, cudaMemcpyHostToDevice, st));
+        if (int rc = redo_exact(d, (int64_t)redo.size(), map_dev, cnt, bb, scheme, tol, max_iter, bp, rows)) return rc;
+        g_redo_count += (int64_t)redo.size();
+        if ((int64_t)redo.size() * 2 > nb) d->fast_vote = false;  // this data does not suit the fp16 vote
+      }
+    }
     if (!out_is_device)
       CK(cudaMemcpyAsync(out + (size_t)b0 * n_out, rows, (size_t)nb * n_out * 8, cudaMemcpyDeviceToHost, st));
     if (iters) CK(cudaMemcpyAsync(iters + b0, base + bb.iters, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
@@ -1244,6 +1469,12 @@ int plspm_profile_get(double* ms, int64_t* launches) {
     if (ms) ms[i] = g_prof.ms[i];
     if (launches) launches[i] = g_prof.launches[i];
   }
+  return PLSPM_OK;
+}
+
+int plspm_redo_count(int64_t* count) {
+  if (!count) return fail(PLSPM_ERR_INVALID, "null argument");
+  *count = g_redo_count;
   return PLSPM_OK;
 }
 

@@ -23,6 +23,7 @@ ModelView HostModel::host_view() const {
   v.eff_from = eff_from.data(); v.eff_to = eff_to.data(); v.chol_b_off = chol_b_off.data();
   v.pred_begin = pred_begin.data(); v.pred_idx = pred_idx.data();
   v.succ_begin = succ_begin.data(); v.succ_idx = succ_idx.data();
+  v.omega = omega.data();
   return v;
 }
 
@@ -152,6 +153,11 @@ int build_model(int L, const int32_t* block_sizes, const int8_t* modes, const in
     m.tile_sb.push_back(t.second);
     m.tile_of[(size_t)t.first * m.ns + t.second] = id;
     if (t.first != t.second) m.tile_of[(size_t)t.second * m.ns + t.first] = -(id + 2);
+  }
+  m.omega.assign((size_t)L * L, full ? 1 : 0);
+  if (!full) {
+    for (int l = 0; l < L; ++l) m.omega[(size_t)l * L + l] = 1;
+    for (auto& pr : und) m.omega[(size_t)pr.first * L + pr.second] = m.omega[(size_t)pr.second * L + pr.first] = 1;
   }
   m.n_tiles = (int)m.tile_sa.size();
   m.tile_owner.assign(m.n_tiles, 0);

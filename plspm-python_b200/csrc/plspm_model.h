@@ -17,7 +17,8 @@ constexpr int TILE = SLOT * SLOT;   // doubles per Gram tile
 
 enum Scheme { SCHEME_CENTROID = 0, SCHEME_FACTORIAL = 1, SCHEME_PATH = 2 };
 enum Mode { MODE_A = 0, MODE_B = 1 };
-enum Status { STATUS_OK = 0, STATUS_NOT_CONVERGED = 1, STATUS_SINGULAR = 2, STATUS_DEGENERATE = 3 };
+enum Status { STATUS_OK = 0, STATUS_NOT_CONVERGED = 1, STATUS_SINGULAR = 2, STATUS_DEGENERATE = 3,
+              STATUS_AMBIGUOUS = 16 /* internal: low-precision sign vote undecided, redo exactly */ };
 enum TilePolicy { TILES_AUTO = 0, TILES_FULL = 1, TILES_SPARSE = 2 };
 
 // Raw-pointer view; the pointers are device pointers in the CUDA library and host
@@ -34,6 +35,7 @@ struct ModelView {
   const int *eff_from, *eff_to;
   const int *chol_b_off;
   const int *pred_begin, *pred_idx, *succ_begin, *succ_idx;
+  const int8_t* omega;                      // [L*L] 1: the Gram tiles of LV pair (i, j) are computed
 };
 
 struct HostModel {
@@ -63,10 +65,11 @@ struct HostModel {
   std::vector<int> eff_from, eff_to;        // structurally reachable (from, to) pairs, reference row order
   std::vector<int> chol_b_off;              // [L] offset of the Mode-B Cholesky factor in the workspace, or -1
   std::vector<int> pred_begin, pred_idx, succ_begin, succ_idx;
+  std::vector<int8_t> omega;                // [L*L] LV pairs covered by the tile set
 
   int n_out() const { return 2 * P + L + 2 * n_eff; }
   // shared-memory doubles the solver needs (see solver_core.h layout)
-  size_t solver_smem_doubles() const { return (size_t)4 * Ppad + n_v + 4 * (size_t)L + 3 * (size_t)L * L + 40 + (L + 1) / 2 + 8; }
+  size_t solver_smem_doubles() const { return (size_t)4 * Ppad + n_v + 4 * (size_t)L + 3 * (size_t)L * L + 40 + 2 * ((L + 1) / 2) + 8; }
   ModelView host_view() const;
 };
 

@@ -50,7 +50,14 @@ struct SolveArgs {
   int max_iter;
   const int* ext_votes;  // unused (kept for layout compatibility)
   int phase;             // 0: everything (full tile set); 1: stop after the final weights (writes wf_out);
-                         // 2: everything, cov(x_p, score_l) taken from the cross-moment tiles
+                         // 2: everything, cov(x_p, score_l) taken from the cross-moment tiles;
+                         // 3: like 2, but LV pairs outside the tile set vote with the SIGN of a
+                         //    low-precision (fp16 tensor-core) cross moment when it is provably right,
+                         //    otherwise the replicate is handed back as STATUS_AMBIGUOUS
+  const float* fast_cross;  // [Ppad][fast_nb][L] fp32 sums of xh_ip * (c_i t_il) (phase 3)
+  const double* inv_sd;     // [Ppad] global 1/sd used to scale xh (phase 3)
+  int64_t fast_nb, fast_b;  // batch size and this replicate's position in fast_cross
+  double* sh_out;           // [L] score means sum_q m_q wf_q (phase 1)
   const double* cross;   // [n_cross*64] raw sum_i c_i x~_ip (x~_i . wf_l) tiles (phase 2)
   double* wf_out;        // [Ppad] final normalised weights, padded layout (phase 1)
   double* ws;            // [M.ws_doubles] global scratch private to this CTA
@@ -163,6 +170,7 @@ PL_HD void solve_replicate(const SolveArgs& A, double* smem) {
   double* red = Bm + (size_t)L * L;  // [40] reduction scratch + flags
   int* flag = (int*)(red + 34);      // [0] status
   int* votes = (int*)(red + 40);     // [L] ints
+  int* unc = votes + 2 * ((L + 1) / 2);  // [L] ints: undecided voters (phase 3)
 
   const double N = A.N, invN = 1.0 / A.N;
   const double a_fac = (N - 1.0) / N;  // 1/correction^2, weights.py:44 (treat(..)/correction)
@@ -331,6 +339,12 @@ PL_HD void solve_replicate(const SolveArgs& A, double* smem) {
   for (int l = tid; l < L; l += nt) votes[l] = 0;
   if (A.phase == 1) {  // sparse tile set, first pass: hand the weights to the cross-moment kernel
     for (int p = tid; p < Ppad; p += nt) A.wf_out[p] = u[p];
+    if (A.sh_out)
+      for (int l = tid; l < L; l += nt) {
+        double sh = 0.0;
+        for (int r = 0; r < M.lv_k[l]; ++r) sh += m[M.lv_off[l] + r] * u[M.lv_off[l] + r];
+        A.sh_out[l] = sh;
+      }
     if (tid == 0) {
       if (A.iters) *A.iters = iteration;
       if (A.status) *A.status = status;
@@ -343,12 +357,24 @@ PL_HD void solve_replicate(const SolveArgs& A, double* smem) {
       for (int r = 0; r < M.lv_k[l]; ++r) sh += m[M.lv_off[l] + r] * u[M.lv_off[l] + r];
       bsum[l] = sh;
     }
+  if (A.phase == 3)
+    for (int l = tid; l < L; l += nt) unc[l] = 0;
   PL_SYNC();
   // cov(x_p, score_l) for ALL (p, l): every manifest variable votes on every LV (quirk Q6)
   for (int t = tid; t < Ppad * L; t += nt) {
     int p = t / L, l = t - p * L;
     if (M.col_lv[p] < 0) continue;
     double acc = 0.0;
+    if (A.phase == 3 && !M.omega[M.col_lv[p] * L + l]) {
+      // E = sum_i xh_ip (c_i t_il) has the sign of cov(x_p, score_l); fp16 operands + fp32 tensor-core
+      // accumulation over <= 4096-row chunks give |fl(E) - E| <= gamma * sqrt(sum c xh^2) * sqrt(sum c t^2)
+      // (Cauchy-Schwarz); sum c t^2 = N / iss because the scores have unit variance on the treated scale
+      const double v = (double)A.fast_cross[((size_t)p * A.fast_nb + A.fast_b) * L + l];
+      const double bound = 2.0e-3 * sqrt(gram_raw(M, A.G, p, p)) * A.inv_sd[p] * sqrt(N / iss);
+      if (v - v == 0.0 && fabs(v) > bound) vote_add(votes, l, v < 0.0 ? -1 : 1);
+      else vote_add(unc, l, 1);
+      continue;
+    }
     if (A.phase == 2) {
       const double raw = A.cross[((size_t)(p >> 3) * M.ng + (l >> 3)) * TILE + (p & 7) * SLOT + (l & 7)];
       acc = (raw * invN - m[p] * bsum[l]) * iss;
@@ -361,6 +387,19 @@ PL_HD void solve_replicate(const SolveArgs& A, double* smem) {
     if (acc == acc) vote_add(votes, l, signbit(acc) ? -1 : 1);
   }
   PL_SYNC();
+  if (A.phase == 3) {
+    // vote = votes + (something in [-unc, +unc]); decided when the interval does not straddle zero
+    for (int l = tid; l < L; l += nt)
+      if (!(votes[l] - unc[l] >= 0 || votes[l] + unc[l] < 0)) flag[1] = 1;
+    PL_SYNC();
+    if (flag[1]) {
+      if (tid == 0) {
+        if (A.iters) *A.iters = iteration;
+        if (A.status) *A.status = (status == STATUS_OK) ? STATUS_AMBIGUOUS : status;
+      }
+      return;
+    }
+  }
   for (int l = tid; l < L; l += nt) sgn[l] = (votes[l] < 0) ? -1.0 : 1.0;
   PL_SYNC();
   // flip score correlations

@@ -21,7 +21,7 @@ EXPORTS = (
     "plspm_version", "plspm_last_error", "plspm_device_count", "plspm_set_device", "plspm_model_create",
     "plspm_model_destroy", "plspm_model_query", "plspm_model_effects", "plspm_data_create", "plspm_data_destroy",
     "plspm_fit", "plspm_bootstrap", "plspm_bootstrap_host", "plspm_resample_indices", "plspm_profile_reset",
-    "plspm_profile_get", "plspm_host_alloc", "plspm_host_free",
+    "plspm_profile_get", "plspm_host_alloc", "plspm_host_free", "plspm_redo_count",
 )
 
 _lib = None
@@ -62,6 +62,7 @@ def load():
                                          _c_i32p]
     lib.plspm_resample_indices.argtypes = [u64, i64, i64, _c_i32p]
     lib.plspm_profile_get.argtypes = [_c_dp, _c_i64p]
+    lib.plspm_redo_count.argtypes = [_c_i64p]
     lib.plspm_host_alloc.argtypes = [ctypes.POINTER(vp), i64]
     lib.plspm_host_free.argtypes = [vp]
     _lib = lib
@@ -229,7 +230,7 @@ def resample_indices(seed: int, replicate: int, N: int) -> np.ndarray:
     return out
 
 
-STAGES = ("counts", "gram", "reduce", "solve", "scores", "upload", "colsum", "cross")
+STAGES = ("counts", "gram", "reduce", "solve", "scores", "upload", "colsum", "cross", "scoregen")
 
 
 def profile_reset():
@@ -237,10 +238,17 @@ def profile_reset():
 
 
 def profile_get():
-    ms = np.zeros(8, dtype=np.float64)
-    n = np.zeros(8, dtype=np.int64)
+    ms = np.zeros(12, dtype=np.float64)
+    n = np.zeros(12, dtype=np.int64)
     _check(load().plspm_profile_get(_ptr(ms, _c_dp), _ptr(n, _c_i64p)))
     return {s: (float(ms[i]), int(n[i])) for i, s in enumerate(STAGES)}
+
+
+def redo_count() -> int:
+    """Replicates redone with exact cross moments after an undecided low-precision sign vote."""
+    n = ctypes.c_int64(0)
+    _check(load().plspm_redo_count(ctypes.byref(n)))
+    return int(n.value)
 
 
 def pinned_empty(shape, dtype=np.float64) -> np.ndarray:

@@ -73,3 +73,12 @@ def fit(X, block_sizes, modes, path, scheme, scaled, idx=None, tol=1e-6, max_ite
     out["status"] = int(status[0])
     out["info"] = info
     return out
+
+
+def set_vote_mode(mode: int):
+    """0: exact cross moments; 1: emulate the low-precision sign vote (solver phase 3) with a worst-case-ish error."""
+    lib().emul_set_vote_mode(int(mode))
+
+
+def last_ambiguous() -> bool:
+    return bool(lib().emul_last_ambiguous())

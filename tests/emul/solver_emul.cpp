@@ -7,6 +7,7 @@
 // sm_100a Gram kernel writes; the solver is the shipped source compiled for the host.
 #define PLSPM_HOST_EMUL 1
 #include <cstdint>
+#include <cmath>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -27,6 +28,11 @@ extern "C" int emul_model_info(int L, const int32_t* block_sizes, const int8_t* 
     for (int e = 0; e < m.n_eff; ++e) { eff_from[e] = m.eff_from[e]; eff_to[e] = m.eff_to[e]; }
   return 0;
 }
+
+static int g_vote_mode = 0;      // 0: exact cross moments; 1: emulate the low-precision vote (phase 3)
+static int g_last_ambiguous = 0;
+extern "C" void emul_set_vote_mode(int mode) { g_vote_mode = mode; }
+extern "C" int emul_last_ambiguous() { return g_last_ambiguous; }
 
 extern "C" int emul_fit(int L, const int32_t* block_sizes, const int8_t* modes, const int8_t* path, int scaled,
                         int tile_policy, const double* X, int64_t N, const int32_t* idx, int scheme, double tol,
@@ -76,8 +82,49 @@ extern "C" int emul_fit(int L, const int32_t* block_sizes, const int8_t* modes, 
     solve_replicate(A, smem.data());
   } else {
     // sparse tile set: weights first, then the P x L cross-moment pass, then the full solve
-    A.phase = 1; A.wf_out = wf.data();
+    std::vector<double> sh(L, 0.0);
+    A.phase = 1; A.wf_out = wf.data(); A.sh_out = sh.data();
     solve_replicate(A, smem.data());
+    g_last_ambiguous = 0;
+    bool need_exact = true;
+    if (g_vote_mode == 1) {
+      // emulate the fp16 tensor-core pass: E[p][l] = sum_i xh_ip c_i t_il with a perturbation of half the
+      // guaranteed error bound (alternating sign), stored as float
+      std::vector<double> inv_sd(Pp, 0.0), sumx2(Pp, 0.0), sumt2(L, 0.0);
+      for (int p = 0; p < Pp; ++p) {
+        double q = 0.0;
+        for (int64_t i = 0; i < N; ++i) q += Xs[i * Pp + p] * Xs[i * Pp + p];
+        inv_sd[p] = q > 0 ? 1.0 / std::sqrt(q / (double)N) : 0.0;
+      }
+      std::vector<double> E((size_t)Pp * L, 0.0);
+      for (int64_t i = 0; i < N; ++i) {
+        if (cnt[i] == 0.0) continue;
+        const double* x = &Xs[i * Pp];
+        for (int p = 0; p < Pp; ++p) sumx2[p] += cnt[i] * x[p] * inv_sd[p] * x[p] * inv_sd[p];
+        for (int l = 0; l < L; ++l) {
+          double t = -sh[l];
+          for (int c = m.lv_off[l]; c < m.lv_off[l + 1]; ++c) t += x[c] * wf[c];
+          sumt2[l] += cnt[i] * t * t;
+          for (int p = 0; p < Pp; ++p) E[(size_t)p * L + l] += x[p] * inv_sd[p] * cnt[i] * t;
+        }
+      }
+      std::vector<float> Ef((size_t)Pp * L);
+      for (int p = 0; p < Pp; ++p)
+        for (int l = 0; l < L; ++l) {
+          double pert = 1.0e-3 * std::sqrt(sumx2[p]) * std::sqrt(sumt2[l]) * (((p + l) & 1) ? 1.0 : -1.0);
+          Ef[(size_t)p * L + l] = (float)(E[(size_t)p * L + l] + pert);
+        }
+      std::fill(smem.begin(), smem.end(), 0.0);
+      A.phase = 3; A.fast_cross = Ef.data(); A.inv_sd = inv_sd.data(); A.fast_nb = 1; A.fast_b = 0;
+      int st_fast = 0;
+      int32_t* user_status = A.status;
+      A.status = &st_fast;
+      solve_replicate(A, smem.data());
+      A.status = user_status;
+      if (st_fast == STATUS_AMBIGUOUS) g_last_ambiguous = 1;
+      else { need_exact = false; if (status) *status = st_fast; }
+    }
+    if (need_exact)
     for (int64_t i = 0; i < N; ++i) {
       if (cnt[i] == 0.0) continue;
       const double* x = &Xs[i * Pp];
@@ -89,9 +136,11 @@ extern "C" int emul_fit(int L, const int32_t* block_sizes, const int8_t* modes, 
           cross[((size_t)(p >> 3) * m.ng + (l >> 3)) * TILE + (p & 7) * SLOT + (l & 7)] += x[p] * sc;
       }
     }
-    std::fill(smem.begin(), smem.end(), 0.0);
-    A.phase = 2; A.cross = cross.data();
-    solve_replicate(A, smem.data());
+    if (need_exact) {
+      std::fill(smem.begin(), smem.end(), 0.0);
+      A.phase = 2; A.cross = cross.data();
+      solve_replicate(A, smem.data());
+    }
   }
   if (scores && !idx)
     for (int64_t i = 0; i < N; ++i)

@@ -256,3 +256,37 @@ def test_sparse_ragged_mixed_modes(eng):
     orows, oiters, _ = orc.bootstrap(X, idx, sizes, modes, path, "path", True)
     np.testing.assert_array_equal(iters, oiters)
     np.testing.assert_allclose(rows, orows, rtol=REL, atol=1e-9)
+
+
+def test_fast_vote_decides_or_falls_back_exactly(eng):
+    """Sparse tile sets vote with an fp16 tensor-core pass when its error bound allows it; undecided
+    replicates are redone with exact fp64 cross moments.  Both routes must reproduce the oracle."""
+    # (1) independent blocks, N = 300k: far cross-correlations are noise ~ 0.0018, inside the 0.002 bound
+    rng = np.random.default_rng(0)
+    L, K, N = 6, 4, 300_000
+    path = np.zeros((L, L), dtype=np.int8)
+    for i in range(1, L):
+        path[i, i - 1] = 1
+    X = np.concatenate([rng.standard_normal((N, 1)) * 0.8 + 0.6 * rng.standard_normal((N, K)) for _ in range(L)], axis=1)
+    model = eng.Model([K] * L, [0] * L, path, True, tile_policy=2)
+    data = eng.Data(model, X)
+    before = eng.redo_count()
+    rows, status, iters = eng.bootstrap(model, data, "centroid", 0, 6, seed=4)
+    assert eng.redo_count() > before, "expected undecided votes on uncorrelated blocks"
+    idx = np.stack([orc.philox_indices(4, b, N) for b in range(6)])
+    orows, oiters, _ = orc.bootstrap(X, idx, [K] * L, [0] * L, path, "centroid", True)
+    assert (status == 0).all()
+    np.testing.assert_array_equal(iters, oiters)
+    np.testing.assert_allclose(rows, orows, rtol=REL, atol=1e-9)
+    # (2) a correlated chain with reverse-coded blocks: decided by the fast vote (no redo), signs still right
+    N, L, K = 20000, 12, 8
+    X, path = make_synthetic(N, L, K, seed=6, reverse_blocks=(2, 7))
+    model = eng.Model([K] * L, [0] * L, path, True, tile_policy=2)
+    data = eng.Data(model, X)
+    before = eng.redo_count()
+    rows, status, iters = eng.bootstrap(model, data, "factorial", 0, 8, seed=9)
+    assert eng.redo_count() == before
+    idx = np.stack([orc.philox_indices(9, b, N) for b in range(8)])
+    orows, oiters, _ = orc.bootstrap(X, idx, [K] * L, [0] * L, path, "factorial", True)
+    np.testing.assert_array_equal(iters, oiters)
+    np.testing.assert_allclose(rows, orows, rtol=REL, atol=1e-9)
