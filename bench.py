@@ -285,17 +285,19 @@ def run_gpu_arm(args):
     e2e_value = world * reps * e2e_steps / float(e2e_el.item())
 
     if rank == 0:
-        # the streaming kernel: gram_kernel<false> (Gram tiles) and, for sparse tile sets, its second
-        # instantiation gram_kernel<true> (cross moments); one launch of each per batch
+        # every kernel that streams X for the batch: the Gram kernel (dominant), the column sums, and the
+        # sign-vote pass (exact fp64 cross moments, or score generation + fp16 GEMMs)
+        stream_stages = ("gram", "cross", "colsum", "scoregen")
         gram_ms, gram_n = prof["gram"]
-        cross_ms, cross_n = prof.get("cross", (0.0, 0))
-        gram_ms = gram_ms + cross_ms
+        stream_ms = sum(prof.get(k, (0.0, 0))[0] for k in stream_stages)
         alg_bytes = float((iters_cat + 2.0).sum()) * N * P * 8.0           # all fits of the timed region, this rank
         peak, peak_src = hbm_peak()
-        achieved = alg_bytes / 1e9 / (gram_ms / 1e3) if gram_ms > 0 else 0.0
-        # fp64 FMAs the streaming kernels issue (8x8 tiles; ~63.2 % of the rows have non-zero multiplicity)
-        fma_per_row = (model.n_tiles + (0 if model.full_tiles else model.n_cross_tiles)) * 64
-        fp64_tflops = 2.0 * fma_per_row * 0.632 * N * reps * args.steps / (gram_ms / 1e3) / 1e12 if gram_ms > 0 else 0.0
+        achieved = alg_bytes / 1e9 / (stream_ms / 1e3) if stream_ms > 0 else 0.0
+        # fp64 FMAs of the Gram kernel (8x8 tiles; ~63.2 % of the rows have non-zero multiplicity)
+        fp64_tflops = 2.0 * model.n_tiles * 64 * 0.632 * N * reps * args.steps / (gram_ms / 1e3) / 1e12 if gram_ms > 0 else 0.0
+        vote = "n/a (full tile set)" if model.full_tiles else (
+            "exact fp64 cross moments" if prof.get("scoregen", (0, 0))[1] == 0 else
+            "fp16 tensor-core GEMM with error bound, %d replicates redone exactly" % engine.redo_count())
         traffic = None
         tp = os.path.join(ROOT, "profiles", "gram_traffic.json")
         if os.path.exists(tp):
@@ -315,16 +317,19 @@ def run_gpu_arm(args):
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic,
-                         "kernel": "gram_kernel<false>" + ("" if model.full_tiles else " + gram_kernel<true>"),
-                         "tile_set": "full" if model.full_tiles else "sparse + cross moments",
+                         "kernel": "gram_kernel<false>", "kernel_share_of_streaming_time": gram_ms / stream_ms,
+                         "streaming_stages": list(stream_stages),
+                         "tile_set": "full" if model.full_tiles else "sparse", "sign_vote": vote,
                          "fp64_tflops_est": fp64_tflops, "fp64_peak_nominal_tflops": 37.2,
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes / max(gram_n, 1),
-                         "launch_ms": gram_ms / max(gram_n, 1), "launches": gram_n,
-                         "note": "algorithmic bytes = (n_iter+2)*N*P*8 per fit (SURVEY 8d). The engine reads X once per "
-                                 "wave of replicates per streaming pass instead of (n_iter+2) times per replicate "
-                                 "(covariance-domain solver), so frac exceeds 1; the kernels are bound by the fp64 "
-                                 "FMA pipe (fp64_tflops_est vs the nominal 37.2 TFLOP/s), not by HBM"},
+                         "launch_ms": stream_ms / max(gram_n, 1), "gram_launch_ms": gram_ms / max(gram_n, 1),
+                         "launches": gram_n,
+                         "note": "achieved = algorithmic bytes (n_iter+2)*N*P*8 per fit (SURVEY 8d) over the CUDA-event "
+                                 "time of ALL X-streaming kernels of the batch. The engine reads X once per wave of "
+                                 "replicates per pass instead of (n_iter+2) times per replicate (covariance-domain "
+                                 "solver), so frac exceeds 1; the dominant Gram kernel is bound by the fp64 FMA pipe "
+                                 "(fp64_tflops_est vs the nominal 37.2 TFLOP/s), not by HBM"},
             "stages_ms_per_step": {k: v[0] / args.steps for k, v in prof.items() if v[1]},
             "mean_iterations": float(iters_cat.mean()), "failed_replicates": bad,
         }

@@ -366,23 +366,9 @@ __global__ void __launch_bounds__(SG_THREADS) scoregen_kernel(const double* __re
   float* cs = reinterpret_cast<float*>(xs + (size_t)SG_ROWS * Ppad);  // [reps_per_cta][SG_ROWS]
   const int nbl = SG_THREADS / L;                           // replicate lanes per CTA
   const int reps_per_cta = nbl * SG_RPT;
-  const int row0 = blockIdx.x * SG_ROWS;
   const int64_t rep0 = (int64_t)blockIdx.y * reps_per_cta;
-  const int rows = min(SG_ROWS, rc - row0);
-  for (int e = threadIdx.x; e < SG_ROWS * Ppad; e += SG_THREADS) {
-    const int r = e / Ppad;
-    xs[e] = (r < rows) ? X[(i0 + row0) * Ppad + e] : 0.0;
-  }
-  for (int e = threadIdx.x; e < reps_per_cta * SG_ROWS; e += SG_THREADS) {
-    const int bl = e / SG_ROWS, r = e - bl * SG_ROWS;
-    const int64_t bb = rep0 + bl;
-    float c = 0.f;
-    if (r < rows && bb < nrep) c = counts ? (float)counts[bb * N + i0 + row0 + r] : 1.f;
-    cs[e] = c;
-  }
-  __syncthreads();
-  const int bl = threadIdx.x / L, l = threadIdx.x - bl * L;
-  if (bl >= nbl) return;
+  const int bl = min(threadIdx.x / L, nbl - 1), l = threadIdx.x % L;
+  const bool active = threadIdx.x < nbl * L;
   const int slot = lv_off[l] >> 3;
   const int rot = (slot >> 1) & 3;  // rotated chunk order: the 64-byte slot stride would alias shared-memory banks
   double w[SG_RPT][8], shv[SG_RPT];
@@ -400,6 +386,23 @@ __global__ void __launch_bounds__(SG_THREADS) scoregen_kernel(const double* __re
     }
   }
   const int64_t ldb = nrep * L;
+  // the block weights stay in registers while the CTA walks its share of the chunk's row tiles
+  for (int row0 = blockIdx.x * SG_ROWS; row0 < rc; row0 += gridDim.x * SG_ROWS) {
+  const int rows = min(SG_ROWS, rc - row0);
+  __syncthreads();
+  for (int e = threadIdx.x; e < SG_ROWS * Ppad; e += SG_THREADS) {
+    const int r = e / Ppad;
+    xs[e] = (r < rows) ? X[(i0 + row0) * Ppad + e] : 0.0;
+  }
+  for (int e = threadIdx.x; e < reps_per_cta * SG_ROWS; e += SG_THREADS) {
+    const int eb = e / SG_ROWS, r = e - eb * SG_ROWS;
+    const int64_t bb = rep0 + eb;
+    float c = 0.f;
+    if (r < rows && bb < nrep) c = counts ? (float)counts[bb * N + i0 + row0 + r] : 1.f;
+    cs[e] = c;
+  }
+  __syncthreads();
+  if (active)
   for (int r = 0; r < rows; ++r) {
     double x[8];
 #pragma unroll
@@ -417,6 +420,7 @@ __global__ void __launch_bounds__(SG_THREADS) scoregen_kernel(const double* __re
         B[(int64_t)(row0 + r) * ldb + bb * L + l] = __double2half((double)cs[(bl * SG_RPT + j) * SG_ROWS + r] * t);
       }
     }
+  }
   }
 }
 
@@ -711,55 +715,52 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const GramParams 
 }
 
 // Weighted column sums colsum[b][p] = sum_i c_bi x~_ip  (a skinny fp64 GEMM, counts x X~).
-// CTA = 32 replicates x 64 columns over one row chunk; thread (i, j) of a 16 x 16 grid owns
-// replicates {2i, 2i+1} x columns {4j..4j+3}.  ~1 % of the Gram kernel's FMAs.
-constexpr int CS_REPS = 32, CS_COLS = 64, CS_ROWS = 32;
-__global__ void __launch_bounds__(256) colsum_kernel(const double* __restrict__ X, const uint32_t* __restrict__ counts,
-                                                     int64_t N, int Ppad, int64_t nrep, int n_chunks,
-                                                     int64_t chunk_rows, double* __restrict__ out) {
-  __shared__ __align__(16) double xs[CS_ROWS][CS_COLS];
+// Thread = one column with CS_REPS replicate accumulators in registers; the CTA walks a row chunk,
+// reading X straight from global memory (coalesced over columns) and the multiplicities of its
+// replicates from a shared tile (converted to fp64 once, broadcast LDS.128).
+constexpr int CS_REPS = 32, CS_COLS = 256, CS_ROWS = 32;
+__global__ void __launch_bounds__(CS_COLS) colsum_kernel(const double* __restrict__ X, const uint32_t* __restrict__ counts,
+                                                         int64_t N, int Ppad, int64_t nrep, int n_chunks,
+                                                         int64_t chunk_rows, double* __restrict__ out) {
   __shared__ __align__(16) double cw[CS_ROWS][CS_REPS];
-  const int col0 = blockIdx.x * CS_COLS;
+  const int col = blockIdx.x * CS_COLS + threadIdx.x;
+  const bool col_ok = col < Ppad;
   const int64_t rep0 = (int64_t)blockIdx.y * CS_REPS;
   const int chunk = blockIdx.z;
   const int64_t r0 = (int64_t)chunk * chunk_rows, r1 = min(r0 + chunk_rows, N);
-  const int ti = threadIdx.x >> 4, tj = threadIdx.x & 15;
-  double acc[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+  double acc[CS_REPS];
+#pragma unroll
+  for (int j = 0; j < CS_REPS; ++j) acc[j] = 0.0;
   for (int64_t row = r0; row < r1; row += CS_ROWS) {
     const int rows = (int)min((int64_t)CS_ROWS, r1 - row);
-    for (int e = threadIdx.x; e < CS_ROWS * CS_COLS; e += 256) {
-      const int r = e / CS_COLS, c = e - r * CS_COLS;
-      xs[r][c] = (r < rows && col0 + c < Ppad) ? X[(row + r) * Ppad + col0 + c] : 0.0;
-    }
-    for (int e = threadIdx.x; e < CS_ROWS * CS_REPS; e += 256) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < CS_ROWS * CS_REPS; e += CS_COLS) {
       const int b = e / CS_ROWS, r = e - b * CS_ROWS;  // consecutive threads: consecutive rows of one replicate
       double v = 0.0;
       if (r < rows && rep0 + b < nrep) v = counts ? (double)counts[(rep0 + b) * N + row + r] : 1.0;
       cw[r][b] = v;
     }
+    double x[CS_ROWS / 4];
     __syncthreads();
-#pragma unroll 4
-    for (int r = 0; r < CS_ROWS; ++r) {
-      const double2 c2 = *reinterpret_cast<const double2*>(&cw[r][2 * ti]);
-      const double2 x01 = *reinterpret_cast<const double2*>(&xs[r][4 * tj]);
-      const double2 x23 = *reinterpret_cast<const double2*>(&xs[r][4 * tj + 2]);
-      acc[0][0] = fma(c2.x, x01.x, acc[0][0]); acc[0][1] = fma(c2.x, x01.y, acc[0][1]);
-      acc[0][2] = fma(c2.x, x23.x, acc[0][2]); acc[0][3] = fma(c2.x, x23.y, acc[0][3]);
-      acc[1][0] = fma(c2.y, x01.x, acc[1][0]); acc[1][1] = fma(c2.y, x01.y, acc[1][1]);
-      acc[1][2] = fma(c2.y, x23.x, acc[1][2]); acc[1][3] = fma(c2.y, x23.y, acc[1][3]);
-    }
-    __syncthreads();
-  }
 #pragma unroll
-  for (int u = 0; u < 2; ++u) {
-    const int64_t b = rep0 + 2 * ti + u;
-    if (b >= nrep) continue;
+    for (int r4 = 0; r4 < CS_ROWS; r4 += CS_ROWS / 4) {
 #pragma unroll
-    for (int v = 0; v < 4; ++v) {
-      const int c = col0 + 4 * tj + v;
-      if (c < Ppad) out[(b * n_chunks + chunk) * Ppad + c] = acc[u][v];
+      for (int u = 0; u < CS_ROWS / 4; ++u)  // independent global loads first
+        x[u] = (col_ok && r4 + u < rows) ? X[(row + r4 + u) * Ppad + col] : 0.0;
+#pragma unroll
+      for (int u = 0; u < CS_ROWS / 4; ++u)
+#pragma unroll
+        for (int j = 0; j < CS_REPS; j += 2) {
+          const double2 c2 = *reinterpret_cast<const double2*>(&cw[r4 + u][j]);
+          acc[j] = fma(c2.x, x[u], acc[j]);
+          acc[j + 1] = fma(c2.y, x[u], acc[j + 1]);
+        }
     }
   }
+  if (col_ok)
+#pragma unroll
+    for (int j = 0; j < CS_REPS; ++j)
+      if (rep0 + j < nrep) out[((rep0 + j) * n_chunks + chunk) * Ppad + col] = acc[j];
 }
 
 // sum of the per-chunk partials in chunk order (deterministic)
@@ -1243,7 +1244,7 @@ static int run_batch(plspm_data* d, int64_t nb, const uint32_t* counts_dev, cons
   {
     dim3 grid_cs((h.Ppad + CS_COLS - 1) / CS_COLS, (unsigned)((nb + CS_REPS - 1) / CS_REPS), bp.cs_chunks);
     d->timer.begin(ST_COLSUM, st);
-    colsum_kernel<<<grid_cs, 256, 0, st>>>(d->X, counts_dev, d->N, h.Ppad, nb, bp.cs_chunks, bp.cs_chunk_rows,
+    colsum_kernel<<<grid_cs, CS_COLS, 0, st>>>(d->X, counts_dev, d->N, h.Ppad, nb, bp.cs_chunks, bp.cs_chunk_rows,
                                             bp.cs_chunks > 1 ? D(bb.cspart) : D(bb.colsum));
     d->timer.end(st);
     if (bp.cs_chunks > 1) {
@@ -1286,7 +1287,10 @@ static int run_batch(plspm_data* d, int64_t nb, const uint32_t* counts_dev, cons
       const float one = 1.f, zero = 0.f;
       for (int64_t i0 = 0; i0 < d->N; i0 += FAST_RC) {
         const int rc = (int)std::min<int64_t>(FAST_RC, d->N - i0);
-        dim3 grid_sg((rc + SG_ROWS - 1) / SG_ROWS, (unsigned)((nb + reps_per_cta - 1) / reps_per_cta));
+        const unsigned gy = (unsigned)((nb + reps_per_cta - 1) / reps_per_cta);
+        const unsigned gx = (unsigned)std::max<int64_t>(1, std::min<int64_t>((rc + SG_ROWS - 1) / SG_ROWS,
+                                                                            (4 * d->sm_count + gy - 1) / gy));
+        dim3 grid_sg(gx, gy);
         d->timer.begin(ST_SCOREGEN, st);
         scoregen_kernel<<<grid_sg, SG_THREADS, sg_smem, st>>>(d->X, counts_dev, D(bb.wf), D(bb.sh), d->N, h.Ppad, h.L,
                                                              m->dv.lv_off, nb, i0, rc, BT);
