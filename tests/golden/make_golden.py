@@ -272,6 +272,17 @@ def main():
             r = run_reference_replicates(df, pdf, blk, {n: mode for n in names}, SCHEMES[sname], scaled, idx)
             syn.update(flatten(name + "/boot", r))
             syn[name + "/boot/idx"] = idx
+    # ---- higher-order constructs: stage-1 path expansion (estimator.py:60-74).  The reference cannot run
+    # the two-stage estimation itself on METRIC data (stage 2 raises "matrices are not aligned" at
+    # weights.py:30), so only the path expansion is pinned here.
+    st = c.Structure()
+    st.add_path(["Expectation", "Quality"], ["Satisfaction"])
+    st.add_path(["Satisfaction"], ["Complaints", "Loyalty"])
+    cfg = c.Config(st.path())
+    cfg.add_higher_order("Satisfaction", Mode.A, ["Image", "Value"])
+    fs = Estimator(cfg).hoc_path_first_stage(cfg)
+    syn["hoc/first_stage_lvs"] = np.array([str(v) for v in fs.index])
+    syn["hoc/first_stage_path"] = fs.values.astype(np.int8)
     syn["cases"] = np.array([cs[0] for cs in cases])
     assert not [k for k, v in syn.items() if np.asarray(v).dtype == object]
     np.savez_compressed(os.path.join(HERE, "synthetic.npz"), **syn)

@@ -160,3 +160,4 @@ def test_missing_values_single_fit_is_mean_imputed(sat):
     ref = orc.fit(X, sat["block_sizes"], [0] * 6, sat["path"], "centroid", False)
     np.testing.assert_allclose(calc.outer_model().loc[[str(v) for v in sat["mvs"]], "weight"].values, ref["weights"],
                                rtol=1e-6)
+

@@ -167,3 +167,20 @@ def test_enums():
     assert Mode.A != Mode.B and Mode.A.value.engine_id == 0 and Mode.B.value.engine_id == 1
     assert Scheme.CENTROID.value.engine_id == 0 and Scheme.FACTORIAL.value.engine_id == 1
     assert Scheme.PATH.value.engine_id == 2
+
+
+def test_hoc_first_stage_path_matches_reference(syn):
+    from plspm.estimator import Estimator
+    if "hoc/first_stage_path" not in syn.files:
+        pytest.skip("fixture without the HOC case")
+    st = c.Structure()
+    st.add_path(["Expectation", "Quality"], ["Satisfaction"])
+    st.add_path(["Satisfaction"], ["Complaints", "Loyalty"])
+    cfg = c.Config(st.path())
+    cfg.add_higher_order("Satisfaction", Mode.A, ["Image", "Value"])
+    fs = Estimator(cfg).hoc_path_first_stage(cfg)
+    assert list(fs.index) == [str(v) for v in syn["hoc/first_stage_lvs"]]
+    np.testing.assert_array_equal(fs.values, syn["hoc/first_stage_path"])
+    assert "Satisfaction" not in fs.index and {"Image", "Value"} <= set(fs.index)
+    with pytest.raises(NotImplementedError):
+        Estimator(cfg).estimate(type("Calc", (), {"config": lambda self: cfg})(), None)
