@@ -349,27 +349,32 @@ __global__ void make_half_kernel(const double* __restrict__ X, int64_t N, int Pp
     out[e] = __double2half(X[e] * inv_sd[e % Ppad]);
 }
 
-// Scores for the tensor-core sign vote (models whose blocks fit one slot, K <= 8):
+// Scores for the tensor-core sign vote:
 //   B[i - i0][b*L + l] = fp16( c_bi * (x~_i . wf_b,l - sh_b,l) )        rows [i0, i0 + rc) of one chunk.
-// Thread = (replicate lane, latent variable): it keeps the block weights of SG_RPT replicates in
-// registers and walks the rows of the CTA's tile, reading the row's block (8 doubles) once for all of
-// them.  t is computed in fp64; only the product with the multiplicity is rounded to fp16.
-constexpr int SG_ROWS = 32, SG_RPT = 4, SG_THREADS = 256;
+// A group of nsl_pad adjacent lanes (power of two >= slots of the widest block) serves one (replicate
+// lane, latent variable) pair: lane `sub` of the group owns slot `sub` of the block, keeps the weights
+// of that slot for SG_RPT replicates in registers, walks the rows of the CTA's tiles reading the slot
+// (8 doubles) once for all of them, and the partial dot products are combined with a shuffle butterfly.
+// t is computed in fp64; only the product with the multiplicity is rounded to fp16.
+constexpr int SG_MAX_ROWS = 32, SG_RPT = 4, SG_THREADS = 256;
 __global__ void __launch_bounds__(SG_THREADS) scoregen_kernel(const double* __restrict__ X,
                                                               const uint32_t* __restrict__ counts,
                                                               const double* __restrict__ wf,
                                                               const double* __restrict__ sh, int64_t N, int Ppad, int L,
-                                                              const int* __restrict__ lv_off, int64_t nrep, int64_t i0,
-                                                              int rc, __half* __restrict__ B) {
+                                                              const int* __restrict__ lv_off,
+                                                              const int* __restrict__ lv_k, int nsl_pad, int SG_ROWS,
+                                                              int64_t nrep, int64_t i0, int rc, __half* __restrict__ B) {
   extern __shared__ __align__(16) double sg_smem[];
-  double* xs = sg_smem;                                     // [SG_ROWS][Ppad]
+  double* xs = sg_smem;                                     // [SG_ROWS][Ppad]  (SG_ROWS <= 32 rows per tile)
   float* cs = reinterpret_cast<float*>(xs + (size_t)SG_ROWS * Ppad);  // [reps_per_cta][SG_ROWS]
-  const int nbl = SG_THREADS / L;                           // replicate lanes per CTA
+  const int nbl = SG_THREADS / (L * nsl_pad);               // replicate lanes per CTA
   const int reps_per_cta = nbl * SG_RPT;
   const int64_t rep0 = (int64_t)blockIdx.y * reps_per_cta;
-  const int bl = min(threadIdx.x / L, nbl - 1), l = threadIdx.x % L;
-  const bool active = threadIdx.x < nbl * L;
-  const int slot = lv_off[l] >> 3;
+  const int item = threadIdx.x / nsl_pad, sub = threadIdx.x - item * nsl_pad;
+  const int bl = min(item / L, nbl - 1), l = item % L;
+  const bool active = item < nbl * L;                       // (whole lane groups are active or not)
+  const bool has_slot = sub < ((lv_k[l] + SLOT - 1) >> 3);
+  const int slot = (lv_off[l] >> 3) + (has_slot ? sub : 0);
   const int rot = (slot >> 1) & 3;  // rotated chunk order: the 64-byte slot stride would alias shared-memory banks
   double w[SG_RPT][8], shv[SG_RPT];
   bool ok[SG_RPT];
@@ -377,50 +382,53 @@ __global__ void __launch_bounds__(SG_THREADS) scoregen_kernel(const double* __re
   for (int j = 0; j < SG_RPT; ++j) {
     const int64_t bb = rep0 + bl * SG_RPT + j;
     ok[j] = bb < nrep;
-    shv[j] = ok[j] ? sh[bb * L + l] : 0.0;
+    shv[j] = (ok[j] && sub == 0) ? sh[bb * L + l] : 0.0;
 #pragma unroll
     for (int ch = 0; ch < 4; ++ch) {
       const int col = slot * SLOT + 2 * ((ch + rot) & 3);
-      w[j][2 * ch] = ok[j] ? wf[bb * Ppad + col] : 0.0;
-      w[j][2 * ch + 1] = ok[j] ? wf[bb * Ppad + col + 1] : 0.0;
+      w[j][2 * ch] = (ok[j] && has_slot) ? wf[bb * Ppad + col] : 0.0;
+      w[j][2 * ch + 1] = (ok[j] && has_slot) ? wf[bb * Ppad + col + 1] : 0.0;
     }
   }
   const int64_t ldb = nrep * L;
   // the block weights stay in registers while the CTA walks its share of the chunk's row tiles
   for (int row0 = blockIdx.x * SG_ROWS; row0 < rc; row0 += gridDim.x * SG_ROWS) {
-  const int rows = min(SG_ROWS, rc - row0);
-  __syncthreads();
-  for (int e = threadIdx.x; e < SG_ROWS * Ppad; e += SG_THREADS) {
-    const int r = e / Ppad;
-    xs[e] = (r < rows) ? X[(i0 + row0) * Ppad + e] : 0.0;
-  }
-  for (int e = threadIdx.x; e < reps_per_cta * SG_ROWS; e += SG_THREADS) {
-    const int eb = e / SG_ROWS, r = e - eb * SG_ROWS;
-    const int64_t bb = rep0 + eb;
-    float c = 0.f;
-    if (r < rows && bb < nrep) c = counts ? (float)counts[bb * N + i0 + row0 + r] : 1.f;
-    cs[e] = c;
-  }
-  __syncthreads();
-  if (active)
-  for (int r = 0; r < rows; ++r) {
-    double x[8];
-#pragma unroll
-    for (int ch = 0; ch < 4; ++ch) {
-      const double2 v = *reinterpret_cast<const double2*>(xs + (size_t)r * Ppad + slot * SLOT + 2 * ((ch + rot) & 3));
-      x[2 * ch] = v.x; x[2 * ch + 1] = v.y;
+    const int rows = min(SG_ROWS, rc - row0);
+    __syncthreads();
+    for (int e = threadIdx.x; e < SG_ROWS * Ppad; e += SG_THREADS) {
+      const int r = e / Ppad;
+      xs[e] = (r < rows) ? X[(i0 + row0) * Ppad + e] : 0.0;
     }
+    for (int e = threadIdx.x; e < reps_per_cta * SG_ROWS; e += SG_THREADS) {
+      const int eb = e / SG_ROWS, r = e - eb * SG_ROWS;
+      const int64_t bb = rep0 + eb;
+      float c = 0.f;
+      if (r < rows && bb < nrep) c = counts ? (float)counts[bb * N + i0 + row0 + r] : 1.f;
+      cs[e] = c;
+    }
+    __syncthreads();
+    // (inactive lane groups run along so that the full-mask shuffles below are well defined)
+      for (int r = 0; r < rows; ++r) {
+        double x[8];
 #pragma unroll
-    for (int j = 0; j < SG_RPT; ++j) {
-      double t = -shv[j];
+        for (int ch = 0; ch < 4; ++ch) {
+          const double2 v =
+              *reinterpret_cast<const double2*>(xs + (size_t)r * Ppad + slot * SLOT + 2 * ((ch + rot) & 3));
+          x[2 * ch] = v.x; x[2 * ch + 1] = v.y;
+        }
 #pragma unroll
-      for (int k = 0; k < 8; ++k) t = fma(x[k], w[j][k], t);
-      if (ok[j]) {
-        const int64_t bb = rep0 + bl * SG_RPT + j;
-        B[(int64_t)(row0 + r) * ldb + bb * L + l] = __double2half((double)cs[(bl * SG_RPT + j) * SG_ROWS + r] * t);
+        for (int j = 0; j < SG_RPT; ++j) {
+          double t = -shv[j];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) t = fma(x[k], w[j][k], t);
+          for (int o = nsl_pad >> 1; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+          if (ok[j] && sub == 0 && active) {
+            const int64_t bb = rep0 + bl * SG_RPT + j;
+            B[(int64_t)(row0 + r) * ldb + bb * L + l] =
+                __double2half((double)cs[(bl * SG_RPT + j) * SG_ROWS + r] * t);
+          }
+        }
       }
-    }
-  }
   }
 }
 
@@ -998,7 +1006,9 @@ int plspm_data_create(const plspm_model* m, const double* X, int64_t N, int64_t 
     CK(cudaGetLastError());
     // fp16 copy for the tensor-core sign vote of sparse tile sets (PLSPM_VOTE=exact disables it)
     static const bool vote_exact = getenv("PLSPM_VOTE") && std::string(getenv("PLSPM_VOTE")) == "exact";
-    if (!h.full && !vote_exact && N >= 4096 && h.kmax <= SLOT && h.L <= SG_THREADS) {
+    int nsl_pad_chk = 1;
+    while (nsl_pad_chk * SLOT < h.kmax) nsl_pad_chk <<= 1;
+    if (!h.full && !vote_exact && N >= 4096 && nsl_pad_chk <= 32 && h.L * nsl_pad_chk <= SG_THREADS) {
       double* sq = nullptr;
       CK(g_pool.alloc((void**)&sq, (size_t)nblocks * h.Ppad * sizeof(double)));
       CK(g_pool.alloc((void**)&d->inv_sd, (size_t)h.Ppad * sizeof(double)));
@@ -1281,7 +1291,11 @@ static int run_batch(plspm_data* d, int64_t nb, const uint32_t* counts_dev, cons
       // of FAST_RC rows (cuBLAS: a plain fp16 GEMM, m = nb*L, n = Ppad, k = rows of the chunk)
       __half* BT = (__half*)(base + bb.BT);
       float* Cf = (float*)(base + bb.Cf);
-      const int reps_per_cta = (SG_THREADS / h.L) * SG_RPT;
+      int nsl_pad = 1;
+      while (nsl_pad * SLOT < h.kmax) nsl_pad <<= 1;
+      const int reps_per_cta = (SG_THREADS / (h.L * nsl_pad)) * SG_RPT;
+      const int SG_ROWS = (int)std::max<size_t>(1, std::min<size_t>(SG_MAX_ROWS, (size_t)(d->max_smem - 16384) /
+                                                                                  ((size_t)h.Ppad * 8 + reps_per_cta * 4)));
       const size_t sg_smem = (size_t)SG_ROWS * h.Ppad * 8 + (size_t)reps_per_cta * SG_ROWS * 4;
       CK(cudaFuncSetAttribute(scoregen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sg_smem));
       const float one = 1.f, zero = 0.f;
@@ -1293,7 +1307,7 @@ static int run_batch(plspm_data* d, int64_t nb, const uint32_t* counts_dev, cons
         dim3 grid_sg(gx, gy);
         d->timer.begin(ST_SCOREGEN, st);
         scoregen_kernel<<<grid_sg, SG_THREADS, sg_smem, st>>>(d->X, counts_dev, D(bb.wf), D(bb.sh), d->N, h.Ppad, h.L,
-                                                             m->dv.lv_off, nb, i0, rc, BT);
+                                                             m->dv.lv_off, m->dv.lv_k, nsl_pad, SG_ROWS, nb, i0, rc, BT);
         d->timer.end(st);
         CK(cudaGetLastError());
         // C[nb*L x Ppad] (+)= B^T-free NT product: A = scores stored [nb*L x rc] (column-major view of the

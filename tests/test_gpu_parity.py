@@ -290,3 +290,22 @@ def test_fast_vote_decides_or_falls_back_exactly(eng):
     orows, oiters, _ = orc.bootstrap(X, idx, [K] * L, [0] * L, path, "factorial", True)
     np.testing.assert_array_equal(iters, oiters)
     np.testing.assert_allclose(rows, orows, rtol=REL, atol=1e-9)
+
+
+@pytest.mark.parametrize("L,K,N,scheme,mode", ((40, 16, 5000, "centroid", 0), (70, 3, 4500, "factorial", 0),
+                                               (20, 24, 6000, "path", 1), (33, 8, 9000, "centroid", 0)))
+@pytest.mark.parametrize("policy", (1, 2))
+def test_wide_models(eng, L, K, N, scheme, mode, policy):
+    """Shapes beyond c3: P up to 640 (several column slabs), L > 32 / L not a multiple of 8, blocks spanning
+    several slots (K = 16, 24), for both tile policies; single fit + bootstrap (fast vote where eligible)."""
+    X, path = make_synthetic(N, L, K, seed=L + K, reverse_blocks=(1, L - 2))
+    model = eng.Model([K] * L, [mode] * L, path, True, tile_policy=policy)
+    data = eng.Data(model, X)
+    got = eng.fit(model, data, scheme)
+    check_fit(got, orc.fit(X, [K] * L, [mode] * L, path, scheme, True))
+    rows, status, iters = eng.bootstrap(model, data, scheme, 3, 5, seed=21)
+    idx = np.stack([orc.philox_indices(21, 3 + b, N) for b in range(5)])
+    orows, oiters, _ = orc.bootstrap(X, idx, [K] * L, [mode] * L, path, scheme, True)
+    assert (status == 0).all()
+    np.testing.assert_array_equal(iters, oiters)
+    np.testing.assert_allclose(rows, orows, rtol=REL, atol=1e-9)
