@@ -820,7 +820,6 @@ __global__ void __launch_bounds__(SOLVE_THREADS) solve_kernel(const SolveBatch b
   A.scheme = b.scheme;
   A.tol = b.tol;
   A.max_iter = b.max_iter;
-  A.ext_votes = nullptr;
   A.phase = b.phase;
   A.wf_out = b.wf ? b.wf + rep * b.M.Ppad : nullptr;
   A.cross = b.cross ? b.cross + rep * b.cross_stride : nullptr;

@@ -17,7 +17,7 @@ ModelView HostModel::host_view() const {
   v.lv_off = lv_off.data(); v.lv_k = lv_k.data(); v.lv_mode = lv_mode.data();
   v.col_lv = col_lv.data(); v.col_src = col_src.data(); v.path = path.data();
   v.tile_sa = tile_sa.data(); v.tile_sb = tile_sb.data(); v.tile_of = tile_of.data();
-  v.lane_tile = lane_tile.data(); v.tile_owner = tile_owner.data();
+  v.lane_tile = lane_tile.data();
   v.pair_l = pair_l.data(); v.pair_j = pair_j.data(); v.pair_voff = pair_voff.data();
   v.lv_pair_begin = lv_pair_begin.data();
   v.eff_from = eff_from.data(); v.eff_to = eff_to.data(); v.chol_b_off = chol_b_off.data();
@@ -160,13 +160,6 @@ int build_model(int L, const int32_t* block_sizes, const int8_t* modes, const in
     for (auto& pr : und) m.omega[(size_t)pr.first * L + pr.second] = m.omega[(size_t)pr.second * L + pr.first] = 1;
   }
   m.n_tiles = (int)m.tile_sa.size();
-  m.tile_owner.assign(m.n_tiles, 0);
-  for (int sl = 0; sl < m.ns; ++sl) {
-    int best = -1;
-    for (int t = 0; t < m.n_tiles; ++t)
-      if (m.tile_sb[t] == sl && (best < 0 || m.tile_sa[t] > m.tile_sa[best])) best = t;
-    m.tile_owner[best] = 1;
-  }
   // pack tiles into warps (tile groups of 32 lanes): chunks of one row slot, first-fit decreasing
   {
     std::vector<std::vector<int>> chunks;

@@ -17,7 +17,7 @@ constexpr int TILE = SLOT * SLOT;   // doubles per Gram tile
 
 enum Scheme { SCHEME_CENTROID = 0, SCHEME_FACTORIAL = 1, SCHEME_PATH = 2 };
 enum Mode { MODE_A = 0, MODE_B = 1 };
-enum Status { STATUS_OK = 0, STATUS_NOT_CONVERGED = 1, STATUS_SINGULAR = 2, STATUS_DEGENERATE = 3,
+enum Status { STATUS_OK = 0, STATUS_NOT_CONVERGED = 1, STATUS_SINGULAR = 2,
               STATUS_AMBIGUOUS = 16 /* internal: low-precision sign vote undecided, redo exactly */ };
 enum TilePolicy { TILES_AUTO = 0, TILES_FULL = 1, TILES_SPARSE = 2 };
 
@@ -30,7 +30,6 @@ struct ModelView {
   const int8_t* path;                       // [L*L] path[i*L+j]==1 : j -> i
   const int *tile_sa, *tile_sb, *tile_of;   // tile list and ns*ns lookup (see tile_of encoding)
   const int* lane_tile;                     // [n_tg*32] tile id handled by lane (or -1)
-  const int* tile_owner;                    // [n_tiles] 1: this tile's lane accumulates the column sums of slot sb
   const int *pair_l, *pair_j, *pair_voff, *lv_pair_begin;
   const int *eff_from, *eff_to;
   const int *chol_b_off;
@@ -56,9 +55,6 @@ struct HostModel {
   // Tile -> (tile group, lane) packing: tiles of one row slot stay in one warp so that the row
   // operand is a shared-memory broadcast; lane_tile[g*32+lane] = tile id or -1.
   std::vector<int> lane_tile;
-  // tile_owner[t] = 1 for exactly one tile per slot s (sb == s, largest sa): its lane also sums the
-  // slot's columns (the replicate's weighted column sums) from registers it has loaded anyway.
-  std::vector<int> tile_owner;
   // directed LV pairs (l <- j) whose block covariance the iteration needs; sorted by l, the
   // diagonal pair (l <- l) first.  V[pair_voff[d] + r], r < K_l, receives (S_lj w_j)[r].
   std::vector<int> pair_l, pair_j, pair_voff, lv_pair_begin;

@@ -48,7 +48,6 @@ struct SolveArgs {
   int scheme;
   double tol;
   int max_iter;
-  const int* ext_votes;  // unused (kept for layout compatibility)
   int phase;             // 0: everything (full tile set); 1: stop after the final weights (writes wf_out);
                          // 2: everything, cov(x_p, score_l) taken from the cross-moment tiles;
                          // 3: like 2, but LV pairs outside the tile set vote with the SIGN of a

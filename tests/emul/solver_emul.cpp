@@ -72,7 +72,7 @@ extern "C" int emul_fit(int L, const int32_t* block_sizes, const int8_t* modes, 
   std::memset(&A, 0, sizeof(A));
   A.M = m.host_view();
   A.G = G.data(); A.colsum = colsum.data(); A.mu = mu.data(); A.N = (double)N;
-  A.scheme = scheme; A.tol = tol; A.max_iter = max_iter; A.ext_votes = nullptr; A.ws = ws.data();
+  A.scheme = scheme; A.tol = tol; A.max_iter = max_iter; A.ws = ws.data();
   A.out_row = out_row; A.weights = weights; A.loadings = loadings; A.r2 = r2; A.paths = paths; A.total = total;
   A.crossloadings = crossloadings; A.score_coef = coef.data(); A.score_shift = shift.data();
   A.iters = iters; A.status = status;
