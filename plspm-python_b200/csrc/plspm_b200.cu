@@ -646,6 +646,7 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const GramParams 
     __syncwarp();
     mbar_wait(&full_bar[s], use & 1);
     const uint32_t base = tiles_addr + (uint32_t)s * (uint32_t)(stage_doubles * 8);
+    uint32_t release_dep = 0;
     if constexpr (CROSS) {
       // scores of the tile's non-zero rows for the LVs this warp's tiles touch, one (row, LV) pair
       // per lane:  scratch[k][l] = c_k * sum_{q in block l} x~[row_k][q] wf[q]   (pad rows: c = 0)
@@ -700,9 +701,13 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const GramParams 
         load_entry(k + 3, oe1, ce1);
         accumulate(xa1, xb1, c1);
       }
+      // The loop prefetches one row set past the end (a pad row of this stage).  Make the stage release
+      // below depend on that last load, so no shared-memory read of the stage is still in flight when
+      // the producer's next bulk copy may overwrite it.
+      asm volatile("{\n.reg .b32 lo, hi;\nmov.b64 {lo, hi}, %1;\nand.b32 %0, lo, 0;\n}" : "=r"(release_dep) : "d"(xb0[7]));
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(&empty_bar[s]);
+    if (lane == 0) mbar_arrive(&empty_bar[s] + release_dep);
   }
 
   // ---- write the partial tile (undo the chunk rotation) and the column sums --------------------

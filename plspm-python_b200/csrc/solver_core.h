@@ -336,6 +336,7 @@ PL_HD void solve_replicate(const SolveArgs& A, double* smem) {
     u[p] = (l >= 0) ? w[p] * dinv[l] : 0.0;  // wf: scores have unit population variance
   }
   for (int l = tid; l < L; l += nt) votes[l] = 0;
+  PL_SYNC();  // u is read across threads below (racecheck: shared-memory RAW hazard without this)
   if (A.phase == 1) {  // sparse tile set, first pass: hand the weights to the cross-moment kernel
     for (int p = tid; p < Ppad; p += nt) A.wf_out[p] = u[p];
     if (A.sh_out)
