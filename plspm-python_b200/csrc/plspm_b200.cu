@@ -367,12 +367,31 @@ __global__ void __launch_bounds__(SG_THREADS) scoregen_kernel(const double* __re
   extern __shared__ __align__(16) double sg_smem[];
   double* xs = sg_smem;                                     // [SG_ROWS][Ppad]  (SG_ROWS <= 32 rows per tile)
   float* cs = reinterpret_cast<float*>(xs + (size_t)SG_ROWS * Ppad);  // [reps_per_cta][SG_ROWS]
-  const int nbl = SG_THREADS / (L * nsl_pad);               // replicate lanes per CTA
+  int nbl = SG_THREADS / (L * nsl_pad);                     // replicate lanes per CTA (same rule on the host)
+  if (nsl_pad == 1 && nbl >= 4) nbl = (SG_THREADS / 32 / ((L + 7) >> 3)) * 4;
   const int reps_per_cta = nbl * SG_RPT;
   const int64_t rep0 = (int64_t)blockIdx.y * reps_per_cta;
-  const int item = threadIdx.x / nsl_pad, sub = threadIdx.x - item * nsl_pad;
-  const int bl = min(item / L, nbl - 1), l = item % L;
-  const bool active = item < nbl * L;                       // (whole lane groups are active or not)
+  // Thread -> (replicate lane bl, latent variable l, slot sub).  Single-slot blocks: a warp is 8 LVs x 4
+  // replicate lanes, so the 32 LDS.128 of a row touch only 8 distinct slots (2 wavefronts instead of 4).
+  int item, sub, bl, l;
+  bool active;
+  if (nsl_pad == 1 && nbl >= 4) {
+    const int lvg = (L + 7) >> 3, w = threadIdx.x >> 5, ln = threadIdx.x & 31;
+    l = (w % lvg) * 8 + (ln & 7);
+    bl = (w / lvg) * 4 + (ln >> 3);
+    sub = 0;
+    active = l < L && bl < nbl;
+    l = min(l, L - 1);
+    bl = min(bl, nbl - 1);
+    item = 0;
+  } else {
+    item = threadIdx.x / nsl_pad;
+    sub = threadIdx.x - item * nsl_pad;
+    bl = min(item / L, nbl - 1);
+    l = item % L;
+    active = item < nbl * L;                                // (whole lane groups are active or not)
+  }
+  (void)item;
   const bool has_slot = sub < ((lv_k[l] + SLOT - 1) >> 3);
   const int slot = (lv_off[l] >> 3) + (has_slot ? sub : 0);
   const int rot = (slot >> 1) & 3;  // rotated chunk order: the 64-byte slot stride would alias shared-memory banks
@@ -728,52 +747,69 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const GramParams 
 }
 
 // Weighted column sums colsum[b][p] = sum_i c_bi x~_ip  (a skinny fp64 GEMM, counts x X~).
-// Thread = one column with CS_REPS replicate accumulators in registers; the CTA walks a row chunk,
-// reading X straight from global memory (coalesced over columns) and the multiplicities of its
-// replicates from a shared tile (converted to fp64 once, broadcast LDS.128).
+// CTA = 32 replicates x 256 columns over one row chunk; the X row tile and the (fp64-converted)
+// multiplicities are staged in shared memory, thread = 8 replicates x 4 columns in registers
+// (6 LDS.128 per 32 FMAs), two CTAs per SM overlap staging and arithmetic.
 constexpr int CS_REPS = 32, CS_COLS = 256, CS_ROWS = 32;
-__global__ void __launch_bounds__(CS_COLS) colsum_kernel(const double* __restrict__ X, const uint32_t* __restrict__ counts,
-                                                         int64_t N, int Ppad, int64_t nrep, int n_chunks,
-                                                         int64_t chunk_rows, double* __restrict__ out) {
-  __shared__ __align__(16) double cw[CS_ROWS][CS_REPS];
-  const int col = blockIdx.x * CS_COLS + threadIdx.x;
-  const bool col_ok = col < Ppad;
+__global__ void __launch_bounds__(256, 2) colsum_kernel(const double* __restrict__ X, const uint32_t* __restrict__ counts,
+                                                        int64_t N, int Ppad, int64_t nrep, int n_chunks,
+                                                        int64_t chunk_rows, double* __restrict__ out) {
+  extern __shared__ __align__(16) double cs_smem[];
+  double* xs = cs_smem;                       // [CS_ROWS][CS_COLS]
+  double* cw = xs + CS_ROWS * CS_COLS;        // [CS_ROWS][CS_REPS]
+  const int col0 = blockIdx.x * CS_COLS;
   const int64_t rep0 = (int64_t)blockIdx.y * CS_REPS;
   const int chunk = blockIdx.z;
   const int64_t r0 = (int64_t)chunk * chunk_rows, r1 = min(r0 + chunk_rows, N);
-  double acc[CS_REPS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rg = warp >> 1;                   // replicate group: replicates 8*rg .. 8*rg+7
+  const int cg = (warp & 1) * 32 + lane;      // column group: columns 4*cg .. 4*cg+3
+  double acc[8][4];
 #pragma unroll
-  for (int j = 0; j < CS_REPS; ++j) acc[j] = 0.0;
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
   for (int64_t row = r0; row < r1; row += CS_ROWS) {
     const int rows = (int)min((int64_t)CS_ROWS, r1 - row);
     __syncthreads();
-    for (int e = threadIdx.x; e < CS_ROWS * CS_REPS; e += CS_COLS) {
+    for (int e = threadIdx.x; e < CS_ROWS * CS_COLS; e += 256) {
+      const int r = e / CS_COLS, c = e - r * CS_COLS;
+      xs[e] = (r < rows && col0 + c < Ppad) ? X[(row + r) * Ppad + col0 + c] : 0.0;
+    }
+    for (int e = threadIdx.x; e < CS_ROWS * CS_REPS; e += 256) {
       const int b = e / CS_ROWS, r = e - b * CS_ROWS;  // consecutive threads: consecutive rows of one replicate
       double v = 0.0;
       if (r < rows && rep0 + b < nrep) v = counts ? (double)counts[(rep0 + b) * N + row + r] : 1.0;
-      cw[r][b] = v;
+      cw[r * CS_REPS + b] = v;
     }
-    double x[CS_ROWS / 4];
     __syncthreads();
+#pragma unroll 2
+    for (int r = 0; r < CS_ROWS; ++r) {
+      const double2 x01 = *reinterpret_cast<const double2*>(&xs[r * CS_COLS + 4 * cg]);
+      const double2 x23 = *reinterpret_cast<const double2*>(&xs[r * CS_COLS + 4 * cg + 2]);
+      double c[8];
 #pragma unroll
-    for (int r4 = 0; r4 < CS_ROWS; r4 += CS_ROWS / 4) {
+      for (int k = 0; k < 4; ++k) {
+        const double2 c2 = *reinterpret_cast<const double2*>(&cw[r * CS_REPS + 8 * rg + 2 * k]);
+        c[2 * k] = c2.x; c[2 * k + 1] = c2.y;
+      }
 #pragma unroll
-      for (int u = 0; u < CS_ROWS / 4; ++u)  // independent global loads first
-        x[u] = (col_ok && r4 + u < rows) ? X[(row + r4 + u) * Ppad + col] : 0.0;
-#pragma unroll
-      for (int u = 0; u < CS_ROWS / 4; ++u)
-#pragma unroll
-        for (int j = 0; j < CS_REPS; j += 2) {
-          const double2 c2 = *reinterpret_cast<const double2*>(&cw[r4 + u][j]);
-          acc[j] = fma(c2.x, x[u], acc[j]);
-          acc[j + 1] = fma(c2.y, x[u], acc[j + 1]);
-        }
+      for (int i = 0; i < 8; ++i) {
+        acc[i][0] = fma(c[i], x01.x, acc[i][0]); acc[i][1] = fma(c[i], x01.y, acc[i][1]);
+        acc[i][2] = fma(c[i], x23.x, acc[i][2]); acc[i][3] = fma(c[i], x23.y, acc[i][3]);
+      }
     }
   }
-  if (col_ok)
 #pragma unroll
-    for (int j = 0; j < CS_REPS; ++j)
-      if (rep0 + j < nrep) out[((rep0 + j) * n_chunks + chunk) * Ppad + col] = acc[j];
+  for (int i = 0; i < 8; ++i) {
+    const int64_t b = rep0 + 8 * rg + i;
+    if (b >= nrep) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = col0 + 4 * cg + j;
+      if (c < Ppad) out[(b * n_chunks + chunk) * Ppad + c] = acc[i][j];
+    }
+  }
 }
 
 // sum of the per-chunk partials in chunk order (deterministic)
@@ -1258,7 +1294,9 @@ static int run_batch(plspm_data* d, int64_t nb, const uint32_t* counts_dev, cons
   {
     dim3 grid_cs((h.Ppad + CS_COLS - 1) / CS_COLS, (unsigned)((nb + CS_REPS - 1) / CS_REPS), bp.cs_chunks);
     d->timer.begin(ST_COLSUM, st);
-    colsum_kernel<<<grid_cs, CS_COLS, 0, st>>>(d->X, counts_dev, d->N, h.Ppad, nb, bp.cs_chunks, bp.cs_chunk_rows,
+    const size_t cs_smem_bytes = (size_t)(CS_ROWS * CS_COLS + CS_ROWS * CS_REPS) * 8;
+    CK(cudaFuncSetAttribute(colsum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs_smem_bytes));
+    colsum_kernel<<<grid_cs, 256, cs_smem_bytes, st>>>(d->X, counts_dev, d->N, h.Ppad, nb, bp.cs_chunks, bp.cs_chunk_rows,
                                             bp.cs_chunks > 1 ? D(bb.cspart) : D(bb.colsum));
     d->timer.end(st);
     if (bp.cs_chunks > 1) {
@@ -1297,7 +1335,11 @@ static int run_batch(plspm_data* d, int64_t nb, const uint32_t* counts_dev, cons
       float* Cf = (float*)(base + bb.Cf);
       int nsl_pad = 1;
       while (nsl_pad * SLOT < h.kmax) nsl_pad <<= 1;
-      const int reps_per_cta = (SG_THREADS / (h.L * nsl_pad)) * SG_RPT;
+      // replicate lanes per CTA: SG_THREADS / (L * nsl_pad); with single-slot blocks the warp layout is
+      // (8 LVs x 4 lanes) x ceil(L/8) LV groups, i.e. lanes come in fours
+      int nbl_host = SG_THREADS / (h.L * nsl_pad);
+      if (nsl_pad == 1 && nbl_host >= 4) nbl_host = (SG_THREADS / 32 / ((h.L + 7) / 8)) * 4;
+      const int reps_per_cta = std::max(1, nbl_host) * SG_RPT;
       const int SG_ROWS = (int)std::max<size_t>(1, std::min<size_t>(SG_MAX_ROWS, (size_t)(d->max_smem - 16384) /
                                                                                   ((size_t)h.Ppad * 8 + reps_per_cta * 4)));
       const size_t sg_smem = (size_t)SG_ROWS * h.Ppad * 8 + (size_t)reps_per_cta * SG_ROWS * 4;
@@ -1401,6 +1443,7 @@ int plspm_bootstrap(const plspm_model* m, const plspm_data* dc, int32_t scheme, 
   const size_t per_rep = (size_t)N * 4 + ((size_t)h.n_tiles * TILE + (h.full ? 0 : (size_t)h.n_cross * TILE) +
                                           2 * h.Ppad + h.ws_doubles + n_out) * 8 + (idx ? (size_t)N * 4 : 0) + 64;
   int64_t nb_max = std::max<int64_t>(1, (int64_t)((size_t)1536 * 1024 * 1024 / per_rep));
+  if (getenv("PLSPM_MAX_BATCH")) nb_max = std::max<int64_t>(1, std::min<int64_t>(nb_max, atoll(getenv("PLSPM_MAX_BATCH"))));
   nb_max = std::min<int64_t>(nb_max, rep_count);
   const int64_t wave = (int64_t)d->sm_count * GRAM_WARPS;  // warp items per wave
   const int64_t items_per_rep = h.full ? h.n_tg : std::max(h.n_tg, h.n_tg_cross);

@@ -309,3 +309,45 @@ def test_wide_models(eng, L, K, N, scheme, mode, policy):
     assert (status == 0).all()
     np.testing.assert_array_equal(iters, oiters)
     np.testing.assert_allclose(rows, orows, rtol=REL, atol=1e-9)
+
+
+def test_batching_and_replicate_ranges_are_transparent(eng, monkeypatch):
+    """Replicates are keyed by their GLOBAL id: splitting a run into batches (PLSPM_MAX_BATCH) or into
+    several calls over sub-ranges must give the same rows as one call."""
+    N, L, K = 6000, 10, 8
+    X, path = make_synthetic(N, L, K, seed=12, reverse_blocks=(3,))
+    model = eng.Model([K] * L, [0] * L, path, True)
+    data = eng.Data(model, X)
+    rows, status, iters = eng.bootstrap(model, data, "centroid", 50, 23, seed=5)
+    monkeypatch.setenv("PLSPM_MAX_BATCH", "4")
+    rows_b, status_b, iters_b = eng.bootstrap(model, data, "centroid", 50, 23, seed=5)
+    monkeypatch.delenv("PLSPM_MAX_BATCH")
+    np.testing.assert_array_equal(rows, rows_b)
+    np.testing.assert_array_equal(iters, iters_b)
+    parts = [eng.bootstrap(model, data, "centroid", 50 + o, n, seed=5)[0] for o, n in ((0, 10), (10, 1), (11, 12))]
+    np.testing.assert_array_equal(rows, np.concatenate(parts))
+
+
+def test_tiny_and_degenerate_shapes(eng):
+    """Two latent variables (effects: total == direct), single-item blocks, and N barely above P."""
+    rng = np.random.default_rng(1)
+    eta = rng.standard_normal((40, 1))
+    X = np.concatenate([eta + 0.5 * rng.standard_normal((40, 3)), 0.7 * eta + 0.5 * rng.standard_normal((40, 1))], axis=1)
+    path = np.array([[0, 0], [1, 0]], dtype=np.int8)
+    for scheme in ("centroid", "factorial", "path"):
+        for policy in (1, 2):
+            model = eng.Model([3, 1], [0, 0], path, True, tile_policy=policy)
+            data = eng.Data(model, X)
+            got = eng.fit(model, data, scheme)
+            check_fit(got, orc.fit(X, [3, 1], [0, 0], path, scheme, True))
+            idx = rng.integers(0, 40, (11, 40), dtype=np.int32)
+            rows, status, iters = eng.bootstrap(model, data, scheme, 0, 11, idx=idx)
+            orows, oiters, ostatus = orc.bootstrap(X, idx, [3, 1], [0, 0], path, scheme, True)
+            np.testing.assert_array_equal(iters, oiters)
+            np.testing.assert_allclose(rows, orows, rtol=REL, atol=1e-9)
+    X2 = rng.standard_normal((12, 2)) + np.arange(12)[:, None] * 0.3   # all blocks single-item
+    model = eng.Model([1, 1], [0, 0], path, False)
+    data = eng.Data(model, X2)
+    got = eng.fit(model, data, "centroid")
+    check_fit(got, orc.fit(X2, [1, 1], [0, 0], path, "centroid", False))
+    np.testing.assert_allclose(np.abs(got["loadings"]), 1.0, rtol=1e-12)
