@@ -357,6 +357,7 @@ __global__ void make_half_kernel(const double* __restrict__ X, int64_t N, int Pp
 // (8 doubles) once for all of them, and the partial dot products are combined with a shuffle butterfly.
 // t is computed in fp64; only the product with the multiplicity is rounded to fp16.
 constexpr int SG_MAX_ROWS = 32, SG_RPT = 4, SG_THREADS = 256;
+template <bool SINGLE_SLOT>  // every block fits one slot (nsl_pad == 1): no shuffle butterfly, idle lanes skip the rows
 __global__ void __launch_bounds__(SG_THREADS) scoregen_kernel(const double* __restrict__ X,
                                                               const uint32_t* __restrict__ counts,
                                                               const double* __restrict__ wf,
@@ -366,16 +367,16 @@ __global__ void __launch_bounds__(SG_THREADS) scoregen_kernel(const double* __re
                                                               int64_t nrep, int64_t i0, int rc, __half* __restrict__ B) {
   extern __shared__ __align__(16) double sg_smem[];
   double* xs = sg_smem;                                     // [SG_ROWS][Ppad]  (SG_ROWS <= 32 rows per tile)
-  float* cs = reinterpret_cast<float*>(xs + (size_t)SG_ROWS * Ppad);  // [reps_per_cta][SG_ROWS]
+  double* cs = xs + (size_t)SG_ROWS * Ppad;                 // [SG_ROWS][reps_per_cta] multiplicities as fp64
   int nbl = SG_THREADS / (L * nsl_pad);                     // replicate lanes per CTA (same rule on the host)
-  if (nsl_pad == 1 && nbl >= 4) nbl = (SG_THREADS / 32 / ((L + 7) >> 3)) * 4;
+  if (SINGLE_SLOT && nbl >= 4) nbl = (SG_THREADS / 32 / ((L + 7) >> 3)) * 4;
   const int reps_per_cta = nbl * SG_RPT;
   const int64_t rep0 = (int64_t)blockIdx.y * reps_per_cta;
   // Thread -> (replicate lane bl, latent variable l, slot sub).  Single-slot blocks: a warp is 8 LVs x 4
   // replicate lanes, so the 32 LDS.128 of a row touch only 8 distinct slots (2 wavefronts instead of 4).
-  int item, sub, bl, l;
+  int sub, bl, l;
   bool active;
-  if (nsl_pad == 1 && nbl >= 4) {
+  if (SINGLE_SLOT && nbl >= 4) {
     const int lvg = (L + 7) >> 3, w = threadIdx.x >> 5, ln = threadIdx.x & 31;
     l = (w % lvg) * 8 + (ln & 7);
     bl = (w / lvg) * 4 + (ln >> 3);
@@ -383,33 +384,36 @@ __global__ void __launch_bounds__(SG_THREADS) scoregen_kernel(const double* __re
     active = l < L && bl < nbl;
     l = min(l, L - 1);
     bl = min(bl, nbl - 1);
-    item = 0;
   } else {
-    item = threadIdx.x / nsl_pad;
+    const int item = threadIdx.x / nsl_pad;
     sub = threadIdx.x - item * nsl_pad;
     bl = min(item / L, nbl - 1);
     l = item % L;
     active = item < nbl * L;                                // (whole lane groups are active or not)
   }
-  (void)item;
   const bool has_slot = sub < ((lv_k[l] + SLOT - 1) >> 3);
   const int slot = (lv_off[l] >> 3) + (has_slot ? sub : 0);
   const int rot = (slot >> 1) & 3;  // rotated chunk order: the 64-byte slot stride would alias shared-memory banks
   double w[SG_RPT][8], shv[SG_RPT];
-  bool ok[SG_RPT];
+  __half* out[SG_RPT];                                      // B + bb*L + l of the thread's replicates (null: no store)
 #pragma unroll
   for (int j = 0; j < SG_RPT; ++j) {
     const int64_t bb = rep0 + bl * SG_RPT + j;
-    ok[j] = bb < nrep;
-    shv[j] = (ok[j] && sub == 0) ? sh[bb * L + l] : 0.0;
+    const bool ok = bb < nrep;
+    out[j] = (ok && active && sub == 0) ? B + bb * L + l : nullptr;
+    shv[j] = (ok && sub == 0) ? sh[bb * L + l] : 0.0;
 #pragma unroll
     for (int ch = 0; ch < 4; ++ch) {
       const int col = slot * SLOT + 2 * ((ch + rot) & 3);
-      w[j][2 * ch] = (ok[j] && has_slot) ? wf[bb * Ppad + col] : 0.0;
-      w[j][2 * ch + 1] = (ok[j] && has_slot) ? wf[bb * Ppad + col + 1] : 0.0;
+      w[j][2 * ch] = (ok && has_slot) ? wf[bb * Ppad + col] : 0.0;
+      w[j][2 * ch + 1] = (ok && has_slot) ? wf[bb * Ppad + col + 1] : 0.0;
     }
   }
   const int64_t ldb = nrep * L;
+  const double* xcol = xs + slot * SLOT;
+  int xo[4];
+#pragma unroll
+  for (int ch = 0; ch < 4; ++ch) xo[ch] = 2 * ((ch + rot) & 3);
   // the block weights stay in registers while the CTA walks its share of the chunk's row tiles
   for (int row0 = blockIdx.x * SG_ROWS; row0 < rc; row0 += gridDim.x * SG_ROWS) {
     const int rows = min(SG_ROWS, rc - row0);
@@ -419,35 +423,36 @@ __global__ void __launch_bounds__(SG_THREADS) scoregen_kernel(const double* __re
       xs[e] = (r < rows) ? X[(i0 + row0) * Ppad + e] : 0.0;
     }
     for (int e = threadIdx.x; e < reps_per_cta * SG_ROWS; e += SG_THREADS) {
-      const int eb = e / SG_ROWS, r = e - eb * SG_ROWS;
+      const int eb = e / SG_ROWS, r = e - eb * SG_ROWS;     // consecutive threads: consecutive rows of one replicate
       const int64_t bb = rep0 + eb;
-      float c = 0.f;
-      if (r < rows && bb < nrep) c = counts ? (float)counts[bb * N + i0 + row0 + r] : 1.f;
-      cs[e] = c;
+      double c = 0.0;
+      if (r < rows && bb < nrep) c = counts ? (double)counts[bb * N + i0 + row0 + r] : 1.0;
+      cs[r * reps_per_cta + eb] = c;
     }
     __syncthreads();
-    // (inactive lane groups run along so that the full-mask shuffles below are well defined)
-      for (int r = 0; r < rows; ++r) {
-        double x[8];
+    if (SINGLE_SLOT && !active) continue;  // (with lane groups everyone runs along: full-mask shuffles below)
+    const double* cr = cs + bl * SG_RPT;
+    int64_t orow = (int64_t)row0 * ldb;
+    for (int r = 0; r < rows; ++r, orow += ldb) {
+      double x[8];
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          const double2 v =
-              *reinterpret_cast<const double2*>(xs + (size_t)r * Ppad + slot * SLOT + 2 * ((ch + rot) & 3));
-          x[2 * ch] = v.x; x[2 * ch + 1] = v.y;
-        }
-#pragma unroll
-        for (int j = 0; j < SG_RPT; ++j) {
-          double t = -shv[j];
-#pragma unroll
-          for (int k = 0; k < 8; ++k) t = fma(x[k], w[j][k], t);
-          for (int o = nsl_pad >> 1; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-          if (ok[j] && sub == 0 && active) {
-            const int64_t bb = rep0 + bl * SG_RPT + j;
-            B[(int64_t)(row0 + r) * ldb + bb * L + l] =
-                __double2half((double)cs[(bl * SG_RPT + j) * SG_ROWS + r] * t);
-          }
-        }
+      for (int ch = 0; ch < 4; ++ch) {
+        const double2 v = *reinterpret_cast<const double2*>(xcol + (size_t)r * Ppad + xo[ch]);
+        x[2 * ch] = v.x; x[2 * ch + 1] = v.y;
       }
+      const double2 c01 = *reinterpret_cast<const double2*>(cr + r * reps_per_cta);
+      const double2 c23 = *reinterpret_cast<const double2*>(cr + r * reps_per_cta + 2);
+      const double cj[4] = {c01.x, c01.y, c23.x, c23.y};
+#pragma unroll
+      for (int j = 0; j < SG_RPT; ++j) {
+        double t = -shv[j];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t = fma(x[k], w[j][k], t);
+        if (!SINGLE_SLOT)
+          for (int o = nsl_pad >> 1; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (out[j]) out[j][orow] = __double2half(cj[j] * t);
+      }
+    }
   }
 }
 
@@ -1341,9 +1346,10 @@ static int run_batch(plspm_data* d, int64_t nb, const uint32_t* counts_dev, cons
       if (nsl_pad == 1 && nbl_host >= 4) nbl_host = (SG_THREADS / 32 / ((h.L + 7) / 8)) * 4;
       const int reps_per_cta = std::max(1, nbl_host) * SG_RPT;
       const int SG_ROWS = (int)std::max<size_t>(1, std::min<size_t>(SG_MAX_ROWS, (size_t)(d->max_smem - 16384) /
-                                                                                  ((size_t)h.Ppad * 8 + reps_per_cta * 4)));
-      const size_t sg_smem = (size_t)SG_ROWS * h.Ppad * 8 + (size_t)reps_per_cta * SG_ROWS * 4;
-      CK(cudaFuncSetAttribute(scoregen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sg_smem));
+                                                                                  ((size_t)h.Ppad * 8 + reps_per_cta * 8)));
+      const size_t sg_smem = (size_t)SG_ROWS * h.Ppad * 8 + (size_t)reps_per_cta * SG_ROWS * 8;
+      auto sg_kernel = (nsl_pad == 1) ? scoregen_kernel<true> : scoregen_kernel<false>;
+      CK(cudaFuncSetAttribute(sg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sg_smem));
       const float one = 1.f, zero = 0.f;
       for (int64_t i0 = 0; i0 < d->N; i0 += FAST_RC) {
         const int rc = (int)std::min<int64_t>(FAST_RC, d->N - i0);
@@ -1352,7 +1358,7 @@ static int run_batch(plspm_data* d, int64_t nb, const uint32_t* counts_dev, cons
                                                                             (4 * d->sm_count + gy - 1) / gy));
         dim3 grid_sg(gx, gy);
         d->timer.begin(ST_SCOREGEN, st);
-        scoregen_kernel<<<grid_sg, SG_THREADS, sg_smem, st>>>(d->X, counts_dev, D(bb.wf), D(bb.sh), d->N, h.Ppad, h.L,
+        sg_kernel<<<grid_sg, SG_THREADS, sg_smem, st>>>(d->X, counts_dev, D(bb.wf), D(bb.sh), d->N, h.Ppad, h.L,
                                                              m->dv.lv_off, m->dv.lv_k, nsl_pad, SG_ROWS, nb, i0, rc, BT);
         d->timer.end(st);
         CK(cudaGetLastError());
