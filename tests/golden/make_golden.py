@@ -283,6 +283,67 @@ def main():
     fs = Estimator(cfg).hoc_path_first_stage(cfg)
     syn["hoc/first_stage_lvs"] = np.array([str(v) for v in fs.index])
     syn["hoc/first_stage_path"] = fs.values.astype(np.int8)
+    # ---- nonmetric path with numeric scales (groundwork for f3): russa + mobi, Scale.NUM --------------
+    from plspm.scale import Scale
+    nm = {}
+    russa = pd.read_csv(os.path.join(tdata, "russa.csv"), index_col=0)
+    st = c.Structure()
+    st.add_path(["AGRI", "IND"], ["POLINS"])
+    rpath = st.path()
+    rblocks = {"AGRI": ["gini", "rent", "farm"], "IND": ["gnpr", "labo"], "POLINS": ["ecks", "death", "demo", "inst"]}
+    rlvs = list(rpath)
+    rmvs = [m for lv in rlvs for m in rblocks[lv]]
+    nm["russa/X"] = russa.loc[:, rmvs].values.astype(np.float64)
+    nm["russa/path"] = rpath.loc[rlvs, rlvs].values.astype(np.int8)
+    nm["russa/block_sizes"] = np.array([len(rblocks[lv]) for lv in rlvs], dtype=np.int32)
+    nm["russa/lvs"] = np.array(rlvs)
+    nm["russa/mvs"] = np.array(rmvs)
+    for sname, scheme in SCHEMES.items():
+        for mname, mode in (("A", Mode.A), ("B", Mode.B)):
+            cfg = c.Config(rpath, default_scale=Scale.NUM)
+            for lv in rlvs:
+                cfg.add_lv(lv, mode, *[c.MV(m) for m in rblocks[lv]])
+            calc = Plspm(russa, cfg, scheme, 100, 1e-7)
+            tag = "russa/%s/%s/" % (sname, mname)
+            om = calc.outer_model()
+            nm[tag + "weights"] = om.loc[rmvs, "weight"].values.astype(np.float64)
+            nm[tag + "loadings"] = om.loc[rmvs, "loading"].values.astype(np.float64)
+            nm[tag + "scores"] = calc.scores().loc[:, rlvs].values.astype(np.float64)
+            nm[tag + "path_coefficients"] = calc.path_coefficients().loc[rlvs, rlvs].values.astype(np.float64)
+            nm[tag + "crossloadings"] = calc.crossloadings().loc[rmvs, rlvs].values.astype(np.float64)
+    for tag, fn in (("centroid", "russa.outer_model.csv"), ("path", "russa.outer_model_path.csv"),
+                    ("factorial", "russa.outer_model_factorial.csv")):
+        om = pd.read_csv(os.path.join(tdata, fn), index_col=0).loc[rmvs]
+        nm["R/russa/%s/weight" % tag] = om["weight"].values.astype(np.float64)
+        nm["R/russa/%s/loading" % tag] = om["loading"].values.astype(np.float64)
+    nm["R/russa/scores"] = pd.read_csv(os.path.join(tdata, "russa.scores.csv"), index_col=0).loc[:, rlvs].values
+    mobi = pd.read_csv(os.path.join(tdata, "mobi.csv"), index_col=0)
+    st = c.Structure()
+    st.add_path(["Expectation", "Quality"], ["Loyalty"])
+    st.add_path(["Image"], ["Expectation"])
+    st.add_path(["Complaints"], ["Loyalty"])
+    mpath = st.path()
+    mlvs = list(mpath)
+    prefix = {"Expectation": "CUEX", "Quality": "PERQ", "Loyalty": "CUSL", "Image": "IMAG", "Complaints": "CUSCO"}
+    mmode = {"Expectation": Mode.A, "Quality": Mode.B, "Loyalty": Mode.A, "Image": Mode.A, "Complaints": Mode.A}
+    mblocks = {lv: [m for m in mobi.columns if m.startswith(prefix[lv])] for lv in mlvs}
+    mmvs = [m for lv in mlvs for m in mblocks[lv]]
+    cfg = c.Config(mpath, default_scale=Scale.NUM)
+    for lv in mlvs:
+        cfg.add_lv(lv, mmode[lv], *[c.MV(m) for m in mblocks[lv]])
+    calc = Plspm(mobi, cfg, Scheme.PATH, 100, 1e-8)
+    nm["mobi/X"] = mobi.loc[:, mmvs].values.astype(np.float64)
+    nm["mobi/path"] = mpath.loc[mlvs, mlvs].values.astype(np.int8)
+    nm["mobi/block_sizes"] = np.array([len(mblocks[lv]) for lv in mlvs], dtype=np.int32)
+    nm["mobi/modes"] = np.array([0 if mmode[lv] == Mode.A else 1 for lv in mlvs], dtype=np.int8)
+    nm["mobi/weights"] = calc.outer_model().loc[mmvs, "weight"].values.astype(np.float64)
+    nm["mobi/loadings"] = calc.outer_model().loc[mmvs, "loading"].values.astype(np.float64)
+    nm["mobi/path_coefficients"] = calc.path_coefficients().loc[mlvs, mlvs].values.astype(np.float64)
+    som = pd.read_csv(os.path.join(tdata, "seminr-mobi-basic-outer-model.csv"), index_col=0).loc[mmvs]
+    nm["R/mobi/weight"] = som["weight"].values.astype(np.float64)
+    nm["R/mobi/loading"] = som["loading"].values.astype(np.float64)
+    assert not [k for k, v in nm.items() if np.asarray(v).dtype == object]
+    np.savez_compressed(os.path.join(HERE, "nonmetric.npz"), **nm)
     syn["cases"] = np.array([cs[0] for cs in cases])
     assert not [k for k, v in syn.items() if np.asarray(v).dtype == object]
     np.savez_compressed(os.path.join(HERE, "synthetic.npz"), **syn)

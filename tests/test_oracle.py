@@ -177,3 +177,41 @@ def test_missing_values_are_mean_imputed():
 def test_not_converged_raises(sat):
     with pytest.raises(orc.NotConverged):
         orc.fit(sat["X"], sat["block_sizes"], [1] * 6, sat["path"], "centroid", True, tol=1e-30, max_iter=3)
+
+
+# ---- nonmetric path with numeric scales (groundwork for SURVEY §8(f) row f3) ---------------------
+@pytest.fixture(scope="module")
+def nm():
+    import os
+    from tests.conftest import GOLDEN
+    return np.load(os.path.join(GOLDEN, "nonmetric.npz"), allow_pickle=False)
+
+
+@pytest.mark.parametrize("scheme", SCHEMES)
+@pytest.mark.parametrize("mode", ("A", "B"))
+def test_nonmetric_num_russa_vs_reference(nm, scheme, mode):
+    from oracle import plspm_oracle_nonmetric as onm
+    L = len(nm["russa/block_sizes"])
+    r = onm.fit_num(nm["russa/X"], nm["russa/block_sizes"], [0 if mode == "A" else 1] * L, nm["russa/path"], scheme,
+                    tol=1e-7)
+    tag = "russa/%s/%s/" % (scheme, mode)
+    np.testing.assert_allclose(r["weights"], nm[tag + "weights"], rtol=1e-8)
+    np.testing.assert_allclose(r["scores"], nm[tag + "scores"], rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(r["loadings"], nm[tag + "loadings"], rtol=1e-8)
+    np.testing.assert_allclose(r["path_coefficients"], nm[tag + "path_coefficients"], rtol=1e-8, atol=1e-12)
+    np.testing.assert_allclose(r["crossloadings"], nm[tag + "crossloadings"], rtol=1e-8, atol=1e-12)
+
+
+def test_nonmetric_num_r_golden(nm):
+    from oracle import plspm_oracle_nonmetric as onm
+    for scheme in SCHEMES:
+        r = onm.fit_num(nm["russa/X"], nm["russa/block_sizes"], [0] * 3, nm["russa/path"], scheme, tol=1e-7)
+        np.testing.assert_allclose(r["weights"], nm["R/russa/%s/weight" % scheme], rtol=1e-7)
+        np.testing.assert_allclose(r["loadings"], nm["R/russa/%s/loading" % scheme], rtol=1e-7)
+    r = onm.fit_num(nm["russa/X"], nm["russa/block_sizes"], [0] * 3, nm["russa/path"], "centroid", tol=1e-7)
+    np.testing.assert_allclose(r["scores"], nm["R/russa/scores"], rtol=1e-7, atol=1e-10)
+    m = onm.fit_num(nm["mobi/X"], nm["mobi/block_sizes"], nm["mobi/modes"], nm["mobi/path"], "path", tol=1e-8)
+    np.testing.assert_allclose(m["weights"], nm["mobi/weights"], rtol=1e-8)
+    np.testing.assert_allclose(m["path_coefficients"], nm["mobi/path_coefficients"], rtol=1e-8, atol=1e-12)
+    np.testing.assert_allclose(m["weights"], nm["R/mobi/weight"], rtol=1e-5)   # reference test_regression_seminr.py:42
+    np.testing.assert_allclose(m["loadings"], nm["R/mobi/loading"], rtol=1e-5)
