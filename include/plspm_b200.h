@@ -51,8 +51,13 @@ int plspm_model_create(int32_t L, const int32_t* block_sizes, const int8_t* mode
                        int32_t scaled, int32_t tile_policy, plspm_model** out);
 void plspm_model_destroy(plspm_model* m);
 /* info[16]: 0 L, 1 P, 2 padded P, 3 tiles, 4 tile groups, 5 LV pairs, 6 effect rows, 7 doubles per
- * bootstrap row (2P + L + 2*effects), 8 full tile set, 9 scaled, 10 cross-moment tiles */
+ * bootstrap row (2P + L + 2*effects), 8 full tile set, 9 scaled, 10 cross-moment tiles, 11 numeric */
 int plspm_model_query(const plspm_model* m, int32_t* info);
+/* on != 0 selects the reference's non-metric estimator for data whose manifest variables all carry
+ * Scale.NUM or Scale.RAW (config.py:306-319 treatment, weights.py:73-133 `_NonmetricWeights`, mode.py
+ * 31-42 / 54-61): columns standardised per (re)sample, no sign vote, stopping rule on the scores.  The
+ * `scaled` flag of the model is ignored on this path (the reference ignores it too). */
+int plspm_model_set_numeric(plspm_model* m, int32_t on);
 /* (from, to) LV ids of the effect rows, in the row order of InnerModel.effects()
  * (inner_model.py:50-60).  Arrays of info[6] entries. */
 int plspm_model_effects(const plspm_model* m, int32_t* from, int32_t* to);
@@ -60,6 +65,8 @@ int plspm_model_effects(const plspm_model* m, int32_t* from, int32_t* to);
 /* Replaces Config.filter's column selection + the data side of Config.treat
  * (config.py:269, 299-305): uploads X (row-major N x P doubles, leading dimension ld, host or
  * device pointer) once and keeps it resident for any number of fits / bootstrap calls. */
+/* A data handle depends only on the column layout (block sizes in path order) of the model it was created
+ * with; plspm_fit / plspm_bootstrap accept it together with any model of the same layout. */
 int plspm_data_create(const plspm_model* m, const double* X, int64_t N, int64_t ld, int32_t x_is_device,
                       plspm_data** out);
 void plspm_data_destroy(plspm_data* d);

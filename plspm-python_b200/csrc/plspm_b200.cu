@@ -31,6 +31,7 @@
 #include "../../include/plspm_b200.h"
 #include "plspm_model.h"
 #include "solver_core.h"
+#include "solver_num.h"
 
 using namespace plspm;
 
@@ -50,7 +51,7 @@ static int fail(int code, const std::string& msg) {
                   std::string(#expr) + ": " + cudaGetErrorString(e_));                             \
   } while (0)
 
-enum { ST_COUNTS = 0, ST_GRAM = 1, ST_REDUCE = 2, ST_SOLVE = 3, ST_SCORES = 4, ST_UPLOAD = 5, ST_COLSUM = 6, ST_CROSS = 7, ST_SCOREGEN = 8, ST_N = 12 };
+enum { ST_COUNTS = 0, ST_GRAM = 1, ST_REDUCE = 2, ST_SOLVE = 3, ST_SCORES = 4, ST_UPLOAD = 5, ST_COLSUM = 6, ST_CROSS = 7, ST_SCOREGEN = 8, ST_CONV = 9, ST_N = 12 };
 struct Profile {
   std::mutex mu;
   double ms[ST_N] = {0};
@@ -167,6 +168,7 @@ struct StageTimer {
 struct plspm_model {
   HostModel h;
   int device = 0;
+  bool numeric = false;  // non-metric treatment with numeric scales (plspm_model_set_numeric)
   std::vector<void*> dev_allocs;
   ModelView dv;  // device pointers
 };
@@ -454,6 +456,142 @@ __global__ void __launch_bounds__(SG_THREADS) scoregen_kernel(const double* __re
       }
     }
   }
+}
+
+// Stopping criterion of the non-metric path (weights.py:120), per replicate:
+//   conv[b] = sum_l sum_i c_bi ( |x~_i . coef_old,l - sh_old,l| - |x~_i . coef_new,l - sh_new,l| )^2
+// Same thread mapping and tile walk as scoregen_kernel (lane groups of nsl_pad slots per (replicate
+// lane, LV)), two replicates per thread, both coefficient sets in registers.  Every CTA writes one partial
+// per replicate; num_step_kernel adds the partials in a fixed order.
+constexpr int CV_RPT = 2;
+__global__ void __launch_bounds__(SG_THREADS) conv_kernel(const double* __restrict__ X, const uint32_t* __restrict__ counts,
+                                                          const double* __restrict__ coef_old,
+                                                          const double* __restrict__ coef_new,
+                                                          const double* __restrict__ sh_old,
+                                                          const double* __restrict__ sh_new, const int* __restrict__ meta,
+                                                          int64_t N, int Ppad, int L, const int* __restrict__ lv_off,
+                                                          const int* __restrict__ lv_k, int nsl_pad, int ROWS,
+                                                          int64_t nrep, double* __restrict__ conv_part) {
+  extern __shared__ __align__(16) double cv_smem[];
+  double* xs = cv_smem;                                     // [ROWS][Ppad]
+  double* cs = xs + (size_t)ROWS * Ppad;                    // [ROWS][reps_per_cta]
+  double* part = cs + (size_t)ROWS * (SG_THREADS / (L * nsl_pad)) * CV_RPT;  // [SG_THREADS][CV_RPT]
+  const int nbl = SG_THREADS / (L * nsl_pad);
+  const int reps_per_cta = nbl * CV_RPT;
+  const int64_t rep0 = (int64_t)blockIdx.y * reps_per_cta;
+  const int item = threadIdx.x / nsl_pad, sub = threadIdx.x - item * nsl_pad;
+  const int bl = min(item / L, nbl - 1), l = item % L;
+  const bool active = item < nbl * L;
+  const bool has_slot = sub < ((lv_k[l] + SLOT - 1) >> 3);
+  const int slot = (lv_off[l] >> 3) + (has_slot ? sub : 0);
+  const int rot = (slot >> 1) & 3;
+  double wo[CV_RPT][8], wn[CV_RPT][8], so[CV_RPT], sn[CV_RPT], acc[CV_RPT];
+  bool live[CV_RPT];
+#pragma unroll
+  for (int j = 0; j < CV_RPT; ++j) {
+    const int64_t bb = rep0 + bl * CV_RPT + j;
+    live[j] = bb < nrep && meta[bb * 4 + 1] == 0;  // finished replicates are skipped
+    acc[j] = 0.0;
+    so[j] = (live[j] && sub == 0) ? sh_old[bb * L + l] : 0.0;
+    sn[j] = (live[j] && sub == 0) ? sh_new[bb * L + l] : 0.0;
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) {
+      const int col = slot * SLOT + 2 * ((ch + rot) & 3);
+      const bool ld = live[j] && has_slot;
+      wo[j][2 * ch] = ld ? coef_old[bb * Ppad + col] : 0.0;
+      wo[j][2 * ch + 1] = ld ? coef_old[bb * Ppad + col + 1] : 0.0;
+      wn[j][2 * ch] = ld ? coef_new[bb * Ppad + col] : 0.0;
+      wn[j][2 * ch + 1] = ld ? coef_new[bb * Ppad + col + 1] : 0.0;
+    }
+  }
+  for (int64_t row0 = (int64_t)blockIdx.x * ROWS; row0 < N; row0 += (int64_t)gridDim.x * ROWS) {
+    const int rows = (int)min((int64_t)ROWS, N - row0);
+    __syncthreads();
+    for (int e = threadIdx.x; e < ROWS * Ppad; e += SG_THREADS) {
+      const int r = e / Ppad;
+      xs[e] = (r < rows) ? X[row0 * Ppad + e] : 0.0;
+    }
+    for (int e = threadIdx.x; e < reps_per_cta * ROWS; e += SG_THREADS) {
+      const int eb = e / ROWS, r = e - eb * ROWS;
+      const int64_t bb = rep0 + eb;
+      double c = 0.0;
+      if (r < rows && bb < nrep) c = counts ? (double)counts[bb * N + row0 + r] : 1.0;
+      cs[r * reps_per_cta + eb] = c;
+    }
+    __syncthreads();
+    for (int r = 0; r < rows; ++r) {
+      double x[8];
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        const double2 v = *reinterpret_cast<const double2*>(xs + (size_t)r * Ppad + slot * SLOT + 2 * ((ch + rot) & 3));
+        x[2 * ch] = v.x; x[2 * ch + 1] = v.y;
+      }
+#pragma unroll
+      for (int j = 0; j < CV_RPT; ++j) {
+        double to = -so[j], tn = -sn[j];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { to = fma(x[k], wo[j][k], to); tn = fma(x[k], wn[j][k], tn); }
+        for (int o = nsl_pad >> 1; o > 0; o >>= 1) {
+          to += __shfl_xor_sync(0xffffffffu, to, o);
+          tn += __shfl_xor_sync(0xffffffffu, tn, o);
+        }
+        const double df = fabs(to) - fabs(tn);
+        if (sub == 0 && active) acc[j] = fma(cs[r * reps_per_cta + bl * CV_RPT + j] * df, df, acc[j]);
+      }
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < CV_RPT; ++j) part[threadIdx.x * CV_RPT + j] = (sub == 0 && active && live[j]) ? acc[j] : 0.0;
+  __syncthreads();
+  if (threadIdx.x < reps_per_cta) {  // fixed-order sum over the threads that served this replicate
+    const int eb = threadIdx.x, ebl = eb / CV_RPT, ej = eb - ebl * CV_RPT;
+    double s = 0.0;
+    for (int ll = 0; ll < L; ++ll) s += part[((ebl * L + ll) * nsl_pad) * CV_RPT + ej];
+    if (rep0 + eb < nrep) conv_part[(rep0 + eb) * gridDim.x + blockIdx.x] = s;
+  }
+}
+
+struct NumBatch {
+  ModelView M;
+  const double* G; int64_t g_stride;
+  const double* colsum;
+  double N;
+  int scheme; double tol; int max_iter;
+  const double* conv_part; int n_conv_part;
+  double* ws;
+  double *a, *coef_old, *coef_new, *shift_old, *shift_new;
+  int* meta;
+  int* n_done;
+  double* out_rows; int64_t out_stride;
+  double *weights, *loadings, *r2, *paths, *total, *crossloadings, *score_coef, *score_shift;
+  int *iters, *status;
+};
+
+__global__ void __launch_bounds__(128) num_step_kernel(const NumBatch b) {
+  extern __shared__ __align__(16) double solver_smem_num[];
+  const int64_t rep = blockIdx.x;
+  if (b.meta[rep * 4 + 1]) return;
+  NumStepArgs A;
+  A.M = b.M;
+  A.G = b.G + rep * b.g_stride;
+  A.colsum = b.colsum + rep * b.M.Ppad;
+  A.N = b.N; A.scheme = b.scheme; A.tol = b.tol; A.max_iter = b.max_iter;
+  double conv = 0.0;
+  for (int k = 0; k < b.n_conv_part; ++k) conv += b.conv_part[rep * b.n_conv_part + k];
+  A.conv_in = conv;
+  A.ws = b.ws + rep * (int64_t)b.M.ws_doubles;
+  A.a = b.a + rep * b.M.Ppad;
+  A.meta = b.meta + rep * 4;
+  A.coef_old = b.coef_old + rep * b.M.Ppad; A.coef_new = b.coef_new + rep * b.M.Ppad;
+  A.shift_old = b.shift_old + rep * b.M.L; A.shift_new = b.shift_new + rep * b.M.L;
+  A.out_row = b.out_rows ? b.out_rows + rep * b.out_stride : nullptr;
+  A.weights = b.weights; A.loadings = b.loadings; A.r2 = b.r2; A.paths = b.paths; A.total = b.total;
+  A.crossloadings = b.crossloadings; A.score_coef = b.score_coef; A.score_shift = b.score_shift;
+  A.iters = b.iters + rep; A.status = b.status + rep;
+  num_step(A, solver_smem_num);
+  __syncthreads();
+  if (threadIdx.x == 0 && A.meta[1]) atomicAdd(b.n_done, 1);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -976,7 +1114,13 @@ int plspm_model_query(const plspm_model* m, int32_t* info) {
   std::memset(info, 0, 16 * sizeof(int32_t));
   const HostModel& h = m->h;
   info[0] = h.L; info[1] = h.P; info[2] = h.Ppad; info[3] = h.n_tiles; info[4] = h.n_tg; info[5] = h.n_pairs;
-  info[6] = h.n_eff; info[7] = h.n_out(); info[8] = h.full; info[9] = h.scaled; info[10] = h.n_cross;
+  info[6] = h.n_eff; info[7] = h.n_out(); info[8] = h.full; info[9] = h.scaled; info[10] = h.n_cross; info[11] = m->numeric ? 1 : 0;
+  return PLSPM_OK;
+}
+
+int plspm_model_set_numeric(plspm_model* m, int32_t on) {
+  if (!m) return fail(PLSPM_ERR_INVALID, "null argument");
+  m->numeric = on != 0;
   return PLSPM_OK;
 }
 
@@ -984,6 +1128,14 @@ int plspm_model_effects(const plspm_model* m, int32_t* from, int32_t* to) {
   if (!m || !from || !to) return fail(PLSPM_ERR_INVALID, "null argument");
   for (int e = 0; e < m->h.n_eff; ++e) { from[e] = m->h.eff_from[e]; to[e] = m->h.eff_to[e]; }
   return PLSPM_OK;
+}
+
+// A data handle only depends on the column layout of the model it was created with (block sizes in
+// path order); any model with the same layout -- other modes, paths, tile policy, treatment -- may use it.
+static bool same_layout(const plspm_model* a, const plspm_model* b) {
+  if (a == b) return true;
+  return a && b && a->device == b->device && a->h.L == b->h.L && a->h.P == b->h.P && a->h.Ppad == b->h.Ppad &&
+         a->h.lv_off == b->h.lv_off && a->h.lv_k == b->h.lv_k && a->h.col_src == b->h.col_src;
 }
 
 static int ws_reserve(plspm_data* d, size_t bytes) {
@@ -1111,6 +1263,10 @@ struct BatchPlan {
   StreamPlan gram, cross;
   int cs_chunks = 1;  // row chunks of the column-sum kernel
   int64_t cs_chunk_rows = 0;
+  // criterion pass of the numeric non-metric path
+  int cv_nsl_pad = 1, cv_reps_per_cta = 1, cv_rows = 1;
+  unsigned cv_gx = 1, cv_gy = 1;
+  size_t cv_smem = 0;
 };
 
 static void plan_colsum(const plspm_data* d, int64_t nb, BatchPlan& g) {
@@ -1172,11 +1328,27 @@ static int plan_stream(const plspm_data* d, int64_t n_items, size_t extra_row_by
 static int plan_batch(const plspm_data* d, int64_t nb, BatchPlan& bp) {
   const HostModel& h = d->model->h;
   if (int rc = plan_stream(d, nb * h.n_tg, 0, 0, bp.gram)) return rc;
-  if (!h.full) {
+  if (!h.full && !d->model->numeric) {
     const size_t per_row = (size_t)GRAM_WARPS * h.ng * SLOT * 8;  // score scratch row of every warp
     if (int rc = plan_stream(d, nb * h.n_tg_cross, per_row, 8 * per_row, bp.cross)) return rc;
   }
   plan_colsum(d, nb, bp);
+  if (d->model->numeric) {
+    int nsl_pad = 1;
+    while (nsl_pad * SLOT < h.kmax) nsl_pad <<= 1;
+    if (nsl_pad > 32 || h.L * nsl_pad > SG_THREADS)
+      return fail(PLSPM_ERR_UNSUPPORTED, "numeric non-metric path: L x (padded slots per block) exceeds 256");
+    const int nbl = SG_THREADS / (h.L * nsl_pad);
+    bp.cv_nsl_pad = nsl_pad;
+    bp.cv_reps_per_cta = nbl * CV_RPT;
+    const size_t fixed = (size_t)SG_THREADS * CV_RPT * 8;
+    bp.cv_rows = (int)std::max<size_t>(1, std::min<size_t>(SG_MAX_ROWS, ((size_t)d->max_smem - 16384 - fixed) /
+                                                                           ((size_t)h.Ppad * 8 + bp.cv_reps_per_cta * 8)));
+    bp.cv_smem = (size_t)bp.cv_rows * h.Ppad * 8 + (size_t)bp.cv_rows * bp.cv_reps_per_cta * 8 + fixed;
+    bp.cv_gy = (unsigned)((nb + bp.cv_reps_per_cta - 1) / bp.cv_reps_per_cta);
+    bp.cv_gx = (unsigned)std::max<int64_t>(1, std::min<int64_t>((d->N + bp.cv_rows - 1) / bp.cv_rows,
+                                                                 (4 * d->sm_count + bp.cv_gy - 1) / bp.cv_gy));
+  }
   return 0;
 }
 
@@ -1189,6 +1361,8 @@ struct BatchBuffers {
   size_t counts, idx, G, Gpart, colsum, cspart, ws, out, iters, status, wf, CG, CGpart, sh, BT, Cf, rep_map;
   // single-fit outputs
   size_t weights, loadings, r2, paths, totalfx, crossl, coef, shift, scores;
+  // numeric non-metric path: per-replicate iteration state
+  size_t num_a, num_co, num_cn, num_so, num_sn, num_meta, num_done, num_cpart;
 };
 static BatchBuffers layout_batch(const plspm_data* d, int64_t nb, const BatchPlan& bp, bool with_counts, bool with_idx,
                                  bool rows_on_device_of_caller, bool single_fit, bool want_scores) {
@@ -1207,11 +1381,21 @@ static BatchBuffers layout_batch(const plspm_data* d, int64_t nb, const BatchPla
   b.out = take(rows_on_device_of_caller || single_fit ? 0 : (size_t)nb * h.n_out() * 8);
   b.iters = take((size_t)nb * 4);
   b.status = take((size_t)nb * 4);
-  b.wf = take(h.full ? 0 : (size_t)nb * h.Ppad * 8);
-  b.CG = take(h.full ? 0 : (size_t)nb * csz);
-  b.CGpart = take(!h.full && bp.cross.n_chunks > 1 ? (size_t)nb * csz * bp.cross.n_chunks : 0);
-  b.sh = take(h.full ? 0 : (size_t)nb * h.L * 8);
-  const bool fast = d->fast_vote && !single_fit;
+  const bool numeric = d->model->numeric;
+  const bool vote = !h.full && !numeric;  // sparse tile set: buffers of the cross-moment / sign-vote pass
+  b.wf = take(vote ? (size_t)nb * h.Ppad * 8 : 0);
+  b.CG = take(vote ? (size_t)nb * csz : 0);
+  b.CGpart = take(vote && bp.cross.n_chunks > 1 ? (size_t)nb * csz * bp.cross.n_chunks : 0);
+  b.sh = take(vote ? (size_t)nb * h.L * 8 : 0);
+  const bool fast = vote && d->fast_vote && !single_fit;
+  b.num_a = take(numeric ? (size_t)nb * h.Ppad * 8 : 0);
+  b.num_co = take(numeric ? (size_t)nb * h.Ppad * 8 : 0);
+  b.num_cn = take(numeric ? (size_t)nb * h.Ppad * 8 : 0);
+  b.num_so = take(numeric ? (size_t)nb * h.L * 8 : 0);
+  b.num_sn = take(numeric ? (size_t)nb * h.L * 8 : 0);
+  b.num_meta = take(numeric ? (size_t)nb * 16 : 0);
+  b.num_done = take(8);
+  b.num_cpart = take(numeric ? (size_t)nb * bp.cv_gx * 8 : 0);
   b.BT = take(fast ? (size_t)nb * h.L * FAST_RC * sizeof(__half) : 0);
   b.Cf = take(fast ? (size_t)nb * h.L * h.Ppad * sizeof(float) : 0);
   b.rep_map = take((size_t)nb * 4);
@@ -1293,6 +1477,86 @@ static int redo_exact(plspm_data* d, int64_t n_list, const int* rep_map_dev, con
   return 0;
 }
 
+// First and second moments of every replicate of a batch: Gram tiles + column sums.
+static int launch_moments(plspm_data* d, int64_t nb, const uint32_t* counts_dev, const BatchBuffers& bb,
+                          const BatchPlan& bp) {
+  const HostModel& h = d->model->h;
+  cudaStream_t st = d->stream;
+  char* base = (char*)d->ws.ptr;
+  auto D = [&](size_t o) { return (double*)(base + o); };
+  if (int rc = launch_stream(d, false, nb, counts_dev, bp.gram, D(bb.G), D(bb.Gpart), nullptr)) return rc;
+  dim3 grid_cs((h.Ppad + CS_COLS - 1) / CS_COLS, (unsigned)((nb + CS_REPS - 1) / CS_REPS), bp.cs_chunks);
+  d->timer.begin(ST_COLSUM, st);
+  const size_t cs_smem_bytes = (size_t)(CS_ROWS * CS_COLS + CS_ROWS * CS_REPS) * 8;
+  CK(cudaFuncSetAttribute(colsum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs_smem_bytes));
+  colsum_kernel<<<grid_cs, 256, cs_smem_bytes, st>>>(d->X, counts_dev, d->N, h.Ppad, nb, bp.cs_chunks, bp.cs_chunk_rows,
+                                                     bp.cs_chunks > 1 ? D(bb.cspart) : D(bb.colsum));
+  d->timer.end(st);
+  if (bp.cs_chunks > 1) {
+    d->timer.begin(ST_REDUCE, st);
+    reduce_chunks_kernel<<<d->sm_count, 256, 0, st>>>(D(bb.cspart), nb, bp.cs_chunks, h.Ppad, D(bb.colsum));
+    d->timer.end(st);
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// Numeric non-metric path (solver_num.h): the stopping rule is evaluated on the scores, so the outer
+// iteration is driven from here -- one num_step launch (all unfinished replicates advance by one
+// iteration, or finish) and one criterion pass over X per iteration.
+static int run_batch_num(plspm_data* d, int64_t nb, const uint32_t* counts_dev, const BatchBuffers& bb, int scheme,
+                         double tol, int max_iter, const BatchPlan& bp, double* out_rows, bool single_fit) {
+  const plspm_model* m = d->model;
+  const HostModel& h = m->h;
+  cudaStream_t st = d->stream;
+  char* base = (char*)d->ws.ptr;
+  auto D = [&](size_t o) { return (double*)(base + o); };
+  if (int rc = launch_moments(d, nb, counts_dev, bb, bp)) return rc;
+  NumBatch b;
+  std::memset(&b, 0, sizeof(b));
+  b.M = m->dv;
+  b.G = D(bb.G); b.g_stride = (int64_t)h.n_tiles * TILE;
+  b.colsum = D(bb.colsum);
+  b.N = (double)d->N; b.scheme = scheme; b.tol = tol; b.max_iter = max_iter;
+  b.conv_part = D(bb.num_cpart); b.n_conv_part = (int)bp.cv_gx;
+  b.ws = D(bb.ws);
+  b.a = D(bb.num_a); b.coef_old = D(bb.num_co); b.coef_new = D(bb.num_cn);
+  b.shift_old = D(bb.num_so); b.shift_new = D(bb.num_sn);
+  b.meta = (int*)(base + bb.num_meta); b.n_done = (int*)(base + bb.num_done);
+  b.out_rows = out_rows; b.out_stride = h.n_out();
+  b.iters = (int*)(base + bb.iters); b.status = (int*)(base + bb.status);
+  if (single_fit) {
+    b.weights = D(bb.weights); b.loadings = D(bb.loadings); b.r2 = D(bb.r2); b.paths = D(bb.paths);
+    b.total = D(bb.totalfx); b.crossloadings = D(bb.crossl); b.score_coef = D(bb.coef); b.score_shift = D(bb.shift);
+  }
+  CK(cudaMemsetAsync(b.meta, 0, (size_t)nb * 16, st));
+  CK(cudaMemsetAsync(b.n_done, 0, 8, st));
+  CK(cudaMemsetAsync(D(bb.num_cpart), 0, (size_t)nb * bp.cv_gx * 8, st));
+  const size_t smem = h.solver_smem_doubles() * sizeof(double);
+  if (smem > (size_t)d->max_smem) return fail(PLSPM_ERR_UNSUPPORTED, "model too large for the solver's shared memory");
+  CK(cudaFuncSetAttribute(num_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CK(cudaFuncSetAttribute(conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bp.cv_smem));
+  const unsigned gy = (unsigned)((nb + bp.cv_reps_per_cta - 1) / bp.cv_reps_per_cta);
+  int done = 0;
+  for (int step = 0; step < max_iter + 4; ++step) {
+    d->timer.begin(ST_SOLVE, st);
+    num_step_kernel<<<(unsigned)nb, 128, smem, st>>>(b);
+    d->timer.end(st);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(&done, b.n_done, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (done >= nb) break;
+    d->timer.begin(ST_CONV, st);
+    conv_kernel<<<dim3(bp.cv_gx, gy), SG_THREADS, bp.cv_smem, st>>>(
+        d->X, counts_dev, b.coef_old, b.coef_new, b.shift_old, b.shift_new, b.meta, d->N, h.Ppad, h.L, m->dv.lv_off,
+        m->dv.lv_k, bp.cv_nsl_pad, bp.cv_rows, nb, D(bb.num_cpart));
+    d->timer.end(st);
+    CK(cudaGetLastError());
+  }
+  if (done < nb) return fail(PLSPM_ERR_CUDA, "numeric non-metric iteration did not terminate");
+  return 0;
+}
+
 // Shared implementation of fit (counts == null, one "replicate") and bootstrap batches.
 static int run_batch(plspm_data* d, int64_t nb, const uint32_t* counts_dev, const BatchBuffers& bb, int scheme,
                      double tol, int max_iter, const BatchPlan& bp, double* out_rows, bool single_fit) {
@@ -1302,22 +1566,7 @@ static int run_batch(plspm_data* d, int64_t nb, const uint32_t* counts_dev, cons
   cudaStream_t st = d->stream;
   char* base = (char*)d->ws.ptr;
   auto D = [&](size_t o) { return (double*)(base + o); };
-  if (int rc = launch_stream(d, false, nb, counts_dev, bp.gram, D(bb.G), D(bb.Gpart), nullptr)) return rc;
-  {
-    dim3 grid_cs((h.Ppad + CS_COLS - 1) / CS_COLS, (unsigned)((nb + CS_REPS - 1) / CS_REPS), bp.cs_chunks);
-    d->timer.begin(ST_COLSUM, st);
-    const size_t cs_smem_bytes = (size_t)(CS_ROWS * CS_COLS + CS_ROWS * CS_REPS) * 8;
-    CK(cudaFuncSetAttribute(colsum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs_smem_bytes));
-    colsum_kernel<<<grid_cs, 256, cs_smem_bytes, st>>>(d->X, counts_dev, d->N, h.Ppad, nb, bp.cs_chunks, bp.cs_chunk_rows,
-                                            bp.cs_chunks > 1 ? D(bb.cspart) : D(bb.colsum));
-    d->timer.end(st);
-    if (bp.cs_chunks > 1) {
-      d->timer.begin(ST_REDUCE, st);
-      reduce_chunks_kernel<<<d->sm_count, 256, 0, st>>>(D(bb.cspart), nb, bp.cs_chunks, h.Ppad, D(bb.colsum));
-      d->timer.end(st);
-    }
-    CK(cudaGetLastError());
-  }
+  if (int rc = launch_moments(d, nb, counts_dev, bb, bp)) return rc;
   SolveBatch b;
   std::memset(&b, 0, sizeof(b));
   b.M = m->dv;
@@ -1400,9 +1649,10 @@ static int run_batch(plspm_data* d, int64_t nb, const uint32_t* counts_dev, cons
 int plspm_fit(const plspm_model* m, const plspm_data* dc, int32_t scheme, double tol, int32_t max_iter, double* weights,
               double* loadings, double* r_squared, double* paths, double* total_effects, double* crossloadings,
               double* scores, int32_t* iters, int32_t* status) {
-  if (!m || !dc || dc->model != m) return fail(PLSPM_ERR_INVALID, "model/data mismatch");
+  if (!m || !dc || !same_layout(dc->model, m)) return fail(PLSPM_ERR_INVALID, "model/data mismatch");
   if (scheme < 0 || scheme > 2) return fail(PLSPM_ERR_INVALID, "unknown scheme");
   plspm_data* d = const_cast<plspm_data*>(dc);
+  d->model = m;
   const HostModel& h = m->h;
   const int64_t N = d->N;
   const size_t L = h.L, P = h.P;
@@ -1413,7 +1663,13 @@ int plspm_fit(const plspm_model* m, const plspm_data* dc, int32_t scheme, double
   char* base = (char*)d->ws.ptr;
   auto D = [&](size_t o) { return (double*)(base + o); };
   cudaStream_t st = d->stream;
-  if (int rc = run_batch(d, 1, nullptr, bb, scheme, tol, max_iter, bp, nullptr, true)) return rc;
+  if (m->numeric) {
+    if (crossloadings && !h.full)
+      return fail(PLSPM_ERR_UNSUPPORTED, "numeric non-metric fit: crossloadings need a model with the full tile set");
+    if (int rc = run_batch_num(d, 1, nullptr, bb, scheme, tol, max_iter, bp, nullptr, true)) return rc;
+  } else if (int rc = run_batch(d, 1, nullptr, bb, scheme, tol, max_iter, bp, nullptr, true)) {
+    return rc;
+  }
   if (scores) {
     d->timer.begin(ST_SCORES, st);
     scores_kernel<<<d->sm_count * 8, 256, 0, st>>>(d->X, N, h.Ppad, h.L, m->dv.lv_off, m->dv.lv_k, D(bb.coef),
@@ -1441,11 +1697,12 @@ int plspm_fit(const plspm_model* m, const plspm_data* dc, int32_t scheme, double
 int plspm_bootstrap(const plspm_model* m, const plspm_data* dc, int32_t scheme, double tol, int32_t max_iter,
                     int64_t rep_begin, int64_t rep_count, uint64_t seed, const int32_t* idx, double* out,
                     int32_t out_is_device, int32_t* status, int32_t* iters) {
-  if (!m || !dc || dc->model != m) return fail(PLSPM_ERR_INVALID, "model/data mismatch");
+  if (!m || !dc || !same_layout(dc->model, m)) return fail(PLSPM_ERR_INVALID, "model/data mismatch");
   if (scheme < 0 || scheme > 2) return fail(PLSPM_ERR_INVALID, "unknown scheme");
   if (rep_count < 0 || !out) return fail(PLSPM_ERR_INVALID, "bad replicate range / null output");
   if (rep_count == 0) return PLSPM_OK;
   plspm_data* d = const_cast<plspm_data*>(dc);
+  d->model = m;
   const HostModel& h = m->h;
   const int64_t N = d->N;
   const size_t n_out = h.n_out();
@@ -1453,13 +1710,15 @@ int plspm_bootstrap(const plspm_model* m, const plspm_data* dc, int32_t scheme, 
     for (int64_t e = 0; e < rep_count * N; ++e)
       if (idx[e] < 0 || idx[e] >= N) return fail(PLSPM_ERR_INVALID, "resample index out of range");
   // batch size: bound the workspace (~1.5 GB) and keep the Gram grid a whole number of waves
-  const size_t per_rep = (size_t)N * 4 + ((size_t)h.n_tiles * TILE + (h.full ? 0 : (size_t)h.n_cross * TILE) +
-                                          2 * h.Ppad + h.ws_doubles + n_out) * 8 + (idx ? (size_t)N * 4 : 0) + 64;
+  const bool vote = !h.full && !m->numeric;
+  const size_t per_rep = (size_t)N * 4 + ((size_t)h.n_tiles * TILE + (vote ? (size_t)h.n_cross * TILE : 0) +
+                                          (m->numeric ? 6 : 2) * h.Ppad + h.ws_doubles + n_out) * 8 +
+                         (idx ? (size_t)N * 4 : 0) + 64;
   int64_t nb_max = std::max<int64_t>(1, (int64_t)((size_t)1536 * 1024 * 1024 / per_rep));
   if (getenv("PLSPM_MAX_BATCH")) nb_max = std::max<int64_t>(1, std::min<int64_t>(nb_max, atoll(getenv("PLSPM_MAX_BATCH"))));
   nb_max = std::min<int64_t>(nb_max, rep_count);
   const int64_t wave = (int64_t)d->sm_count * GRAM_WARPS;  // warp items per wave
-  const int64_t items_per_rep = h.full ? h.n_tg : std::max(h.n_tg, h.n_tg_cross);
+  const int64_t items_per_rep = vote ? std::max(h.n_tg, h.n_tg_cross) : h.n_tg;
   if (nb_max * items_per_rep > wave) {
     int64_t waves = nb_max * items_per_rep / wave;
     nb_max = std::max<int64_t>(1, waves * wave / items_per_rep);
@@ -1486,8 +1745,12 @@ int plspm_bootstrap(const plspm_model* m, const plspm_data* dc, int32_t scheme, 
     d->timer.end(st);
     CK(cudaGetLastError());
     double* rows = out_is_device ? out + (size_t)b0 * n_out : (double*)(base + bb.out);
-    if (int rc = run_batch(d, nb, cnt, bb, scheme, tol, max_iter, bp, rows, false)) return rc;
-    if (!h.full && d->fast_vote) {
+    if (m->numeric) {
+      if (int rc = run_batch_num(d, nb, cnt, bb, scheme, tol, max_iter, bp, rows, false)) return rc;
+    } else if (int rc = run_batch(d, nb, cnt, bb, scheme, tol, max_iter, bp, rows, false)) {
+      return rc;
+    }
+    if (vote && d->fast_vote) {
       // replicates whose low-precision sign vote was undecided are redone with exact fp64 cross moments
       std::vector<int> st_host(nb);
       CK(cudaMemcpyAsync(st_host.data(), base + bb.status, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));

@@ -109,6 +109,26 @@ class Config:
     def scaled(self):
         return self._scaled
 
+    def numeric(self):
+        """Not in the reference: True for a non-metric configuration whose manifest variables all carry
+        Scale.NUM or Scale.RAW -- the subset of the non-metric path that runs on the device."""
+        kinds = set(self._mv_scales.values())
+        return (not self._metric) and None not in kinds and kinds <= {Scale.NUM, Scale.RAW}
+
+    def check_scales(self):
+        """Scale bookkeeping of the non-metric branch (reference config.py:306-313)."""
+        if None in self._mv_scales.values():
+            raise TypeError("If you supply a scale for any MV, you must either supply a scale for all of them or specify a default scale.")
+        kinds = set(self._mv_scales.values())
+        if kinds == {Scale.RAW}:
+            self._scaled = False
+        if kinds == {Scale.RAW, Scale.NUM}:
+            self._scaled = True
+            self._mv_scales = dict.fromkeys(self._mv_scales, Scale.NUM)
+        if not kinds <= {Scale.NUM, Scale.RAW}:
+            raise NotImplementedError("ordinal / nominal scales (Scale.ORD, Scale.NOM) are outside the accelerated "
+                                      "path of plspm_b200")
+
     def scale(self, mv: str):
         return self._mv_scales[mv]
 
@@ -181,17 +201,14 @@ class Config:
         return data
 
     def treat(self, data: pd.DataFrame) -> pd.DataFrame:
-        """Centres (and, if `scaled`, divides by ONE pooled scalar) metric data (reference config.py:287-305)."""
+        """Centres (and, if `scaled`, divides by ONE pooled scalar) metric data (reference config.py:287-305);
+        standardises every column of non-metric NUM / RAW data (config.py:306-314)."""
         if not self._metric:
-            if None in self._mv_scales.values():
-                raise TypeError("If you supply a scale for any MV, you must either supply a scale for all of them or specify a default scale.")
-            kinds = set(self._mv_scales.values())
-            if kinds == {Scale.RAW}:  # config.py:309-313: scale bookkeeping of the nonmetric branch
-                self._scaled = False
-            if kinds == {Scale.RAW, Scale.NUM}:
-                self._scaled = True
-                self._mv_scales = dict.fromkeys(self._mv_scales, Scale.NUM)
-            raise NotImplementedError("nonmetric data (Scale.*) is outside the accelerated path of plspm_b200")
+            self.check_scales()
+            if self._missing:
+                raise NotImplementedError("non-metric data with missing values are outside the accelerated path")
+            n = data.shape[0]
+            return util.treat(data) / np.sqrt((n - 1) / n)  # config.py:314: unit population variance
         metric = util.impute(data) if self._missing else data
         if self._scaled:
             n = metric.shape[0]

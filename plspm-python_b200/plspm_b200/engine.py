@@ -15,13 +15,14 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libplspm_b200.so")
 
 SCHEME_IDS = {"centroid": 0, "factorial": 1, "path": 2}
+TILES_AUTO, TILES_FULL, TILES_SPARSE = 0, 1, 2
 STATUS_OK, STATUS_NOT_CONVERGED, STATUS_SINGULAR = 0, 1, 2
 
 EXPORTS = (
     "plspm_version", "plspm_last_error", "plspm_device_count", "plspm_set_device", "plspm_model_create",
     "plspm_model_destroy", "plspm_model_query", "plspm_model_effects", "plspm_data_create", "plspm_data_destroy",
     "plspm_fit", "plspm_bootstrap", "plspm_bootstrap_host", "plspm_resample_indices", "plspm_profile_reset",
-    "plspm_profile_get", "plspm_host_alloc", "plspm_host_free", "plspm_redo_count",
+    "plspm_profile_get", "plspm_host_alloc", "plspm_host_free", "plspm_redo_count", "plspm_model_set_numeric",
 )
 
 _lib = None
@@ -53,6 +54,7 @@ def load():
     lib.plspm_model_destroy.restype = None
     lib.plspm_model_query.argtypes = [vp, _c_i32p]
     lib.plspm_model_effects.argtypes = [vp, _c_i32p, _c_i32p]
+    lib.plspm_model_set_numeric.argtypes = [vp, i32]
     lib.plspm_data_create.argtypes = [vp, vp, i64, i64, i32, ctypes.POINTER(vp)]
     lib.plspm_data_destroy.argtypes = [vp]
     lib.plspm_data_destroy.restype = None
@@ -97,7 +99,7 @@ def scheme_id(scheme) -> int:
 class Model:
     """Lowered model: LV blocks (path order), modes (0 = A, 1 = B), path matrix, `scaled` flag."""
 
-    def __init__(self, block_sizes, modes, path, scaled: bool, tile_policy: int = 0):
+    def __init__(self, block_sizes, modes, path, scaled: bool, tile_policy: int = 0, numeric: bool = False):
         self.block_sizes = np.ascontiguousarray(block_sizes, dtype=np.int32)
         self.modes = np.ascontiguousarray(modes, dtype=np.int8)
         self.path = np.ascontiguousarray(path, dtype=np.int8)
@@ -109,6 +111,9 @@ class Model:
         _check(load().plspm_model_create(self.L, _ptr(self.block_sizes, _c_i32p), _ptr(self.modes, _c_i8p),
                                          _ptr(self.path, _c_i8p), int(self.scaled), int(tile_policy),
                                          ctypes.byref(self._h)))
+        self.numeric = bool(numeric)
+        if self.numeric:  # non-metric estimator for all-NUM / RAW scales (weights.py:73-133)
+            _check(load().plspm_model_set_numeric(self._h, 1))
         info = np.zeros(16, dtype=np.int32)
         _check(load().plspm_model_query(self._h, _ptr(info, _c_i32p)))
         self.P, self.Ppad, self.n_tiles, self.n_tile_groups = int(info[1]), int(info[2]), int(info[3]), int(info[4])
@@ -230,7 +235,7 @@ def resample_indices(seed: int, replicate: int, N: int) -> np.ndarray:
     return out
 
 
-STAGES = ("counts", "gram", "reduce", "solve", "scores", "upload", "colsum", "cross", "scoregen")
+STAGES = ("counts", "gram", "reduce", "solve", "scores", "upload", "colsum", "cross", "scoregen", "conv")
 
 
 def profile_reset():

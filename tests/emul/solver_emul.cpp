@@ -14,6 +14,7 @@
 
 #include "../../plspm-python_b200/csrc/plspm_model.h"
 #include "../../plspm-python_b200/csrc/solver_core.h"
+#include "../../plspm-python_b200/csrc/solver_num.h"
 
 using namespace plspm;
 
@@ -141,6 +142,81 @@ extern "C" int emul_fit(int L, const int32_t* block_sizes, const int8_t* modes, 
       A.phase = 2; A.cross = cross.data();
       solve_replicate(A, smem.data());
     }
+  }
+  if (scores && !idx)
+    for (int64_t i = 0; i < N; ++i)
+      for (int l = 0; l < L; ++l) {
+        double s = 0.0;
+        for (int c = m.lv_off[l]; c < m.lv_off[l] + m.lv_k[l]; ++c) s += Xs[i * Pp + c] * coef[c];
+        scores[i * L + l] = s - shift[l];
+      }
+  return 0;
+}
+
+
+// Non-metric (Scale.NUM / RAW) fit: host-driven outer loop around num_step(), with the score criterion
+// sum_{i,l} c_i (|y_old| - |y_new|)^2 evaluated per observation on the host (the CUDA library does this in
+// conv_kernel).
+extern "C" int emul_fit_num(int L, const int32_t* block_sizes, const int8_t* modes, const int8_t* path,
+                            int tile_policy, const double* X, int64_t N, const int32_t* idx, int scheme, double tol,
+                            int max_iter, double* out_row, double* weights, double* loadings, double* r2, double* paths,
+                            double* total, double* crossloadings, double* scores, int32_t* iters, int32_t* status) {
+  HostModel m;
+  std::string err;
+  if (build_model(L, block_sizes, modes, path, 0, tile_policy, m, err)) return 1;
+  const int P = m.P, Pp = m.Ppad;
+  std::vector<double> mu(Pp, 0.0), Xs((size_t)N * Pp, 0.0);
+  for (int p = 0; p < P; ++p) {
+    double s = 0.0;
+    for (int64_t i = 0; i < N; ++i) s += X[i * P + p];
+    mu[m.src_col[p]] = s / (double)N;
+  }
+  for (int64_t i = 0; i < N; ++i)
+    for (int p = 0; p < P; ++p) Xs[i * Pp + m.src_col[p]] = X[i * P + p] - mu[m.src_col[p]];
+  std::vector<double> cnt(N, idx ? 0.0 : 1.0);
+  if (idx)
+    for (int64_t i = 0; i < N; ++i) cnt[idx[i]] += 1.0;
+  std::vector<double> G((size_t)m.n_tiles * TILE, 0.0), colsum(Pp, 0.0);
+  for (int64_t i = 0; i < N; ++i) {
+    if (cnt[i] == 0.0) continue;
+    const double* x = &Xs[i * Pp];
+    for (int p = 0; p < Pp; ++p) colsum[p] += cnt[i] * x[p];
+    for (int t = 0; t < m.n_tiles; ++t) {
+      const double* xa = x + m.tile_sa[t] * SLOT;
+      const double* xb = x + m.tile_sb[t] * SLOT;
+      double* g = &G[(size_t)t * TILE];
+      for (int r = 0; r < SLOT; ++r)
+        for (int c = 0; c < SLOT; ++c) g[r * SLOT + c] += xa[r] * (cnt[i] * xb[c]);
+    }
+  }
+  std::vector<double> smem(m.solver_smem_doubles(), 0.0), ws(m.ws_doubles, 0.0), a(Pp, 0.0), co(Pp), cn(Pp), so(L), sn(L),
+      coef(Pp, 0.0), shift(L, 0.0);
+  int meta[4] = {0, 0, 0, 0};
+  NumStepArgs A;
+  std::memset(&A, 0, sizeof(A));
+  A.M = m.host_view();
+  A.G = G.data(); A.colsum = colsum.data(); A.N = (double)N; A.scheme = scheme; A.tol = tol; A.max_iter = max_iter;
+  A.ws = ws.data(); A.a = a.data(); A.meta = meta;
+  A.coef_old = co.data(); A.coef_new = cn.data(); A.shift_old = so.data(); A.shift_new = sn.data();
+  A.out_row = out_row; A.weights = weights; A.loadings = loadings; A.r2 = r2; A.paths = paths; A.total = total;
+  A.crossloadings = crossloadings; A.score_coef = coef.data(); A.score_shift = shift.data();
+  A.iters = iters; A.status = status;
+  A.conv_in = 0.0;
+  for (int guard = 0; guard < max_iter + 5 && !meta[1]; ++guard) {
+    num_step(A, smem.data());
+    if (meta[1]) break;
+    double conv = 0.0;
+    for (int64_t i = 0; i < N; ++i) {
+      if (cnt[i] == 0.0) continue;
+      const double* x = &Xs[i * Pp];
+      for (int l = 0; l < L; ++l) {
+        double yo = -so[l], yn = -sn[l];
+        for (int c = m.lv_off[l]; c < m.lv_off[l + 1]; ++c) { yo += x[c] * co[c]; yn += x[c] * cn[c]; }
+        const double df = std::fabs(yo) - std::fabs(yn);
+        conv += cnt[i] * df * df;
+      }
+    }
+    A.conv_in = conv;
   }
   if (scores && !idx)
     for (int64_t i = 0; i < N; ++i)

@@ -104,9 +104,18 @@ def test_scale_bookkeeping_of_nonmetric_configs():
     allraw.add_lv("AGRI", Mode.A, c.MV("gini"))
     allraw.add_lv("IND", Mode.A, c.MV("gnpr", Scale.NUM))
     allraw.add_lv("POLINS", Mode.A, c.MV("inst"))
+    df = allraw.filter(frame())
+    treated = allraw.treat(df)  # config.py:314: unit POPULATION variance per column
+    np.testing.assert_allclose(treated.to_numpy().std(axis=0, ddof=0), 1.0, rtol=1e-12)
+    np.testing.assert_allclose(treated.to_numpy().mean(axis=0), 0.0, atol=1e-12)
+    assert allraw.scaled() and allraw.scale("gini") == Scale.NUM and allraw.numeric()
+    ordinal = c.Config(three_lv_path(), default_scale=Scale.ORD)
+    ordinal.add_lv("AGRI", Mode.A, c.MV("gini"))
+    ordinal.add_lv("IND", Mode.A, c.MV("gnpr", Scale.NUM))
+    ordinal.add_lv("POLINS", Mode.A, c.MV("inst"))
+    assert not ordinal.numeric()
     with pytest.raises(NotImplementedError):
-        allraw.treat(allraw.filter(frame()))
-    assert allraw.scaled() and allraw.scale("gini") == Scale.NUM
+        ordinal.treat(ordinal.filter(frame()))
 
 
 def test_structure_builds_lower_triangular_path_in_reference_order():

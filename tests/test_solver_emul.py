@@ -161,3 +161,51 @@ def test_low_precision_vote_logic(syn):
         check(r, orc.fit(X, [K] * L, [0] * L, path, "centroid", True), L, rel=1e-8)
     finally:
         emul.set_vote_mode(0)
+
+
+# ---- non-metric path with numeric scales (solver_num.h) ------------------------------------------
+@pytest.fixture(scope="module")
+def nm():
+    import os
+    from tests.conftest import GOLDEN
+    return np.load(os.path.join(GOLDEN, "nonmetric.npz"), allow_pickle=False)
+
+
+@pytest.mark.parametrize("scheme", ("centroid", "factorial", "path"))
+@pytest.mark.parametrize("mode", (0, 1))
+def test_nonmetric_num_russa(nm, scheme, mode):
+    from oracle import plspm_oracle_nonmetric as onm
+    o = onm.fit_num(nm["russa/X"], nm["russa/block_sizes"], [mode] * 3, nm["russa/path"], scheme, tol=1e-7)
+    r = emul.fit_num(nm["russa/X"], nm["russa/block_sizes"], [mode] * 3, nm["russa/path"], scheme, tol=1e-7,
+                     tile_policy=1)
+    check(r, o, 3, rel=1e-8)
+    tag = "russa/%s/%s/" % (scheme, "AB"[mode])
+    np.testing.assert_allclose(r["weights"], nm[tag + "weights"], rtol=1e-7)
+    np.testing.assert_allclose(r["scores"], nm[tag + "scores"], rtol=1e-7, atol=1e-9)
+
+
+def test_nonmetric_num_mobi_and_synthetic(nm):
+    from oracle import plspm_oracle_nonmetric as onm
+    o = onm.fit_num(nm["mobi/X"], nm["mobi/block_sizes"], nm["mobi/modes"], nm["mobi/path"], "path", tol=1e-8)
+    r = emul.fit_num(nm["mobi/X"], nm["mobi/block_sizes"], nm["mobi/modes"], nm["mobi/path"], "path", tol=1e-8,
+                     tile_policy=1)
+    check(r, o, 5, rel=1e-8)
+    np.testing.assert_allclose(r["weights"], nm["mobi/weights"], rtol=1e-7)
+    X, path = make_synthetic(700, 7, 5, seed=4, reverse_blocks=(2,))
+    for scheme, mode in (("centroid", 0), ("factorial", 1), ("path", 0)):
+        o = onm.fit_num(X, [5] * 7, [mode] * 7, path, scheme)
+        for policy in (1, 2):
+            r = emul.fit_num(X, [5] * 7, [mode] * 7, path, scheme, tile_policy=policy)
+            check(r, o, 7, rel=1e-8, crossloadings=(policy == 1))
+    idx = np.random.default_rng(2).integers(0, 700, 700, dtype=np.int32)
+    o = onm.fit_num(X[idx], [5] * 7, [0] * 7, path, "centroid")
+    r = emul.fit_num(X, [5] * 7, [0] * 7, path, "centroid", idx=idx, tile_policy=2)
+    assert r["iterations"] == o["iterations"]
+    np.testing.assert_allclose(r["weights"], o["weights"], rtol=1e-8)
+    np.testing.assert_allclose(r["path_coefficients"], o["path_coefficients"], rtol=1e-8, atol=1e-11)
+
+
+def test_nonmetric_not_converged(nm):
+    r = emul.fit_num(nm["russa/X"], nm["russa/block_sizes"], [1] * 3, nm["russa/path"], "centroid", tol=1e-30,
+                     max_iter=3, tile_policy=1)
+    assert r["status"] == 1 and r["iterations"] == 4
