@@ -31,8 +31,6 @@ class Bootstrap:
 
     def __init__(self, config, data: pd.DataFrame, inner_model, outer_model, calculator, iterations: int,
                  num_processes: int = 1, seed: int = None, indices: np.ndarray = None):
-        session = calculator.session(data)
-        model = session.model
         rank, world = pdist.rank_world()
         if seed is None:
             seed = int(np.random.randint(0, 2 ** 31 - 1))
@@ -40,8 +38,18 @@ class Bootstrap:
         begin, count = pdist.shard_range(iterations, rank, world)
         idx = None if indices is None else np.ascontiguousarray(indices[begin:begin + count], dtype=np.int32)
         scheme, tol, its = calculator.scheme(), calculator.tolerance(), calculator.iterations()
-        buf = pdist.send_buffer(iterations, model.n_out)
-        if buf is not None:  # NCCL: the solver writes its rows straight into the all-gather send buffer
+        two_stage = bool(calculator.config().hoc())
+        buf = None
+        if two_stage:
+            session, rows, status, iters = self._two_stage_rows(calculator, data, begin, count, seed, idx)
+            model = session.model
+        else:
+            session = calculator.session(data)
+            model = session.model
+            buf = pdist.send_buffer(iterations, model.n_out)
+        if two_stage:
+            pass  # rows were produced replicate by replicate on the host side of the two engine fits
+        elif buf is not None:  # NCCL: the solver writes its rows straight into the all-gather send buffer
             _, status, iters = session.bootstrap(scheme, tol, its, begin, count, seed, idx,
                                                  out_device_ptr=buf.data_ptr())
             rows = None
@@ -52,7 +60,7 @@ class Bootstrap:
         rows = rows[status == 0]  # bootstrap.py:67-68
         w, r2, total, direct, load = model.split_row(rows)
         lvs, mvs = session.lvs, session.mvs
-        cols = list(data.columns)
+        cols = mvs if two_stage else list(data.columns)  # stage-2 manifest variables include the constituents
         weights = pd.DataFrame(w, columns=mvs).loc[:, cols]
         loadings = pd.DataFrame(load, columns=mvs).loc[:, cols]
         r_squared = pd.DataFrame(r2, columns=lvs)
@@ -68,6 +76,36 @@ class Bootstrap:
         self._loading = _create_summary(loadings, om.loc[:, "loading"])
         self._samples = dict(weights=weights, r_squared=r_squared, total_effects=total_effects, paths=paths,
                              loadings=loadings)
+
+    @staticmethod
+    def _two_stage_rows(calculator, data, begin, count, seed, idx):
+        """Higher-order constructs: the stage-2 manifest variables are the replicate's own stage-1 scores, so
+        every replicate is a two-stage estimate of its resampled rows (bootstrap.py:54-66 as written: two
+        engine fits per replicate).  Failed replicates keep status != 0 and are dropped (bootstrap.py:67-68)."""
+        from plspm.estimator import Estimator
+        from plspm_b200 import engine
+        estimator = Estimator(calculator.config())
+        n = data.shape[0]
+        rows, status, iters, session = None, np.ones(count, dtype=np.int32), np.zeros(count, dtype=np.int32), None
+        for b in range(count):
+            pick = idx[b] if idx is not None else engine.resample_indices(seed, begin + b, n)
+            try:
+                estimator.estimate(calculator, data.iloc[pick, :].reset_index(drop=True), want_final_data=False)
+            except NotImplementedError:
+                raise
+            except Exception:
+                continue
+            session, res = estimator.last_result()
+            model = session.model
+            if rows is None:
+                rows = np.zeros((count, model.n_out))
+            ef, et = model.effects_from, model.effects_to
+            rows[b] = np.concatenate([res["weights"], res["r_squared"], res["total_effects"][et, ef],
+                                      res["path_coefficients"][et, ef], res["loadings"]])
+            status[b], iters[b] = 0, res["iterations"]
+        if session is None:
+            raise Exception("Bootstrapping failed: no replicate could be estimated")
+        return session, rows, status, iters
 
     def weights(self) -> pd.DataFrame:
         """Outer weights calculated from bootstrap validation."""

@@ -5,9 +5,10 @@ The reference clones the calculator, treats the data on the host and runs the we
 treatment (config.py:299-305) is folded into the covariance the solver works on, and the iteration
 runs once.
 
-Higher-order constructs (two-stage approach, estimator.py:41-52): the stage-1 path expansion
-(`hoc_path_first_stage`) is provided and tested against the reference; the estimation itself is
-only defined for nonmetric data in the reference (see `estimate`) and is therefore not offered.
+Higher-order constructs (two-stage approach, estimator.py:41-52): two engine fits -- the expanded
+first-order model (`hoc_path_first_stage`), then the structural model with the constituents' stage-1
+scores as the construct's manifest variables.  Like the reference, only nonmetric (NUM / RAW) data can
+run it.
 """
 from typing import Tuple
 
@@ -31,12 +32,41 @@ class Estimator:
             self._last = (session, res)
             final_data = config.treat(data).loc[:, session.mvs] if want_final_data else None
             return final_data, scores, weights
-        # Higher-order constructs: in the reference only the NONMETRIC path can run the two-stage
-        # approach -- its metric path fails in stage 2 ("matrices are not aligned", weights.py:30: the
-        # stage-1 score columns are not in the outer design matrix) -- so there is no reference behaviour
-        # to reproduce for metric data, and the nonmetric path is outside the accelerated scope (f3).
-        raise NotImplementedError("higher order constructs need the nonmetric path, which is outside the "
-                                  "accelerated path of plspm_b200")
+        # Higher-order constructs, two-stage approach (estimator.py:41-52).  In the reference only the
+        # NONMETRIC path can run it -- the metric path fails in stage 2 ("matrices are not aligned",
+        # weights.py:30: the stage-1 score columns are not in the outer design matrix).
+        if config.metric():
+            raise NotImplementedError("higher order constructs need nonmetric data (set default_scale=Scale.NUM): "
+                                      "the reference's metric path cannot estimate them either")
+        from plspm.scale import Scale
+        from plspm_b200.session import EngineSession
+        self._release()
+        config = config.clone()  # the construct is added to a private copy (estimator.py:30-31)
+        stage1 = EngineSession(config, data, self._first_stage_path)
+        try:
+            res1 = stage1.fit(calculator.scheme(), calculator.tolerance(), calculator.iterations(), True)
+            first = dict(zip(stage1.lvs, res1["scores"].T))
+        finally:
+            stage1.close()
+        data2 = data.copy()
+        for hoc, members in config.hoc().items():
+            for lv in members:  # stage-1 scores of the constituents become the construct's manifest variables
+                data2[lv] = first[lv]
+            config.add_lv(hoc, config.mode(hoc), *[c.MV(lv, Scale.NUM) for lv in members])
+        session = EngineSession(config, data2, config.path())
+        self._owned = session
+        res, scores, weights = calculator.run(session)
+        self._config = config
+        self._last = (session, res)
+        final_data = config.treat(data2).loc[:, session.mvs] if want_final_data else None
+        return final_data, scores, weights
+
+    def _release(self):
+        """Closes the stage-2 engine session of a previous two-stage estimate (they are not cached)."""
+        owned = getattr(self, "_owned", None)
+        if owned is not None:
+            owned.close()
+            self._owned = None
 
     def config(self):
         return self._config

@@ -28,6 +28,8 @@ class Unidimensionality:
             k = len(mvs)
             out.loc[lv, "mode"] = cfg.mode(lv).name
             out.loc[lv, "mvs"] = k
+            if not set(mvs) <= set(self._data.columns):
+                continue  # a higher-order construct: its "manifest variables" are stage-1 scores, not data columns
             block = self._data.loc[:, mvs].to_numpy(dtype=np.float64)
             if np.isnan(block).any():
                 continue

@@ -350,5 +350,53 @@ def main():
     print("wrote fixtures to", HERE)
 
 
+def make_hoc():
+    """Higher-order construct, two-stage approach (estimator.py:41-52): the reference's own test case
+    (tests/test_regression_seminr.py:49-74) plus a Mode-B / centroid variant, with the R (seminr) values."""
+    from plspm.scale import Scale
+    tdata = os.path.join(REF, "tests", "data")
+    mobi = pd.read_csv(os.path.join(tdata, "mobi.csv"), index_col=0)
+    prefix = {"Expectation": "CUEX", "Quality": "PERQ", "Loyalty": "CUSL", "Image": "IMAG", "Complaints": "CUSCO",
+              "Value": "PERV"}
+    order = ["Expectation", "Quality", "Loyalty", "Image", "Complaints", "Value"]
+    out = {}
+    mvs_all = [m for lv in order for m in mobi.columns if m.startswith(prefix[lv])]
+    out["mobi/X"] = mobi.loc[:, mvs_all].values.astype(np.float64)
+    out["mobi/mvs"] = np.array(mvs_all)
+    for tag, scheme, hoc_mode, tol in (("path", Scheme.PATH, Mode.A, 1e-8), ("centroid_b", Scheme.CENTROID, Mode.B, 1e-7)):
+        st = c.Structure()
+        st.add_path(["Expectation", "Quality"], ["Satisfaction"])
+        st.add_path(["Satisfaction"], ["Complaints", "Loyalty"])
+        cfg = c.Config(st.path(), default_scale=Scale.NUM)
+        cfg.add_higher_order("Satisfaction", hoc_mode, ["Image", "Value"])
+        for lv in order:
+            cfg.add_lv_with_columns_named(lv, Mode.B if lv == "Quality" else Mode.A, mobi, prefix[lv])
+        calc = Plspm(mobi, cfg, scheme, 100, tol)
+        lvs = list(calc.path_coefficients().index)
+        om = calc.outer_model()
+        out[tag + "/lvs"] = np.array([str(v) for v in lvs])
+        out[tag + "/outer_index"] = np.array([str(v) for v in om.index])
+        out[tag + "/weights"] = om["weight"].values.astype(np.float64)
+        out[tag + "/loadings"] = om["loading"].values.astype(np.float64)
+        out[tag + "/communality"] = om["communality"].values.astype(np.float64)
+        out[tag + "/path_coefficients"] = calc.path_coefficients().loc[lvs, lvs].values.astype(np.float64)
+        out[tag + "/scores"] = calc.scores().loc[:, lvs].values.astype(np.float64)
+        out[tag + "/r_squared"] = calc.inner_summary().loc[lvs, "r_squared"].values.astype(np.float64)
+    r_om = pd.read_csv(os.path.join(tdata, "seminr-mobi-hoc-ts-outer-model.csv"), index_col=0)
+    r_paths = pd.read_csv(os.path.join(tdata, "seminr-mobi-hoc-ts-paths.csv"), index_col=0).transpose()
+    out["R/outer_index"] = np.array([str(v) for v in r_om.index])
+    out["R/weight"] = r_om["weight"].values.astype(np.float64)
+    out["R/loading"] = r_om["loading"].values.astype(np.float64)
+    out["R/path_lvs"] = np.array([str(v) for v in r_paths.index])
+    out["R/path_coefficients"] = r_paths.loc[list(r_paths.index), list(r_paths.index)].values.astype(np.float64)
+    assert not [k for k, v in out.items() if np.asarray(v).dtype == object]
+    np.savez_compressed(os.path.join(HERE, "hoc.npz"), **out)
+    print("wrote hoc.npz")
+
+
 if __name__ == "__main__":
-    main()
+    if "--only-hoc" in sys.argv:
+        make_hoc()
+    else:
+        main()
+        make_hoc()

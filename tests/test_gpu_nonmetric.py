@@ -176,3 +176,92 @@ def test_dropin_api_scale_num(eng, nm):
         o += k
     with pytest.raises(NotImplementedError):
         Plspm(frame, config3, Scheme.CENTROID)
+
+
+# ---- higher-order constructs, two-stage approach -----------------------------------
+MOBI_PREFIX = {"Expectation": "CUEX", "Quality": "PERQ", "Loyalty": "CUSL", "Image": "IMAG", "Complaints": "CUSCO",
+               "Value": "PERV"}
+
+
+@pytest.fixture(scope="module")
+def hz():
+    return np.load(os.path.join(GOLDEN, "hoc.npz"), allow_pickle=False)
+
+
+def mobi_hoc_config(frame, hoc_mode):
+    import plspm.config as c
+    from plspm.mode import Mode
+    from plspm.scale import Scale
+    structure = c.Structure()
+    structure.add_path(["Expectation", "Quality"], ["Satisfaction"])
+    structure.add_path(["Satisfaction"], ["Complaints", "Loyalty"])
+    config = c.Config(structure.path(), default_scale=Scale.NUM)
+    config.add_higher_order("Satisfaction", hoc_mode, ["Image", "Value"])
+    for lv in ("Expectation", "Quality", "Loyalty", "Image", "Complaints", "Value"):
+        config.add_lv_with_columns_named(lv, Mode.B if lv == "Quality" else Mode.A, frame, MOBI_PREFIX[lv])
+    return config
+
+
+@pytest.mark.parametrize("tag", ("path", "centroid_b"))
+def test_hoc_two_stage_dropin(eng, hz, tag):
+    """The reference's own higher-order test (tests/test_regression_seminr.py:49-74) through the drop-in API."""
+    from plspm.mode import Mode
+    from plspm.plspm import Plspm
+    from plspm.scheme import Scheme
+    frame = pd.DataFrame(hz["mobi/X"], columns=[str(v) for v in hz["mobi/mvs"]])
+    scheme, hoc_mode, tol = (Scheme.PATH, Mode.A, 1e-8) if tag == "path" else (Scheme.CENTROID, Mode.B, 1e-7)
+    calc = Plspm(frame, mobi_hoc_config(frame, hoc_mode), scheme, 100, tol)
+    lvs = [str(v) for v in hz[tag + "/lvs"]]
+    index = [str(v) for v in hz[tag + "/outer_index"]]
+    om = calc.outer_model()
+    assert set(om.index) == set(index)
+    np.testing.assert_allclose(om.loc[index, "weight"], hz[tag + "/weights"], rtol=REL)
+    np.testing.assert_allclose(om.loc[index, "loading"], hz[tag + "/loadings"], rtol=REL)
+    np.testing.assert_allclose(om.loc[index, "communality"], hz[tag + "/communality"], rtol=REL)
+    np.testing.assert_allclose(calc.path_coefficients().loc[lvs, lvs].to_numpy(), hz[tag + "/path_coefficients"],
+                               rtol=REL, atol=1e-9)
+    np.testing.assert_allclose(calc.scores().loc[:, lvs].to_numpy(), hz[tag + "/scores"], rtol=REL, atol=1e-8)
+    np.testing.assert_allclose(calc.inner_summary().loc[lvs, "r_squared"], hz[tag + "/r_squared"], rtol=REL, atol=1e-9)
+    if tag == "path":  # seminr values, tolerances of the reference's test
+        r_index = [str(v) for v in hz["R/outer_index"]]
+        common = [m for m in r_index if m in om.index]
+        np.testing.assert_allclose(om.loc[common, "weight"], [hz["R/weight"][r_index.index(m)] for m in common], rtol=1e-4)
+        np.testing.assert_allclose(om.loc[common, "loading"], [hz["R/loading"][r_index.index(m)] for m in common], rtol=1e-4)
+        r_lvs = [str(v) for v in hz["R/path_lvs"]]
+        np.testing.assert_allclose(calc.path_coefficients().loc[r_lvs, r_lvs].to_numpy(), hz["R/path_coefficients"],
+                                   rtol=1e-6, atol=1e-9)
+    uni = calc.unidimensionality()
+    assert np.isfinite(uni.loc["Expectation", "eig_1st"]) and np.isnan(uni.loc["Satisfaction", "eig_1st"])
+
+
+def test_hoc_bootstrap_replicates_vs_oracle(eng, hz):
+    from plspm.mode import Mode
+    from plspm.plspm import Plspm
+    from plspm.scheme import Scheme
+    mvs = [str(v) for v in hz["mobi/mvs"]]
+    X = hz["mobi/X"]
+    frame = pd.DataFrame(X, columns=mvs)
+    N = X.shape[0]
+    idx = np.random.default_rng(8).integers(0, N, size=(10, N)).astype(np.int32)
+    calc = Plspm(frame, mobi_hoc_config(frame, Mode.A), Scheme.PATH, 100, 1e-8, bootstrap=True, bootstrap_iterations=10,
+                 processes=1, bootstrap_indices=idx)
+    boot = calc.bootstrap()
+    status, _ = boot.replicate_status()
+    assert (status == 0).all()
+    lvs = list(calc.path_coefficients().index)
+    path = calc.path_coefficients().loc[lvs, lvs].to_numpy() != 0
+    modes = {lv: 0 for lv in MOBI_PREFIX}
+    modes["Quality"] = 1
+    modes["Satisfaction"] = 0
+    samples = boot.samples()
+    for b in (0, 4, 9):
+        blocks = {lv: X[idx[b]][:, [i for i, m in enumerate(mvs) if m.startswith(p)]] for lv, p in MOBI_PREFIX.items()}
+        _, s2, names = onm.fit_num_hoc(blocks, lvs, path.astype(np.int8), modes, {"Satisfaction": ["Image", "Value"]},
+                                       "path", 1e-8)
+        got = samples["weights"].iloc[b]
+        np.testing.assert_allclose([got["Image"], got["Value"]], [s2["weights"][names.index("Image")],
+                                                                  s2["weights"][names.index("Value")]], rtol=REL)
+        np.testing.assert_allclose(samples["r_squared"].iloc[b].loc[lvs], s2["r_squared"], rtol=REL, atol=1e-9)
+        np.testing.assert_allclose(samples["paths"].iloc[b].loc["Satisfaction -> Loyalty"],
+                                   s2["path_coefficients"][lvs.index("Loyalty"), lvs.index("Satisfaction")], rtol=REL)
+    assert np.isfinite(boot.paths().to_numpy()).all()

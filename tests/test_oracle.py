@@ -215,3 +215,61 @@ def test_nonmetric_num_r_golden(nm):
     np.testing.assert_allclose(m["path_coefficients"], nm["mobi/path_coefficients"], rtol=1e-8, atol=1e-12)
     np.testing.assert_allclose(m["weights"], nm["R/mobi/weight"], rtol=1e-5)   # reference test_regression_seminr.py:42
     np.testing.assert_allclose(m["loadings"], nm["R/mobi/loading"], rtol=1e-5)
+
+
+# ---- higher-order constructs, two-stage approach -----------------------------------
+MOBI_PREFIX = {"Expectation": "CUEX", "Quality": "PERQ", "Loyalty": "CUSL", "Image": "IMAG", "Complaints": "CUSCO",
+               "Value": "PERV"}
+
+
+def mobi_hoc_case(hz, tag):
+    mvs = [str(v) for v in hz["mobi/mvs"]]
+    X = hz["mobi/X"]
+    blocks = {lv: X[:, [i for i, m in enumerate(mvs) if m.startswith(p)]] for lv, p in MOBI_PREFIX.items()}
+    lvs = [str(v) for v in hz[tag + "/lvs"]]
+    edges = [("Expectation", "Satisfaction"), ("Quality", "Satisfaction"), ("Satisfaction", "Complaints"),
+             ("Satisfaction", "Loyalty")]
+    path = np.zeros((5, 5), dtype=np.int8)
+    for f, t in edges:
+        path[lvs.index(t), lvs.index(f)] = 1
+    return blocks, lvs, path
+
+
+@pytest.fixture(scope="module")
+def hz():
+    import os
+    from tests.conftest import GOLDEN
+    return np.load(os.path.join(GOLDEN, "hoc.npz"), allow_pickle=False)
+
+
+@pytest.mark.parametrize("tag,scheme,hoc_mode,tol", [("path", "path", 0, 1e-8), ("centroid_b", "centroid", 1, 1e-7)])
+def test_hoc_two_stage_vs_reference(hz, tag, scheme, hoc_mode, tol):
+    from oracle import plspm_oracle_nonmetric as onm
+    blocks, lvs, path = mobi_hoc_case(hz, tag)
+    modes = {lv: 0 for lv in MOBI_PREFIX}
+    modes["Quality"] = 1
+    modes["Satisfaction"] = hoc_mode
+    _, s2, names = onm.fit_num_hoc(blocks, lvs, path, modes, {"Satisfaction": ["Image", "Value"]}, scheme, tol)
+    np.testing.assert_allclose(s2["path_coefficients"], hz[tag + "/path_coefficients"], rtol=1e-8, atol=1e-12)
+    np.testing.assert_allclose(s2["scores"], hz[tag + "/scores"], rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(s2["r_squared"], hz[tag + "/r_squared"], rtol=1e-8, atol=1e-12)
+    ref_index = [str(v) for v in hz[tag + "/outer_index"]]
+    # stage-2 manifest names: constituents by name, first-order MVs in block order (sorted like the reference index)
+    mvs = [str(v) for v in hz["mobi/mvs"]]
+    label = {}
+    for lv, p in MOBI_PREFIX.items():
+        for j, m in enumerate([m for m in mvs if m.startswith(p)]):
+            label["%s.%d" % (lv, j)] = m
+    got_w = {label.get(n, n): w for n, w in zip(names, s2["weights"])}
+    got_l = {label.get(n, n): w for n, w in zip(names, s2["loadings"])}
+    np.testing.assert_allclose([got_w[m] for m in ref_index], hz[tag + "/weights"], rtol=1e-8)
+    np.testing.assert_allclose([got_l[m] for m in ref_index], hz[tag + "/loadings"], rtol=1e-8)
+    if tag == "path":  # seminr values of the reference's own test (test_regression_seminr.py:65-74)
+        r_index = [str(v) for v in hz["R/outer_index"]]
+        common = [m for m in r_index if m in got_w]
+        assert {"Image", "Value"} <= set(common)
+        np.testing.assert_allclose([got_w[m] for m in common], [hz["R/weight"][r_index.index(m)] for m in common], rtol=1e-4)
+        np.testing.assert_allclose([got_l[m] for m in common], [hz["R/loading"][r_index.index(m)] for m in common], rtol=1e-4)
+        r_lvs = [str(v) for v in hz["R/path_lvs"]]
+        perm = [r_lvs.index(lv) for lv in lvs]
+        np.testing.assert_allclose(s2["path_coefficients"], hz["R/path_coefficients"][np.ix_(perm, perm)], rtol=1e-6, atol=1e-9)
