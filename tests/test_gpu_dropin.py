@@ -143,11 +143,15 @@ def test_argument_rules_and_errors(sat):
     with pytest.raises(Exception, match="Could not converge after 101 iterations"):
         Plspm(df, make_config(df, Mode.B, scaled=True), tolerance=1e-300)
     from plspm.scale import Scale
-    nonmetric = c.Config(satisfaction_path_matrix(), default_scale=Scale.NUM)
-    for lv in ("IMAG", "EXPE", "QUAL", "VAL", "SAT", "LOY"):
-        nonmetric.add_lv_with_columns_named(lv, Mode.A, df, lv.lower())
-    with pytest.raises(NotImplementedError):
-        Plspm(df, nonmetric)
+    for scale, ok in ((Scale.NUM, True), (Scale.ORD, False), (Scale.NOM, False)):
+        nonmetric = c.Config(satisfaction_path_matrix(), default_scale=scale)
+        for lv in ("IMAG", "EXPE", "QUAL", "VAL", "SAT", "LOY"):
+            nonmetric.add_lv_with_columns_named(lv, Mode.A, df, lv.lower())
+        if ok:  # numeric scales run on the device (tests/test_gpu_nonmetric.py)
+            assert Plspm(df, nonmetric).iterations() > 0
+        else:   # ordinal / nominal quantification is outside the accelerated path and says so
+            with pytest.raises(NotImplementedError):
+                Plspm(df, nonmetric)
 
 
 def test_missing_values_single_fit_is_mean_imputed(sat):
