@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """bench.py -- bootstrap PLS-PM fits/s of the B200 engine (BASELINE.json metric), one JSON line.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c2|c4|c5|c3f] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c2|c4|c5|c3f|c3n] [--impl reference]
 
 A *step* is one bootstrap batch on every rank: `replicates_per_gpu_per_step` independent PLS-PM fits
 to convergence (tol 1e-6, max 100 iterations) on resamples of the HBM-resident observation matrix,
@@ -39,6 +39,8 @@ WORKLOADS = {
     "c3f": (100_000, 32, 8, 0, "factorial", 1184, "synthetic N=100k, 32 LVs x 8 MVs, Mode A, factorial, bootstrap"),
     "c4": (100_000, 32, 8, 1, "path", 1184, "synthetic N=100k, 32 LVs x 8 MVs, Mode B, path scheme, bootstrap"),
     "c5": (1_000_000, 64, 16, 0, "centroid", 16, "synthetic N=1M, 64 LVs x 16 MVs (P=1024), Mode A, centroid, bootstrap"),
+    "c3n": (100_000, 32, 8, 0, "centroid", 1184,
+            "synthetic N=100k, 32 LVs x 8 MVs, Scale.NUM (non-metric estimator), Mode A, centroid, bootstrap"),
     "c2": (250, 6, 0, 0, "centroid", 1000, "satisfaction 250x27, 6 LVs, Mode A, centroid, 1000 resamples (latency-bound)"),
 }
 HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
@@ -52,7 +54,8 @@ def load_workload(name):
         return dict(X=np.ascontiguousarray(g["X"]), path=g["path"], blocks=[int(v) for v in g["block_sizes"]],
                     modes=[0] * 6, scheme=scheme, reps=reps, desc=desc, scaled=False)
     X, path = make_synthetic(N, L, K, seed=0)
-    return dict(X=X, path=path, blocks=[K] * L, modes=[mode] * L, scheme=scheme, reps=reps, desc=desc, scaled=True)
+    return dict(X=X, path=path, blocks=[K] * L, modes=[mode] * L, scheme=scheme, reps=reps, desc=desc, scaled=True,
+                numeric=name.endswith("n"))
 
 
 def hbm_peak():
@@ -79,6 +82,10 @@ def _cpu_one(rep):
     w = _CPU["w"]
     idx = orc.philox_indices(0, rep, w["X"].shape[0])
     t = time.perf_counter()
+    if w.get("numeric"):
+        from oracle import plspm_oracle_nonmetric as onm
+        res = onm.fit_num(w["X"][idx], w["blocks"], w["modes"], w["path"], w["scheme"])
+        return time.perf_counter() - t, int(res["iterations"]), 0
     row, iters, status = orc.replicate_row(w["X"], idx, w["blocks"], w["modes"], w["path"], w["scheme"], w["scaled"])
     return time.perf_counter() - t, int(iters), int(status)
 
@@ -145,7 +152,7 @@ def run_reference_arm(args):
 def workload_config(name, w, reps):
     N, P = w["X"].shape
     return {"workload": w["desc"], "name": name, "N": int(N), "P": int(P), "L": len(w["blocks"]),
-            "mode": "B" if w["modes"][0] else "A", "scheme": w["scheme"], "scaled": bool(w["scaled"]),
+            "mode": "B" if w["modes"][0] else "A", "scheme": w["scheme"], "scaled": bool(w["scaled"]), "numeric_scales": bool(w.get("numeric")),
             "tol": 1e-6, "max_iter": 100, "replicates_per_gpu_per_step": int(reps),
             "l2": "inputs larger than L2: X (%.1f MB fp64) + %.1f MB of per-replicate resample counts + Gram "
                   "workspace per step are streamed every step (L2 is 126 MB)" % (N * P * 8 / 1e6, reps * N * 4 / 1e6)}
@@ -221,7 +228,7 @@ def run_gpu_arm(args):
     X = w["X"]
     N, P = X.shape
     reps = args.replicates or w["reps"]
-    model = engine.Model(w["blocks"], w["modes"], w["path"], w["scaled"])
+    model = engine.Model(w["blocks"], w["modes"], w["path"], w["scaled"], numeric=bool(w.get("numeric")))
     data = engine.Data(model, X)
     n_out = model.n_out
     rows_dev = torch.empty((reps, n_out), dtype=torch.float64, device=dev)
@@ -287,7 +294,7 @@ def run_gpu_arm(args):
     if rank == 0:
         # every kernel that streams X for the batch: the Gram kernel (dominant), the column sums, and the
         # sign-vote pass (exact fp64 cross moments, or score generation + fp16 GEMMs)
-        stream_stages = ("gram", "cross", "colsum", "scoregen")
+        stream_stages = ("gram", "cross", "colsum", "scoregen", "conv")
         gram_ms, gram_n = prof["gram"]
         stream_ms = sum(prof.get(k, (0.0, 0))[0] for k in stream_stages)
         alg_bytes = float((iters_cat + 2.0).sum()) * N * P * 8.0           # all fits of the timed region, this rank
@@ -295,7 +302,7 @@ def run_gpu_arm(args):
         achieved = alg_bytes / 1e9 / (stream_ms / 1e3) if stream_ms > 0 else 0.0
         # fp64 FMAs of the Gram kernel (8x8 tiles; ~63.2 % of the rows have non-zero multiplicity)
         fp64_tflops = 2.0 * model.n_tiles * 64 * 0.632 * N * reps * args.steps / (gram_ms / 1e3) / 1e12 if gram_ms > 0 else 0.0
-        vote = "n/a (full tile set)" if model.full_tiles else (
+        vote = "n/a (non-metric estimator: no sign vote)" if w.get("numeric") else "n/a (full tile set)" if model.full_tiles else (
             "exact fp64 cross moments" if prof.get("scoregen", (0, 0))[1] == 0 else
             "fp16 tensor-core GEMM with error bound, %d replicates redone exactly" % engine.redo_count())
         traffic = None
@@ -320,7 +327,7 @@ def run_gpu_arm(args):
                          "kernel": "gram_kernel<false>", "kernel_share_of_streaming_time": gram_ms / stream_ms,
                          "streaming_stages": list(stream_stages),
                          "tile_set": "full" if model.full_tiles else "sparse", "sign_vote": vote,
-                         "fp64_tflops_est": fp64_tflops, "fp64_peak_nominal_tflops": 37.2,
+                         "fp64_tflops_est": fp64_tflops, "fp64_peak_measured_tflops": 36.9,
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes / max(gram_n, 1),
                          "launch_ms": stream_ms / max(gram_n, 1), "gram_launch_ms": gram_ms / max(gram_n, 1),
@@ -329,7 +336,7 @@ def run_gpu_arm(args):
                                  "time of ALL X-streaming kernels of the batch. The engine reads X once per wave of "
                                  "replicates per pass instead of (n_iter+2) times per replicate (covariance-domain "
                                  "solver), so frac exceeds 1; the dominant Gram kernel is bound by the fp64 FMA pipe "
-                                 "(fp64_tflops_est vs the nominal 37.2 TFLOP/s), not by HBM"},
+                                 "(fp64_tflops_est vs the 36.9 TFLOP/s measured by tools/fp64_peak.cu), not by HBM"},
             "stages_ms_per_step": {k: v[0] / args.steps for k, v in prof.items() if v[1]},
             "mean_iterations": float(iters_cat.mean()), "failed_replicates": bad,
         }
