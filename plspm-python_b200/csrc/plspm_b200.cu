@@ -707,8 +707,10 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const GramParams 
   const bool tile_ok = tile >= 0;
   // 16-byte chunks of a slot are read in a lane-dependent rotated order so that the 32 LDS.128 of
   // a warp spread over all bank quads (slot stride 64 B would otherwise be a 16-way conflict).
-  // In Gram mode the row operand xa is a broadcast within a packed tile group: no rotation.
-  const int rot_a = CROSS ? ((sa >> 1) & 3) : 0, rot_b = CROSS ? 0 : ((sb >> 1) & 3);
+  // This holds for the row operand too: a sparse tile group holds ~3 tiles per row slot, i.e. ~11
+  // distinct row slots per warp (ncu: 8.0 wavefronts per unrotated xa LDS.128 vs 4.33 rotated; the
+  // kernel is bound by shared-memory wavefronts, 94 % L1/TEX throughput, before the fp64 pipe).
+  const int rot_a = (sa >> 1) & 3, rot_b = CROSS ? 0 : ((sb >> 1) & 3);
   int off_a[4], off_b[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
