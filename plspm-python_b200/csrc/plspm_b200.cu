@@ -637,7 +637,7 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
 template <bool CROSS>
 __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const GramParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ __align__(8) uint64_t full_bar[GRAM_MAX_STAGES], empty_bar[GRAM_MAX_STAGES];
+  __shared__ __align__(8) uint64_t full_bar[GRAM_MAX_STAGES];
   double* tiles = reinterpret_cast<double*>(smem_raw);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -650,39 +650,30 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const GramParams 
   const int n_rt = (int)((r1 - r0 + p.RT - 1) / p.RT);
   const size_t stage_doubles = (size_t)p.RT * p.Ppad;
 
+  // ---- feeding the ring -------------------------------------------------------------------------
+  // No producer warp (a ninth warp would put three warps on one SM sub-partition and cap every thread at
+  // 168 registers; the 8x8 fp64 accumulator tile alone needs 128).  Thread 0 issues the first `stages`
+  // row tiles; after that the LAST consumer warp to finish with a stage (shared-memory counter) refills it
+  // through the TMA engine at once, so a tile is always requested stages-1 tile times ahead of its use
+  // no matter how the warps drift apart.
+  __shared__ int stage_done[GRAM_MAX_STAGES];
+  auto issue_tile = [&](int tn) {
+    const int st = tn % p.stages;
+    const int64_t row = r0 + (int64_t)tn * p.RT;
+    const uint32_t rows = (uint32_t)min((int64_t)p.RT, r1 - row);
+    const uint32_t bytes = rows * (uint32_t)p.Ppad * 8u;
+    mbar_arrive_expect_tx(&full_bar[st], bytes);
+    bulk_g2s(tiles + (size_t)st * stage_doubles, p.X + row * p.Ppad, bytes, &full_bar[st]);
+  };
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], n_active);
+      stage_done[s] = 0;
     }
     mbar_fence_init();
+    for (int tn = 0; tn < n_rt && tn < p.stages; ++tn) issue_tile(tn);
   }
   __syncthreads();
-
-  // ---- producer duty: lane 0 of warp 0 feeds the ring through the TMA engine ------------------
-  // (a ninth warp would put three warps on one SM sub-partition and cap every thread at 168
-  // registers; the 8x8 fp64 accumulator tile alone needs 128).  Tiles are issued as early as a
-  // stage is free (non-blocking probe), and at the latest -- blocking -- right before warp 0
-  // itself needs them, so the other warps never wait on warp 0's own arithmetic.
-  const bool producer = (threadIdx.x == 0);
-  int tn = 0, tn_stage = 0;      // next row tile to issue and its ring stage (producer only)
-  uint32_t tn_use = 0;           // how many times that stage has been filled before
-  auto feed = [&](int t_cur) {   // t_cur: the tile warp 0 is about to consume / is consuming
-    while (tn < n_rt && tn < t_cur + p.stages) {
-      if (tn_use > 0) {
-        if (tn <= t_cur) mbar_wait(&empty_bar[tn_stage], (tn_use - 1) & 1);
-        else if (!mbar_test(&empty_bar[tn_stage], (tn_use - 1) & 1)) break;
-      }
-      const int64_t row = r0 + (int64_t)tn * p.RT;
-      const uint32_t rows = (uint32_t)min((int64_t)p.RT, r1 - row);
-      const uint32_t bytes = rows * (uint32_t)p.Ppad * 8u;
-      mbar_arrive_expect_tx(&full_bar[tn_stage], bytes);
-      bulk_g2s(tiles + (size_t)tn_stage * stage_doubles, p.X + row * p.Ppad, bytes, &full_bar[tn_stage]);
-      ++tn;
-      if (++tn_stage == p.stages) { tn_stage = 0; ++tn_use; }
-    }
-  };
-  if (producer) feed(0);
   if (warp >= n_active) return;
 
   // ---- consumer warp: one (replicate, tile group); lane = one 8x8 tile ------------------------
@@ -794,7 +785,6 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const GramParams 
   uint32_t cnt_next = load_counts(0);
 
   for (int t = 0; t < n_rt; ++t) {
-    if (producer) feed(t);
     const int s = t % p.stages;
     const uint32_t use = (uint32_t)(t / p.stages);
     const uint32_t cnt = cnt_next;
@@ -871,7 +861,18 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const GramParams 
       asm volatile("{\n.reg .b32 lo, hi;\nmov.b64 {lo, hi}, %1;\nand.b32 %0, lo, 0;\n}" : "=r"(release_dep) : "d"(xb0[7]));
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(&empty_bar[s] + release_dep);
+    if (lane == 0) {
+      // (release_dep == 0, but it makes this release depend on the warp's last shared-memory load)
+      __threadfence_block();
+      const int prev = atomicAdd(&stage_done[s] + release_dep, 1);
+      if (prev == n_active - 1) {  // every consumer is done with this fill: refill the stage
+        stage_done[s] = 0;
+        if (t + p.stages < n_rt) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          issue_tile(t + p.stages);
+        }
+      }
+    }
   }
 
   // ---- write the partial tile (undo the chunk rotation) and the column sums --------------------
