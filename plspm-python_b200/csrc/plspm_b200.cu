@@ -352,7 +352,8 @@ __global__ void make_half_kernel(const double* __restrict__ X, int64_t N, int Pp
 }
 
 // Scores for the tensor-core sign vote:
-//   B[i - i0][b*L + l] = fp16( c_bi * (x~_i . wf_b,l - sh_b,l) )        rows [i0, i0 + rc) of one chunk.
+//   B[i - i0][l*ldl + b] = fp16( c_bi * (x~_i . wf_b,l - sh_b,l) )      rows [i0, i0 + rc) of one chunk,
+// ldl = replicates rounded up to 8: a thread's SG_RPT = 4 consecutive replicates are one 8-byte store.
 // A group of nsl_pad adjacent lanes (power of two >= slots of the widest block) serves one (replicate
 // lane, latent variable) pair: lane `sub` of the group owns slot `sub` of the block, keeps the weights
 // of that slot for SG_RPT replicates in registers, walks the rows of the CTA's tiles reading the slot
@@ -366,7 +367,8 @@ __global__ void __launch_bounds__(SG_THREADS) scoregen_kernel(const double* __re
                                                               const double* __restrict__ sh, int64_t N, int Ppad, int L,
                                                               const int* __restrict__ lv_off,
                                                               const int* __restrict__ lv_k, int nsl_pad, int SG_ROWS,
-                                                              int64_t nrep, int64_t i0, int rc, __half* __restrict__ B) {
+                                                              int64_t nrep, int64_t ldl, int64_t i0, int rc,
+                                                              __half* __restrict__ B) {
   extern __shared__ __align__(16) double sg_smem[];
   double* xs = sg_smem;                                     // [SG_ROWS][Ppad]  (SG_ROWS <= 32 rows per tile)
   double* cs = xs + (size_t)SG_ROWS * Ppad;                 // [SG_ROWS][reps_per_cta] multiplicities as fp64
@@ -397,12 +399,14 @@ __global__ void __launch_bounds__(SG_THREADS) scoregen_kernel(const double* __re
   const int slot = (lv_off[l] >> 3) + (has_slot ? sub : 0);
   const int rot = (slot >> 1) & 3;  // rotated chunk order: the 64-byte slot stride would alias shared-memory banks
   double w[SG_RPT][8], shv[SG_RPT];
-  __half* out[SG_RPT];                                      // B + bb*L + l of the thread's replicates (null: no store)
+  // the thread's SG_RPT replicates are adjacent in B (LV-major layout): one 8-byte store per row; replicates
+  // past nrep (but inside the padded stride) get zeros
+  const int64_t bb0 = rep0 + bl * SG_RPT;
+  uint2* out = (active && sub == 0 && bb0 < ldl) ? reinterpret_cast<uint2*>(B + l * ldl + bb0) : nullptr;
 #pragma unroll
   for (int j = 0; j < SG_RPT; ++j) {
-    const int64_t bb = rep0 + bl * SG_RPT + j;
+    const int64_t bb = bb0 + j;
     const bool ok = bb < nrep;
-    out[j] = (ok && active && sub == 0) ? B + bb * L + l : nullptr;
     shv[j] = (ok && sub == 0) ? sh[bb * L + l] : 0.0;
 #pragma unroll
     for (int ch = 0; ch < 4; ++ch) {
@@ -411,7 +415,7 @@ __global__ void __launch_bounds__(SG_THREADS) scoregen_kernel(const double* __re
       w[j][2 * ch + 1] = (ok && has_slot) ? wf[bb * Ppad + col + 1] : 0.0;
     }
   }
-  const int64_t ldb = nrep * L;
+  const int64_t ldb = ldl * L / SG_RPT;                      // row stride of B in 8-byte units
   const double* xcol = xs + slot * SLOT;
   int xo[4];
 #pragma unroll
@@ -445,14 +449,25 @@ __global__ void __launch_bounds__(SG_THREADS) scoregen_kernel(const double* __re
       const double2 c01 = *reinterpret_cast<const double2*>(cr + r * reps_per_cta);
       const double2 c23 = *reinterpret_cast<const double2*>(cr + r * reps_per_cta + 2);
       const double cj[4] = {c01.x, c01.y, c23.x, c23.y};
+      __half hv[SG_RPT];
 #pragma unroll
       for (int j = 0; j < SG_RPT; ++j) {
-        double t = -shv[j];
+        double t0 = -shv[j], t1 = 0.0;                      // two chains: half the dependent-FMA latency
 #pragma unroll
-        for (int k = 0; k < 8; ++k) t = fma(x[k], w[j][k], t);
+        for (int k = 0; k < 8; k += 2) {
+          t0 = fma(x[k], w[j][k], t0);
+          t1 = fma(x[k + 1], w[j][k + 1], t1);
+        }
+        double t = t0 + t1;
         if (!SINGLE_SLOT)
           for (int o = nsl_pad >> 1; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-        if (out[j]) out[j][orow] = __double2half(cj[j] * t);
+        hv[j] = __double2half(cj[j] * t);
+      }
+      if (out) {
+        uint2 pk;
+        pk.x = (uint32_t)__half_as_ushort(hv[0]) | ((uint32_t)__half_as_ushort(hv[1]) << 16);
+        pk.y = (uint32_t)__half_as_ushort(hv[2]) | ((uint32_t)__half_as_ushort(hv[3]) << 16);
+        out[orow] = pk;
       }
     }
   }
@@ -1399,8 +1414,9 @@ static BatchBuffers layout_batch(const plspm_data* d, int64_t nb, const BatchPla
   b.num_meta = take(numeric ? (size_t)nb * 16 : 0);
   b.num_done = take(8);
   b.num_cpart = take(numeric ? (size_t)nb * bp.cv_gx * 8 : 0);
-  b.BT = take(fast ? (size_t)nb * h.L * FAST_RC * sizeof(__half) : 0);
-  b.Cf = take(fast ? (size_t)nb * h.L * h.Ppad * sizeof(float) : 0);
+  const size_t ldl = (size_t)(nb + 7) / 8 * 8;  // replicate stride of the LV-major score / cross-moment layout
+  b.BT = take(fast ? ldl * h.L * FAST_RC * sizeof(__half) : 0);
+  b.Cf = take(fast ? ldl * h.L * h.Ppad * sizeof(float) : 0);
   b.rep_map = take((size_t)nb * 4);
   if (single_fit) {
     const size_t L = h.L, P = h.P;
@@ -1565,7 +1581,7 @@ static int run_batch(plspm_data* d, int64_t nb, const uint32_t* counts_dev, cons
                      double tol, int max_iter, const BatchPlan& bp, double* out_rows, bool single_fit) {
   const plspm_model* m = d->model;
   const HostModel& h = m->h;
-  const bool use_fast = !h.full && d->fast_vote && !single_fit && (int64_t)nb * h.L < (1 << 30);
+  const bool use_fast = !h.full && d->fast_vote && !single_fit && (int64_t)(nb + 8) * h.L < (1 << 30);
   cudaStream_t st = d->stream;
   char* base = (char*)d->ws.ptr;
   auto D = [&](size_t o) { return (double*)(base + o); };
@@ -1610,6 +1626,10 @@ static int run_batch(plspm_data* d, int64_t nb, const uint32_t* counts_dev, cons
       auto sg_kernel = (nsl_pad == 1) ? scoregen_kernel<true> : scoregen_kernel<false>;
       CK(cudaFuncSetAttribute(sg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sg_smem));
       const float one = 1.f, zero = 0.f;
+      const int64_t ldl = (nb + 7) / 8 * 8;
+      const int gemm_m = (int)(ldl * h.L);
+      // padded replicate columns of the score buffer are only written up to the CTA grid's reach: clear once
+      CK(cudaMemsetAsync(BT, 0, (size_t)gemm_m * FAST_RC * sizeof(__half), st));
       for (int64_t i0 = 0; i0 < d->N; i0 += FAST_RC) {
         const int rc = (int)std::min<int64_t>(FAST_RC, d->N - i0);
         const unsigned gy = (unsigned)((nb + reps_per_cta - 1) / reps_per_cta);
@@ -1618,20 +1638,20 @@ static int run_batch(plspm_data* d, int64_t nb, const uint32_t* counts_dev, cons
         dim3 grid_sg(gx, gy);
         d->timer.begin(ST_SCOREGEN, st);
         sg_kernel<<<grid_sg, SG_THREADS, sg_smem, st>>>(d->X, counts_dev, D(bb.wf), D(bb.sh), d->N, h.Ppad, h.L,
-                                                             m->dv.lv_off, m->dv.lv_k, nsl_pad, SG_ROWS, nb, i0, rc, BT);
+                                                             m->dv.lv_off, m->dv.lv_k, nsl_pad, SG_ROWS, nb, ldl, i0, rc,
+                                                             BT);
         d->timer.end(st);
         CK(cudaGetLastError());
         // C[nb*L x Ppad] (+)= B^T-free NT product: A = scores stored [nb*L x rc] (column-major view of the
         // row-major [rc][nb*L] buffer), B = xh chunk stored [Ppad x rc]
         d->timer.begin(ST_CROSS, st);
-        cublasStatus_t cs = cublasGemmEx(d->blas, CUBLAS_OP_N, CUBLAS_OP_T, (int)(nb * h.L), h.Ppad, rc, &one, BT,
-                                         CUDA_R_16F, (int)(nb * h.L), d->Xh + i0 * h.Ppad, CUDA_R_16F, h.Ppad,
-                                         i0 == 0 ? &zero : &one, Cf, CUDA_R_32F, (int)(nb * h.L), CUBLAS_COMPUTE_32F,
-                                         CUBLAS_GEMM_DEFAULT);
+        cublasStatus_t cs = cublasGemmEx(d->blas, CUBLAS_OP_N, CUBLAS_OP_T, gemm_m, h.Ppad, rc, &one, BT, CUDA_R_16F,
+                                         gemm_m, d->Xh + i0 * h.Ppad, CUDA_R_16F, h.Ppad, i0 == 0 ? &zero : &one, Cf,
+                                         CUDA_R_32F, gemm_m, CUBLAS_COMPUTE_32F, CUBLAS_GEMM_DEFAULT);
         d->timer.end(st);
         if (cs != CUBLAS_STATUS_SUCCESS) return fail(PLSPM_ERR_CUDA, "cublasGemmEx failed: " + std::to_string((int)cs));
       }
-      b.fast_cross = Cf; b.inv_sd = d->inv_sd; b.fast_nb = nb;
+      b.fast_cross = Cf; b.inv_sd = d->inv_sd; b.fast_nb = ldl;
     } else {
       if (int rc = launch_stream(d, true, nb, counts_dev, bp.cross, D(bb.CG), D(bb.CGpart), D(bb.wf))) return rc;
     }

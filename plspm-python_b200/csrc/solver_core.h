@@ -53,9 +53,9 @@ struct SolveArgs {
                          // 3: like 2, but LV pairs outside the tile set vote with the SIGN of a
                          //    low-precision (fp16 tensor-core) cross moment when it is provably right,
                          //    otherwise the replicate is handed back as STATUS_AMBIGUOUS
-  const float* fast_cross;  // [Ppad][fast_nb][L] fp32 sums of xh_ip * (c_i t_il) (phase 3)
+  const float* fast_cross;  // [Ppad][L][fast_nb] fp32 sums of xh_ip * (c_i t_il) (phase 3)
   const double* inv_sd;     // [Ppad] global 1/sd used to scale xh (phase 3)
-  int64_t fast_nb, fast_b;  // batch size and this replicate's position in fast_cross
+  int64_t fast_nb, fast_b;  // replicate stride (batch size rounded up to 8) and this replicate's position
   double* sh_out;           // [L] score means sum_q m_q wf_q (phase 1)
   const double* cross;   // [n_cross*64] raw sum_i c_i x~_ip (x~_i . wf_l) tiles (phase 2)
   double* wf_out;        // [Ppad] final normalised weights, padded layout (phase 1)
@@ -369,7 +369,7 @@ PL_HD void solve_replicate(const SolveArgs& A, double* smem) {
       // E = sum_i xh_ip (c_i t_il) has the sign of cov(x_p, score_l); fp16 operands + fp32 tensor-core
       // accumulation over <= 4096-row chunks give |fl(E) - E| <= gamma * sqrt(sum c xh^2) * sqrt(sum c t^2)
       // (Cauchy-Schwarz); sum c t^2 = N / iss because the scores have unit variance on the treated scale
-      const double v = (double)A.fast_cross[((size_t)p * A.fast_nb + A.fast_b) * L + l];
+      const double v = (double)A.fast_cross[((size_t)p * L + l) * A.fast_nb + A.fast_b];
       const double bound = 2.0e-3 * sqrt(gram_raw(M, A.G, p, p)) * A.inv_sd[p] * sqrt(N / iss);
       if (v - v == 0.0 && fabs(v) > bound) vote_add(votes, l, v < 0.0 ? -1 : 1);
       else vote_add(unc, l, 1);

@@ -20,18 +20,20 @@ ap.add_argument("--scheme", default="centroid")
 ap.add_argument("--mode", type=int, default=0)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--policy", type=int, default=0)
+ap.add_argument("--numeric", action="store_true", help="non-metric estimator for numeric scales")
 a = ap.parse_args()
 
 engine.set_device(0)
 t0 = time.time()
 X, path = make_synthetic(a.N, a.L, a.K, seed=0)
 print("gen %.1fs" % (time.time() - t0), flush=True)
-model = engine.Model([a.K] * a.L, [a.mode] * a.L, path, True, a.policy)
+model = engine.Model([a.K] * a.L, [a.mode] * a.L, path, True, a.policy, numeric=a.numeric)
 t0 = time.time()
 data = engine.Data(model, X)
 print("upload %.3fs  tiles=%d tile_groups=%d full=%s" % (time.time() - t0, model.n_tiles, model.n_tile_groups, model.full_tiles), flush=True)
 t0 = time.time()
-f = engine.fit(model, data, a.scheme)
+fit_model = engine.Model([a.K] * a.L, [a.mode] * a.L, path, True, engine.TILES_FULL, numeric=True) if a.numeric else model
+f = engine.fit(fit_model, data, a.scheme)
 print("fit %.4fs iters=%d status=%d" % (time.time() - t0, f["iterations"], f["status"]), flush=True)
 for r in range(a.reps):
     engine.profile_reset()
