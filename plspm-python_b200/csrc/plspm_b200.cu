@@ -16,6 +16,8 @@
 //
 // Nothing here falls back to a CPU path: without a CUDA device every entry point fails.
 #include <cublas_v2.h>
+#include <chrono>
+#include <map>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -173,6 +175,27 @@ struct plspm_model {
   ModelView dv;  // device pointers
 };
 
+// cuBLAS handles, recycled per device (a data handle owns one exclusively while it lives)
+static std::mutex g_blas_mu;
+static std::map<int, std::vector<cublasHandle_t>> g_blas_free;
+static cublasHandle_t blas_acquire(int device) {
+  {
+    std::lock_guard<std::mutex> lk(g_blas_mu);
+    auto& v = g_blas_free[device];
+    if (!v.empty()) {
+      cublasHandle_t h = v.back();
+      v.pop_back();
+      return h;
+    }
+  }
+  cublasHandle_t h = nullptr;
+  return cublasCreate(&h) == CUBLAS_STATUS_SUCCESS ? h : nullptr;
+}
+static void blas_release(int device, cublasHandle_t h) {
+  std::lock_guard<std::mutex> lk(g_blas_mu);
+  g_blas_free[device].push_back(h);
+}
+
 struct Workspace {
   void* ptr = nullptr;
   size_t bytes = 0;
@@ -187,6 +210,7 @@ struct plspm_data {
   __half* Xh = nullptr;      // [N][Ppad]
   double* inv_sd = nullptr;  // [Ppad]
   cublasHandle_t blas = nullptr;
+  int blas_device = 0;
   bool fast_vote = false;    // the fp16 pass is worth trying on this data
   cudaStream_t stream = nullptr;
   Workspace ws;          // grown on demand, reused across calls
@@ -1185,9 +1209,18 @@ int plspm_data_create(const plspm_model* m, const double* X, int64_t N, int64_t 
   d->sm_count = prop.multiProcessorCount;
   d->max_smem = (int)prop.sharedMemPerBlockOptin;
   auto bail = [&](int rc) { plspm_data_destroy(d); return rc; };
+  static const bool tracing = getenv("PLSPM_TRACE") != nullptr;
+  const auto t_begin = std::chrono::steady_clock::now();
+  auto trace = [&](const char* what) {
+    if (!tracing) return;
+    cudaStreamSynchronize(d->stream);
+    fprintf(stderr, "[plspm_data_create] %-18s %8.3f ms\n", what,
+            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
+  };
   if (cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking) != cudaSuccess)
     return bail(fail(PLSPM_ERR_CUDA, "cudaStreamCreate failed"));
   cudaStream_t st = d->stream;
+  trace("stream created");
   double* raw = nullptr;
   const double* Xd = X;
   int rc = 0;
@@ -1197,8 +1230,12 @@ int plspm_data_create(const plspm_model* m, const double* X, int64_t N, int64_t 
     CK(cudaMemsetAsync(d->mu, 0, (size_t)h.Ppad * sizeof(double), st));
     if (!x_is_device) {
       CK(g_pool.alloc((void**)&raw, (size_t)N * h.P * sizeof(double)));
-      CK(cudaMemcpy2DAsync(raw, (size_t)h.P * sizeof(double), X, (size_t)ld * sizeof(double),
-                           (size_t)h.P * sizeof(double), (size_t)N, cudaMemcpyHostToDevice, st));
+      if (ld == h.P)
+        CK(cudaMemcpyAsync(raw, X, (size_t)N * h.P * sizeof(double), cudaMemcpyHostToDevice, st));
+      else
+        CK(cudaMemcpy2DAsync(raw, (size_t)h.P * sizeof(double), X, (size_t)ld * sizeof(double),
+                             (size_t)h.P * sizeof(double), (size_t)N, cudaMemcpyHostToDevice, st));
+      trace("h2d issued");
       Xd = raw;
       ld = h.P;
     }
@@ -1219,6 +1256,7 @@ int plspm_data_create(const plspm_model* m, const double* X, int64_t N, int64_t 
     relayout_kernel<<<d->sm_count * 8, 256, 0, st>>>(Xd, N, ld, h.Ppad, m->dv.col_src, d->mu, d->X);
     d->timer.end(st);
     CK(cudaGetLastError());
+    trace("relayout done");
     // fp16 copy for the tensor-core sign vote of sparse tile sets (PLSPM_VOTE=exact disables it)
     static const bool vote_exact = getenv("PLSPM_VOTE") && std::string(getenv("PLSPM_VOTE")) == "exact";
     int nsl_pad_chk = 1;
@@ -1240,12 +1278,22 @@ int plspm_data_create(const plspm_model* m, const double* X, int64_t N, int64_t 
       CK(cudaGetLastError());
       CK(cudaStreamSynchronize(st));
       g_pool.release(sq);
-      if (cublasCreate(&d->blas) != CUBLAS_STATUS_SUCCESS) return fail(PLSPM_ERR_CUDA, "cublasCreate failed");
+      d->blas = blas_acquire(dev);  // cublasCreate costs milliseconds: handles are recycled per device
+      if (!d->blas) return fail(PLSPM_ERR_CUDA, "cublasCreate failed");
+      d->blas_device = dev;
       cublasSetStream(d->blas, st);
       d->fast_vote = true;
+      trace("fp16 copy + blas");
     }
     CK(cudaStreamSynchronize(st));
     d->timer.collect();
+    trace("timer collected");
+    {  // a NaN / Inf anywhere in a column poisons its mean: one P-length check instead of a host pass over X
+      std::vector<double> mu_host(h.Ppad);
+      CK(cudaMemcpy(mu_host.data(), d->mu, (size_t)h.Ppad * sizeof(double), cudaMemcpyDeviceToHost));
+      for (double v : mu_host)
+        if (!std::isfinite(v)) return fail(PLSPM_ERR_INVALID, "non-finite values in the observation matrix");
+    }
     g_pool.release(partial);
     g_pool.release(src_col);
     return 0;
@@ -1263,7 +1311,7 @@ void plspm_data_destroy(plspm_data* d) {
   if (d->mu) g_pool.release(d->mu);
   if (d->Xh) g_pool.release(d->Xh);
   if (d->inv_sd) g_pool.release(d->inv_sd);
-  if (d->blas) cublasDestroy(d->blas);
+  if (d->blas) blas_release(d->blas_device, d->blas);
   if (d->ws.ptr) g_pool.release(d->ws.ptr);
   if (d->stream) cudaStreamDestroy(d->stream);
   delete d;

@@ -158,11 +158,14 @@ class Data:
                 raise ValueError("X must be [N, %d]" % model.P)
             if X.dtype != np.float64 or not X.flags.c_contiguous:
                 X = np.ascontiguousarray(X, dtype=np.float64)
-            if not np.isfinite(X).all():
-                raise NotImplementedError("missing / non-finite values are not supported by the CUDA path yet")
             self.N = int(X.shape[0])
-            _check(load().plspm_data_create(model._h, X.ctypes.data_as(ctypes.c_void_p), self.N, int(X.shape[1]), 0,
-                                            ctypes.byref(self._h)))
+            try:
+                _check(load().plspm_data_create(model._h, X.ctypes.data_as(ctypes.c_void_p), self.N, int(X.shape[1]), 0,
+                                                ctypes.byref(self._h)))
+            except EngineError as e:  # the library finds NaN / Inf through the column means (no host pass over X)
+                if "non-finite" in str(e):
+                    raise NotImplementedError("missing / non-finite values are not supported by the CUDA path yet")
+                raise
 
     def close(self):
         if self._h:

@@ -351,3 +351,14 @@ def test_tiny_and_degenerate_shapes(eng):
     got = eng.fit(model, data, "centroid")
     check_fit(got, orc.fit(X2, [1, 1], [0, 0], path, "centroid", False))
     np.testing.assert_allclose(np.abs(got["loadings"]), 1.0, rtol=1e-12)
+
+
+def test_non_finite_input_is_refused(eng):
+    X, path = make_synthetic(500, 3, 3, 1)
+    model = eng.Model([3] * 3, [0] * 3, path, False)
+    for bad in (np.nan, np.inf):
+        Xb = X.copy()
+        Xb[17, 4] = bad
+        with pytest.raises(NotImplementedError):
+            eng.Data(model, Xb)
+    eng.Data(model, X).close()
