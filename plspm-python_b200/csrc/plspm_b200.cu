@@ -212,6 +212,11 @@ struct plspm_data {
   cublasHandle_t blas = nullptr;
   int blas_device = 0;
   bool fast_vote = false;    // the fp16 pass is worth trying on this data
+  // exact integer digit planes of x~ for the tensor-core column sums (see digits_kernel)
+  int8_t* D8 = nullptr;      // [I8_DIGITS * Ppad][Npad]
+  double* dscale = nullptr;  // [Ppad] value of one unit of the least significant digit
+  int64_t Npad = 0;
+  bool i8_colsum = false;
   cudaStream_t stream = nullptr;
   Workspace ws;          // grown on demand, reused across calls
   StageTimer timer;
@@ -373,6 +378,104 @@ __global__ void make_half_kernel(const double* __restrict__ X, int64_t N, int Pp
   const int64_t total = N * Ppad;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x)
     out[e] = __double2half(X[e] * inv_sd[e % Ppad]);
+}
+
+// ---- column sums on the tensor cores, exactly ------------------------------------------------------
+// colsum[b][p] = sum_i c_bi x~_ip has a small-integer operand (the multiplicities), so it can be an INT8
+// GEMM with int32 accumulation -- exact integer arithmetic -- if x~ is an integer too.  At upload every
+// column is scaled by a power of two to |q| <= 2^40 (q = rint(x~ 2^(40-e_p)), 2^e_p >= max|x~_p|) and q is
+// split into six balanced base-128 digits d_k in [-64, 63], stored as int8 planes D8[k][p][i] (k-major,
+// each column contiguous over the rows: the "TN" operand layout of the IMMA kernels).  Per batch:
+// S_k = counts8 x D8_k (one cuBLAS int8 GEMM over all planes), colsum = dscale_p * sum_k 128^k S_k.
+// Rounding: |x~ - q 2^(e_p-40)| <= 2^(e_p-41), i.e. 4.5e-13 of the column's largest value, random in sign.
+// Multiplicities above 127 (impossible for practical bootstrap draws, possible with injected indices)
+// raise a flag and the batch is redone with the fp64 kernel.
+constexpr int I8_DIGITS = 6;
+constexpr int64_t I8_KCHUNK = 262144;  // rows per GEMM: 262144 * 64 * 127 < 2^31
+__global__ void colabsmax_partial_kernel(const double* __restrict__ X, int64_t N, int Ppad, int64_t rows_per_block,
+                                         double* __restrict__ partial) {
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block, r1 = min(r0 + rows_per_block, N);
+  for (int p = threadIdx.x; p < Ppad; p += blockDim.x) {
+    double m = 0.0;
+    for (int64_t i = r0; i < r1; ++i) m = fmax(m, fabs(X[i * Ppad + p]));
+    partial[(int64_t)blockIdx.x * Ppad + p] = m;
+  }
+}
+__global__ void digit_scale_kernel(const double* __restrict__ partial, int nblocks, int Ppad, double* __restrict__ dscale,
+                                   double* __restrict__ qscale) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= Ppad) return;
+  double m = 0.0;
+  for (int b = 0; b < nblocks; ++b) m = fmax(m, partial[(int64_t)b * Ppad + p]);
+  int e = 0;
+  if (m > 0.0) {
+    frexp(m, &e);  // m = f 2^e, f in [0.5, 1): 2^e > m
+  }
+  dscale[p] = ldexp(1.0, e - 40);
+  qscale[p] = ldexp(1.0, 40 - e);
+}
+// tile = 32 columns x 128 rows; digits go through shared memory so that both the reads of X (along p) and
+// the writes of the planes (along i) are coalesced
+__global__ void __launch_bounds__(256) digits_kernel(const double* __restrict__ X, int64_t N, int Ppad, int64_t Npad,
+                                                     const double* __restrict__ qscale, int8_t* __restrict__ D8) {
+  __shared__ __align__(4) int8_t sm[I8_DIGITS][32][132];
+  const int p0 = blockIdx.x * 32;
+  const int64_t i0 = (int64_t)blockIdx.y * 128;
+  for (int e = threadIdx.x; e < 32 * 128; e += 256) {
+    const int pl = e & 31, il = e >> 5;
+    const int64_t i = i0 + il;
+    const int p = p0 + pl;
+    long long q = 0;
+    if (i < N && p < Ppad) q = __double2ll_rn(X[i * Ppad + p] * qscale[p]);
+#pragma unroll
+    for (int k = 0; k < I8_DIGITS; ++k) {
+      const long long dgt = ((q + 64) & 127) - 64;
+      q = (q - dgt) >> 7;
+      sm[k][pl][il] = (int8_t)dgt;
+    }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < I8_DIGITS * 32 * 32; e += 256) {
+    const int w = e & 31, row = e >> 5, k = row >> 5, pl = row & 31;
+    const int p = p0 + pl;
+    const int64_t i = i0 + 4 * w;
+    if (p < Ppad && i < Npad)
+      *reinterpret_cast<uint32_t*>(D8 + ((int64_t)k * Ppad + p) * Npad + i) = *reinterpret_cast<const uint32_t*>(&sm[k][pl][4 * w]);
+  }
+}
+// multiplicities as int8 [nrep][Npad]; thread = 4 rows
+__global__ void counts8_kernel(const uint32_t* __restrict__ counts, int64_t N, int64_t Npad, int64_t nrep,
+                               int8_t* __restrict__ out, int* __restrict__ overflow) {
+  const int64_t per_rep = Npad / 4;
+  const int64_t total = nrep * per_rep;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = e / per_rep, i = (e - b * per_rep) * 4;
+    uint32_t pk = 0;
+    bool big = false;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t c = (i + j < N) ? counts[b * N + i + j] : 0u;
+      big |= c > 127u;
+      pk |= (c & 127u) << (8 * j);
+    }
+    if (big) *overflow = 1;
+    *reinterpret_cast<uint32_t*>(out + b * Npad + i) = pk;
+  }
+}
+// colsum[b][p] (+)= dscale_p * sum_k 128^k S[b][k*Ppad + p]
+__global__ void digits_combine_kernel(const int32_t* __restrict__ S, int64_t nrep, int Ppad, const double* __restrict__ dscale,
+                                      int accumulate, double* __restrict__ colsum) {
+  const int64_t total = nrep * Ppad;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = e / Ppad;
+    const int p = (int)(e - b * Ppad);
+    const int32_t* s = S + b * (int64_t)I8_DIGITS * Ppad + p;
+    double v = 0.0;
+#pragma unroll
+    for (int k = I8_DIGITS - 1; k >= 0; --k) v = v * 128.0 + (double)s[(int64_t)k * Ppad];
+    v *= dscale[p];
+    colsum[e] = accumulate ? colsum[e] + v : v;
+  }
 }
 
 // Scores for the tensor-core sign vote:
@@ -1285,6 +1388,38 @@ int plspm_data_create(const plspm_model* m, const double* X, int64_t N, int64_t 
       d->fast_vote = true;
       trace("fp16 copy + blas");
     }
+    // integer digit planes for the tensor-core column sums (PLSPM_COLSUM=fp64 keeps the fp64 kernel)
+    static const bool colsum_fp64 = getenv("PLSPM_COLSUM") && std::string(getenv("PLSPM_COLSUM")) == "fp64";
+    if (!colsum_fp64 && N >= 4096 && N < ((int64_t)1 << 31) - 16) {
+      if (!d->blas) {
+        d->blas = blas_acquire(dev);
+        if (!d->blas) return fail(PLSPM_ERR_CUDA, "cublasCreate failed");
+        d->blas_device = dev;
+        cublasSetStream(d->blas, st);
+      }
+      d->Npad = (N + 15) / 16 * 16;
+      double *amax = nullptr, *qscale = nullptr;
+      CK(g_pool.alloc((void**)&amax, (size_t)nblocks * h.Ppad * sizeof(double)));
+      CK(g_pool.alloc((void**)&qscale, (size_t)h.Ppad * sizeof(double)));
+      CK(g_pool.alloc((void**)&d->dscale, (size_t)h.Ppad * sizeof(double)));
+      CK(g_pool.alloc((void**)&d->D8, (size_t)I8_DIGITS * h.Ppad * d->Npad));
+      d->timer.begin(ST_UPLOAD, st);
+      colabsmax_partial_kernel<<<nblocks, 256, 0, st>>>(d->X, N, h.Ppad, rpb, amax);
+      d->timer.end(st);
+      d->timer.begin(ST_UPLOAD, st);
+      digit_scale_kernel<<<(h.Ppad + 127) / 128, 128, 0, st>>>(amax, nblocks, h.Ppad, d->dscale, qscale);
+      d->timer.end(st);
+      d->timer.begin(ST_UPLOAD, st);
+      digits_kernel<<<dim3((h.Ppad + 31) / 32, (unsigned)((d->Npad + 127) / 128)), 256, 0, st>>>(d->X, N, h.Ppad, d->Npad,
+                                                                                            qscale, d->D8);
+      d->timer.end(st);
+      CK(cudaGetLastError());
+      CK(cudaStreamSynchronize(st));
+      g_pool.release(amax);
+      g_pool.release(qscale);
+      d->i8_colsum = true;
+      trace("digit planes");
+    }
     CK(cudaStreamSynchronize(st));
     d->timer.collect();
     trace("timer collected");
@@ -1311,6 +1446,8 @@ void plspm_data_destroy(plspm_data* d) {
   if (d->mu) g_pool.release(d->mu);
   if (d->Xh) g_pool.release(d->Xh);
   if (d->inv_sd) g_pool.release(d->inv_sd);
+  if (d->D8) g_pool.release(d->D8);
+  if (d->dscale) g_pool.release(d->dscale);
   if (d->blas) blas_release(d->blas_device, d->blas);
   if (d->ws.ptr) g_pool.release(d->ws.ptr);
   if (d->stream) cudaStreamDestroy(d->stream);
@@ -1429,6 +1566,8 @@ struct BatchBuffers {
   size_t weights, loadings, r2, paths, totalfx, crossl, coef, shift, scores;
   // numeric non-metric path: per-replicate iteration state
   size_t num_a, num_co, num_cn, num_so, num_sn, num_meta, num_done, num_cpart;
+  // tensor-core column sums: int8 multiplicities, int32 digit sums, overflow flag
+  size_t c8, s32, ovf;
 };
 static BatchBuffers layout_batch(const plspm_data* d, int64_t nb, const BatchPlan& bp, bool with_counts, bool with_idx,
                                  bool rows_on_device_of_caller, bool single_fit, bool want_scores) {
@@ -1461,6 +1600,10 @@ static BatchBuffers layout_batch(const plspm_data* d, int64_t nb, const BatchPla
   b.num_sn = take(numeric ? (size_t)nb * h.L * 8 : 0);
   b.num_meta = take(numeric ? (size_t)nb * 16 : 0);
   b.num_done = take(8);
+  const bool i8 = d->i8_colsum && with_counts;
+  b.c8 = take(i8 ? (size_t)nb * d->Npad : 0);
+  b.s32 = take(i8 ? (size_t)nb * I8_DIGITS * h.Ppad * sizeof(int32_t) : 0);
+  b.ovf = take(8);
   b.num_cpart = take(numeric ? (size_t)nb * bp.cv_gx * 8 : 0);
   const size_t ldl = (size_t)(nb + 7) / 8 * 8;  // replicate stride of the LV-major score / cross-moment layout
   b.BT = take(fast ? ldl * h.L * FAST_RC * sizeof(__half) : 0);
@@ -1552,6 +1695,32 @@ static int launch_moments(plspm_data* d, int64_t nb, const uint32_t* counts_dev,
   char* base = (char*)d->ws.ptr;
   auto D = [&](size_t o) { return (double*)(base + o); };
   if (int rc = launch_stream(d, false, nb, counts_dev, bp.gram, D(bb.G), D(bb.Gpart), nullptr)) return rc;
+  if (d->i8_colsum && counts_dev) {
+    int8_t* c8 = (int8_t*)(base + bb.c8);
+    int32_t* s32 = (int32_t*)(base + bb.s32);
+    d->timer.begin(ST_COLSUM, st);
+    counts8_kernel<<<d->sm_count * 8, 256, 0, st>>>(counts_dev, d->N, d->Npad, nb, c8, (int*)(base + bb.ovf));
+    d->timer.end(st);
+    CK(cudaGetLastError());
+    const int32_t one = 1, zero = 0;
+    const int gemm_m = I8_DIGITS * h.Ppad;
+    bool ok = true;
+    for (int64_t k0 = 0; k0 < d->Npad && ok; k0 += I8_KCHUNK) {
+      const int kc = (int)std::min<int64_t>(I8_KCHUNK, d->Npad - k0);
+      d->timer.begin(ST_COLSUM, st);
+      cublasStatus_t cs = cublasGemmEx(d->blas, CUBLAS_OP_T, CUBLAS_OP_N, gemm_m, (int)nb, kc, &one, d->D8 + k0, CUDA_R_8I,
+                                       (int)d->Npad, c8 + k0, CUDA_R_8I, (int)d->Npad, &zero, s32, CUDA_R_32I, gemm_m,
+                                       CUBLAS_COMPUTE_32I, CUBLAS_GEMM_DEFAULT);
+      d->timer.end(st);
+      if (cs != CUBLAS_STATUS_SUCCESS) { ok = false; break; }
+      d->timer.begin(ST_COLSUM, st);
+      digits_combine_kernel<<<d->sm_count * 2, 256, 0, st>>>(s32, nb, h.Ppad, d->dscale, k0 > 0 ? 1 : 0, D(bb.colsum));
+      d->timer.end(st);
+      CK(cudaGetLastError());
+    }
+    if (ok) return 0;
+    d->i8_colsum = false;  // this cuBLAS build has no int8 GEMM for the shape: fp64 kernel from now on
+  }
   dim3 grid_cs((h.Ppad + CS_COLS - 1) / CS_COLS, (unsigned)((nb + CS_REPS - 1) / CS_REPS), bp.cs_chunks);
   d->timer.begin(ST_COLSUM, st);
   const size_t cs_smem_bytes = (size_t)(CS_ROWS * CS_COLS + CS_ROWS * CS_REPS) * 8;
@@ -1784,7 +1953,7 @@ int plspm_bootstrap(const plspm_model* m, const plspm_data* dc, int32_t scheme, 
   const bool vote = !h.full && !m->numeric;
   const size_t per_rep = (size_t)N * 4 + ((size_t)h.n_tiles * TILE + (vote ? (size_t)h.n_cross * TILE : 0) +
                                           (m->numeric ? 6 : 2) * h.Ppad + h.ws_doubles + n_out) * 8 +
-                         (idx ? (size_t)N * 4 : 0) + 64;
+                         (idx ? (size_t)N * 4 : 0) + (d->i8_colsum ? (size_t)d->Npad + I8_DIGITS * h.Ppad * 4 : 0) + 64;
   int64_t nb_max = std::max<int64_t>(1, (int64_t)((size_t)1536 * 1024 * 1024 / per_rep));
   if (getenv("PLSPM_MAX_BATCH")) nb_max = std::max<int64_t>(1, std::min<int64_t>(nb_max, atoll(getenv("PLSPM_MAX_BATCH"))));
   nb_max = std::min<int64_t>(nb_max, rep_count);
@@ -1800,6 +1969,7 @@ int plspm_bootstrap(const plspm_model* m, const plspm_data* dc, int32_t scheme, 
   if (int rc = ws_reserve(d, bb.total)) return rc;
   char* base = (char*)d->ws.ptr;
   cudaStream_t st = d->stream;
+  CK(cudaMemsetAsync(base + bb.ovf, 0, 8, st));
   for (int64_t b0 = 0; b0 < rep_count; b0 += nb_max) {
     const int64_t nb = std::min(nb_max, rep_count - b0);
     // a short last batch reuses the plan (and therefore the workspace layout) of a full one
@@ -1816,10 +1986,20 @@ int plspm_bootstrap(const plspm_model* m, const plspm_data* dc, int32_t scheme, 
     d->timer.end(st);
     CK(cudaGetLastError());
     double* rows = out_is_device ? out + (size_t)b0 * n_out : (double*)(base + bb.out);
-    if (m->numeric) {
-      if (int rc = run_batch_num(d, nb, cnt, bb, scheme, tol, max_iter, bp, rows, false)) return rc;
-    } else if (int rc = run_batch(d, nb, cnt, bb, scheme, tol, max_iter, bp, rows, false)) {
-      return rc;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+      if (m->numeric) {
+        if (int rc = run_batch_num(d, nb, cnt, bb, scheme, tol, max_iter, bp, rows, false)) return rc;
+      } else if (int rc = run_batch(d, nb, cnt, bb, scheme, tol, max_iter, bp, rows, false)) {
+        return rc;
+      }
+      if (!d->i8_colsum) break;
+      // a multiplicity above 127 does not fit the int8 operand of the tensor-core column sums: redo in fp64
+      int ovf = 0;
+      CK(cudaMemcpyAsync(&ovf, base + bb.ovf, 4, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      if (!ovf) break;
+      CK(cudaMemsetAsync(base + bb.ovf, 0, 8, st));
+      d->i8_colsum = false;
     }
     if (vote && d->fast_vote) {
       // replicates whose low-precision sign vote was undecided are redone with exact fp64 cross moments

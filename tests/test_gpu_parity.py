@@ -362,3 +362,28 @@ def test_non_finite_input_is_refused(eng):
         with pytest.raises(NotImplementedError):
             eng.Data(model, Xb)
     eng.Data(model, X).close()
+
+
+def test_tensor_core_column_sums_match_fp64_and_overflow_falls_back(eng):
+    """Column sums run as an exact int8 digit-plane GEMM for N >= 4096; multiplicities above 127 (only
+    reachable with injected indices) must fall back to the fp64 kernel.  Both routes vs the oracle."""
+    N, L, K = 6000, 4, 5
+    X, path = make_synthetic(N, L, K, 21)
+    X = X * np.array([1e-3, 1.0, 37.0, 1e4] * 5)[None, :] + 3.0  # columns of very different scale, non-zero mean
+    model = eng.Model([K] * L, [0] * L, path, True)
+    data = eng.Data(model, X)
+    rng = np.random.default_rng(2)
+    idx = rng.integers(0, N, size=(4, N)).astype(np.int32)
+    idx[2, :300] = 11          # row 11 drawn 300+ times in replicate 2: overflows int8
+    rows, status, iters = eng.bootstrap(model, data, "centroid", 0, 4, idx=idx)
+    w, r2, total, direct, load = model.split_row(rows)
+    for b in range(4):
+        ref, it, st = orc.replicate_row(X, idx[b], [K] * L, [0] * L, path, "centroid", True)
+        assert status[b] == st == 0 and iters[b] == it
+        np.testing.assert_allclose(rows[b], ref, rtol=REL, atol=1e-9)
+    # after the fallback the handle keeps working (fp64 route), and a fresh handle uses the int8 route again
+    rows2, _, _ = eng.bootstrap(model, data, "centroid", 0, 2, idx=idx[:2])
+    np.testing.assert_allclose(rows2, rows[:2], rtol=1e-9, atol=1e-12)
+    data2 = eng.Data(model, X)
+    rows3, _, _ = eng.bootstrap(model, data2, "centroid", 0, 2, idx=idx[:2])
+    np.testing.assert_allclose(rows3, rows[:2], rtol=1e-9, atol=1e-12)
