@@ -819,9 +819,12 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const GramParams 
   if (warp >= n_active) return;
 
   // ---- consumer warp: one (replicate, tile group); lane = one 8x8 tile ------------------------
+  // items are tile-group major: the warps of a CTA work on the same tile group for 8 replicates, so a CTA
+  // is (except at a group boundary) all "diagonal" or all "generic" warps -- see below
   const int64_t item = item0 + warp;
-  const int64_t rep_pos = item / p.n_tg;
-  const int tg = (int)(item - rep_pos * p.n_tg);
+  const int64_t nrep_pos = p.n_items / p.n_tg;
+  const int tg = (int)(item / nrep_pos);
+  const int64_t rep_pos = item - (int64_t)tg * nrep_pos;
   const int64_t rep = p.rep_map ? (int64_t)p.rep_map[rep_pos] : rep_pos;
   int tile, sa, sb;
   if constexpr (CROSS) {
@@ -838,6 +841,9 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const GramParams 
     sb = tile >= 0 ? p.tile_sb[tile] : 0;
   }
   const bool tile_ok = tile >= 0;
+  // A tile group that holds only diagonal tiles (sa == sb; the model builder packs them together) needs one
+  // operand per row and, by symmetry, 36 of the 64 products.
+  const bool diag = !CROSS && __all_sync(0xffffffffu, !tile_ok || sa == sb);
   // 16-byte chunks of a slot are read in a lane-dependent rotated order so that the 32 LDS.128 of
   // a warp spread over all bank quads (slot stride 64 B would otherwise be a 16-way conflict).
   // This holds for the row operand too: a sparse tile group holds ~3 tiles per row slot, i.e. ~11
@@ -901,6 +907,41 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const GramParams 
             "+d"(acc[i][6]), "+d"(acc[i][7])
           : "d"(xa[i]), "d"(xb[0]), "d"(xb[1]), "d"(xb[2]), "d"(xb[3]), "d"(xb[4]), "d"(xb[5]), "d"(xb[6]),
             "d"(xb[7]));
+  };
+  auto accumulate_diag = [&](double (&xa)[8], double (&xs)[8], double c) {  // xs = c * xa, upper triangle only
+    asm volatile(
+        "mul.f64 %0, %8, %16;\n\tmul.f64 %1, %9, %16;\n\tmul.f64 %2, %10, %16;\n\tmul.f64 %3, %11, %16;\n\t"
+        "mul.f64 %4, %12, %16;\n\tmul.f64 %5, %13, %16;\n\tmul.f64 %6, %14, %16;\n\tmul.f64 %7, %15, %16;"
+        : "=d"(xs[0]), "=d"(xs[1]), "=d"(xs[2]), "=d"(xs[3]), "=d"(xs[4]), "=d"(xs[5]), "=d"(xs[6]), "=d"(xs[7])
+        : "d"(xa[0]), "d"(xa[1]), "d"(xa[2]), "d"(xa[3]), "d"(xa[4]), "d"(xa[5]), "d"(xa[6]), "d"(xa[7]), "d"(c));
+    asm volatile("fma.rn.f64 %0, %8, %9, %0;\n\tfma.rn.f64 %1, %8, %10, %1;\n\tfma.rn.f64 %2, %8, %11, %2;\n\tfma.rn.f64 %3, %8, %12, %3;\n\tfma.rn.f64 %4, %8, %13, %4;\n\tfma.rn.f64 %5, %8, %14, %5;\n\tfma.rn.f64 %6, %8, %15, %6;\n\tfma.rn.f64 %7, %8, %16, %7;"
+                 : "+d"(acc[0][0]), "+d"(acc[0][1]), "+d"(acc[0][2]), "+d"(acc[0][3]), "+d"(acc[0][4]), "+d"(acc[0][5]), "+d"(acc[0][6]), "+d"(acc[0][7])
+                 : "d"(xa[0]), "d"(xs[0]), "d"(xs[1]), "d"(xs[2]), "d"(xs[3]), "d"(xs[4]), "d"(xs[5]), "d"(xs[6]), "d"(xs[7]));
+    asm volatile("fma.rn.f64 %0, %7, %8, %0;\n\tfma.rn.f64 %1, %7, %9, %1;\n\tfma.rn.f64 %2, %7, %10, %2;\n\tfma.rn.f64 %3, %7, %11, %3;\n\tfma.rn.f64 %4, %7, %12, %4;\n\tfma.rn.f64 %5, %7, %13, %5;\n\tfma.rn.f64 %6, %7, %14, %6;"
+                 : "+d"(acc[1][1]), "+d"(acc[1][2]), "+d"(acc[1][3]), "+d"(acc[1][4]), "+d"(acc[1][5]), "+d"(acc[1][6]), "+d"(acc[1][7])
+                 : "d"(xa[1]), "d"(xs[1]), "d"(xs[2]), "d"(xs[3]), "d"(xs[4]), "d"(xs[5]), "d"(xs[6]), "d"(xs[7]));
+    asm volatile("fma.rn.f64 %0, %6, %7, %0;\n\tfma.rn.f64 %1, %6, %8, %1;\n\tfma.rn.f64 %2, %6, %9, %2;\n\tfma.rn.f64 %3, %6, %10, %3;\n\tfma.rn.f64 %4, %6, %11, %4;\n\tfma.rn.f64 %5, %6, %12, %5;"
+                 : "+d"(acc[2][2]), "+d"(acc[2][3]), "+d"(acc[2][4]), "+d"(acc[2][5]), "+d"(acc[2][6]), "+d"(acc[2][7])
+                 : "d"(xa[2]), "d"(xs[2]), "d"(xs[3]), "d"(xs[4]), "d"(xs[5]), "d"(xs[6]), "d"(xs[7]));
+    asm volatile("fma.rn.f64 %0, %5, %6, %0;\n\tfma.rn.f64 %1, %5, %7, %1;\n\tfma.rn.f64 %2, %5, %8, %2;\n\tfma.rn.f64 %3, %5, %9, %3;\n\tfma.rn.f64 %4, %5, %10, %4;"
+                 : "+d"(acc[3][3]), "+d"(acc[3][4]), "+d"(acc[3][5]), "+d"(acc[3][6]), "+d"(acc[3][7])
+                 : "d"(xa[3]), "d"(xs[3]), "d"(xs[4]), "d"(xs[5]), "d"(xs[6]), "d"(xs[7]));
+    asm volatile("fma.rn.f64 %0, %4, %5, %0;\n\tfma.rn.f64 %1, %4, %6, %1;\n\tfma.rn.f64 %2, %4, %7, %2;\n\tfma.rn.f64 %3, %4, %8, %3;"
+                 : "+d"(acc[4][4]), "+d"(acc[4][5]), "+d"(acc[4][6]), "+d"(acc[4][7])
+                 : "d"(xa[4]), "d"(xs[4]), "d"(xs[5]), "d"(xs[6]), "d"(xs[7]));
+    asm volatile("fma.rn.f64 %0, %3, %4, %0;\n\tfma.rn.f64 %1, %3, %5, %1;\n\tfma.rn.f64 %2, %3, %6, %2;"
+                 : "+d"(acc[5][5]), "+d"(acc[5][6]), "+d"(acc[5][7])
+                 : "d"(xa[5]), "d"(xs[5]), "d"(xs[6]), "d"(xs[7]));
+    asm volatile("fma.rn.f64 %0, %2, %3, %0;\n\tfma.rn.f64 %1, %2, %4, %1;"
+                 : "+d"(acc[6][6]), "+d"(acc[6][7])
+                 : "d"(xa[6]), "d"(xs[6]), "d"(xs[7]));
+    asm volatile("fma.rn.f64 %0, %1, %2, %0;"
+                 : "+d"(acc[7][7])
+                 : "d"(xa[7]), "d"(xs[7]));
+  };
+  auto load_row_diag = [&](uint32_t row_addr, double (&xa)[8]) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) lds128(row_addr + boff_a[k], xa[2 * k], xa[2 * k + 1]);
   };
   // per-warp list of the tile's non-zero rows: {row byte offset in the stage, multiplicity as fp64},
   // built once per tile by all lanes, so that the row loop is a plain counted loop
@@ -973,7 +1014,26 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const GramParams 
       }
       __syncwarp();
     }
-    if (n_nz > 0) {
+    if (n_nz > 0 && diag) {
+      // diagonal tile group: same software pipeline, one operand per row, 8 DMUL + 36 DFMA per row
+      double xa0[8], xa1[8], xs[8], c0, c1, ce0, ce1;
+      uint32_t oe0, oe1;
+      load_entry(0, oe0, ce0);
+      load_entry(1, oe1, ce1);
+      load_row_diag(base + oe0, xa0);
+      c0 = ce0;
+      for (int k = 0; k < n_nz; k += 2) {
+        load_row_diag(base + oe1, xa1);
+        c1 = ce1;
+        load_entry(k + 2, oe0, ce0);
+        accumulate_diag(xa0, xs, c0);
+        load_row_diag(base + oe0, xa0);
+        c0 = ce0;
+        load_entry(k + 3, oe1, ce1);
+        accumulate_diag(xa1, xs, c1);
+      }
+      asm volatile("{\n.reg .b32 lo, hi;\nmov.b64 {lo, hi}, %1;\nand.b32 %0, lo, 0;\n}" : "=r"(release_dep) : "d"(xa0[7]));
+    } else if (n_nz > 0) {
       // Software pipeline over the non-zero rows, two rows per trip, straight-line body: the
       // operands of row k+1 are in flight (LDS) while the 64 FMAs of row k issue, and the list
       // entries of rows k+2 / k+3 are already in registers.  An odd row count runs one padded row
@@ -1028,7 +1088,7 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const GramParams 
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int cb = 2 * (((j >> 1) + rot_b) & 3) + (j & 1);
-        g[ra * SLOT + cb] = acc[i][j];
+        g[ra * SLOT + cb] = (diag && j < i) ? acc[j][i] : acc[i][j];  // diagonal groups hold the upper triangle
       }
     }
   }

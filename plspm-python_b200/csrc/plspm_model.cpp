@@ -160,32 +160,51 @@ int build_model(int L, const int32_t* block_sizes, const int8_t* modes, const in
     for (auto& pr : und) m.omega[(size_t)pr.first * L + pr.second] = m.omega[(size_t)pr.second * L + pr.first] = 1;
   }
   m.n_tiles = (int)m.tile_sa.size();
-  // pack tiles into warps (tile groups of 32 lanes): chunks of one row slot, first-fit decreasing
+  // pack tiles into warps (tile groups of 32 lanes): chunks of one row slot, first-fit decreasing.
+  // Diagonal tiles (sa == sb) go into groups of their own when that costs no extra group: such a warp
+  // needs one operand per row and 36 of the 64 products (gram_kernel, "diag"); they are listed last so
+  // that the shorter CTAs fill the tail of the launch.
   {
-    std::vector<std::vector<int>> chunks;
-    for (int t = 0; t < m.n_tiles;) {
-      int e = t;
-      while (e < m.n_tiles && m.tile_sa[e] == m.tile_sa[t] && e - t < 32) ++e;
-      chunks.emplace_back();
-      for (int k = t; k < e; ++k) chunks.back().push_back(k);
-      t = e;
-    }
     const bool pack = !(getenv("PLSPM_TILE_PACK") && atoi(getenv("PLSPM_TILE_PACK")) == 0);
-    if (!pack) {  // natural order, 32 consecutive tiles per group (experiment switch)
-      chunks.clear();
-      for (int t = 0; t < m.n_tiles; t += 32) {
-        chunks.emplace_back();
-        for (int k = t; k < std::min(t + 32, m.n_tiles); ++k) chunks.back().push_back(k);
+    auto pack_bins = [&](const std::vector<int>& ids) {
+      std::vector<std::vector<int>> chunks;
+      for (size_t t = 0; t < ids.size();) {
+        size_t e = t;
+        while (e < ids.size() && m.tile_sa[ids[e]] == m.tile_sa[ids[t]] && e - t < 32) ++e;
+        chunks.emplace_back(ids.begin() + t, ids.begin() + e);
+        t = e;
       }
+      if (!pack) {  // natural order, 32 consecutive tiles per group (experiment switch)
+        chunks.clear();
+        for (size_t t = 0; t < ids.size(); t += 32)
+          chunks.emplace_back(ids.begin() + t, ids.begin() + std::min(t + 32, ids.size()));
+      }
+      std::stable_sort(chunks.begin(), chunks.end(),
+                       [](const std::vector<int>& a, const std::vector<int>& b) { return a.size() > b.size(); });
+      std::vector<std::vector<int>> bins;
+      for (auto& ch : chunks) {
+        bool placed = false;
+        for (auto& b : bins)
+          if (b.size() + ch.size() <= 32) { b.insert(b.end(), ch.begin(), ch.end()); placed = true; break; }
+        if (!placed) bins.push_back(ch);
+      }
+      return bins;
+    };
+    std::vector<int> all_ids, diag_ids, off_ids;
+    for (int t = 0; t < m.n_tiles; ++t) {
+      all_ids.push_back(t);
+      (m.tile_sa[t] == m.tile_sb[t] ? diag_ids : off_ids).push_back(t);
     }
-    std::stable_sort(chunks.begin(), chunks.end(),
-                     [](const std::vector<int>& a, const std::vector<int>& b) { return a.size() > b.size(); });
-    std::vector<std::vector<int>> bins;
-    for (auto& ch : chunks) {
-      bool placed = false;
-      for (auto& b : bins)
-        if (b.size() + ch.size() <= 32) { b.insert(b.end(), ch.begin(), ch.end()); placed = true; break; }
-      if (!placed) bins.push_back(ch);
+    std::vector<std::vector<int>> bins = pack_bins(all_ids);
+    const bool split_ok = !(getenv("PLSPM_TILE_DIAG") && atoi(getenv("PLSPM_TILE_DIAG")) == 0);
+    if (split_ok && pack && !off_ids.empty()) {
+      std::vector<std::vector<int>> off_bins = pack_bins(off_ids), diag_bins;
+      for (size_t t = 0; t < diag_ids.size(); t += 32)
+        diag_bins.emplace_back(diag_ids.begin() + t, diag_ids.begin() + std::min(t + 32, diag_ids.size()));
+      if (off_bins.size() + diag_bins.size() <= bins.size()) {
+        bins = off_bins;
+        bins.insert(bins.end(), diag_bins.begin(), diag_bins.end());
+      }
     }
     m.n_tg = (int)bins.size();
     m.lane_tile.assign((size_t)m.n_tg * 32, -1);
