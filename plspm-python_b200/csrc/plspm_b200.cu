@@ -16,6 +16,7 @@
 //
 // Nothing here falls back to a CPU path: without a CUDA device every entry point fails.
 #include <cublas_v2.h>
+#include <type_traits>
 #include <chrono>
 #include <map>
 #include <cuda_fp16.h>
@@ -890,8 +891,10 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const GramParams 
   // them AFTER the (volatile) shared-memory loads of the NEXT row in program order: without this
   // the loads get sunk below the FMA block to save registers and the software pipeline is lost
   // (measured: 6.5 % of all issue slots stalled on the first DMUL of every row).
-  auto accumulate = [&](double (&xa)[8], double (&xb)[8], double c) {
-    if constexpr (!CROSS)  // (the score scratch is already multiplied by the multiplicity)
+  // `scale` is a compile-time tag: rows of multiplicity 1 (58 % of the non-zero rows of a resample) are
+  // listed first and skip the 8 multiplications
+  auto accumulate = [&](auto scale, double (&xa)[8], double (&xb)[8], double c) {
+    if constexpr (!CROSS && decltype(scale)::value)  // (the score scratch is already multiplied by the multiplicity)
     asm volatile(
         "mul.f64 %0, %0, %8;\n\tmul.f64 %1, %1, %8;\n\tmul.f64 %2, %2, %8;\n\tmul.f64 %3, %3, %8;\n\t"
         "mul.f64 %4, %4, %8;\n\tmul.f64 %5, %5, %8;\n\tmul.f64 %6, %6, %8;\n\tmul.f64 %7, %7, %8;"
@@ -908,7 +911,11 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const GramParams 
           : "d"(xa[i]), "d"(xb[0]), "d"(xb[1]), "d"(xb[2]), "d"(xb[3]), "d"(xb[4]), "d"(xb[5]), "d"(xb[6]),
             "d"(xb[7]));
   };
-  auto accumulate_diag = [&](double (&xa)[8], double (&xs)[8], double c) {  // xs = c * xa, upper triangle only
+  auto accumulate_diag = [&](auto scale, double (&xa)[8], double (&xs)[8], double c) {  // xs = c * xa, upper triangle only
+    if constexpr (!decltype(scale)::value) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) xs[k] = xa[k];
+    } else
     asm volatile(
         "mul.f64 %0, %8, %16;\n\tmul.f64 %1, %9, %16;\n\tmul.f64 %2, %10, %16;\n\tmul.f64 %3, %11, %16;\n\t"
         "mul.f64 %4, %12, %16;\n\tmul.f64 %5, %13, %16;\n\tmul.f64 %6, %14, %16;\n\tmul.f64 %7, %15, %16;"
@@ -972,12 +979,15 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const GramParams 
     const uint32_t use = (uint32_t)(t / p.stages);
     const uint32_t cnt = cnt_next;
     if (t + 1 < n_rt) cnt_next = load_counts(t + 1);  // prefetch: hides the global-load latency
-    const uint32_t mask = __ballot_sync(0xffffffffu, cnt != 0);
-    const int n_nz = __popc(mask);
+    // rows of multiplicity 1 first, then the others
+    const uint32_t mask1 = __ballot_sync(0xffffffffu, cnt == 1), mask2 = __ballot_sync(0xffffffffu, cnt > 1);
+    const int n_one = __popc(mask1), n_nz = n_one + __popc(mask2);
     if (cnt != 0) {
-      const int pos = __popc(mask & ((1u << lane) - 1u));
+      const uint32_t below = (1u << lane) - 1u;
+      const int pos = (cnt == 1) ? __popc(mask1 & below) : n_one + __popc(mask2 & below);
       my_list[pos] = make_double2(__longlong_as_double((long long)((uint32_t)lane * row_bytes)), (double)cnt);
     }
+    const int n_pairs_one = CROSS ? 0 : (n_one & ~1);  // an odd last multiplicity-1 row takes the scaled path
     // pads: multiplicity 0 on row 0 of the stage, so the pipelined loop below needs no branches
     if (lane < 8) my_list[n_nz + lane] = make_double2(__longlong_as_double(0ll), 0.0);
     __syncwarp();
@@ -1022,15 +1032,25 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const GramParams 
       load_entry(1, oe1, ce1);
       load_row_diag(base + oe0, xa0);
       c0 = ce0;
-      for (int k = 0; k < n_nz; k += 2) {
+      int k = 0;
+      for (; k < n_pairs_one; k += 2) {
+        load_row_diag(base + oe1, xa1);
+        load_entry(k + 2, oe0, ce0);
+        accumulate_diag(std::false_type{}, xa0, xs, 1.0);
+        load_row_diag(base + oe0, xa0);
+        load_entry(k + 3, oe1, ce1);
+        accumulate_diag(std::false_type{}, xa1, xs, 1.0);
+      }
+      c0 = ce0;
+      for (; k < n_nz; k += 2) {
         load_row_diag(base + oe1, xa1);
         c1 = ce1;
         load_entry(k + 2, oe0, ce0);
-        accumulate_diag(xa0, xs, c0);
+        accumulate_diag(std::true_type{}, xa0, xs, c0);
         load_row_diag(base + oe0, xa0);
         c0 = ce0;
         load_entry(k + 3, oe1, ce1);
-        accumulate_diag(xa1, xs, c1);
+        accumulate_diag(std::true_type{}, xa1, xs, c1);
       }
       asm volatile("{\n.reg .b32 lo, hi;\nmov.b64 {lo, hi}, %1;\nand.b32 %0, lo, 0;\n}" : "=r"(release_dep) : "d"(xa0[7]));
     } else if (n_nz > 0) {
@@ -1046,16 +1066,26 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const GramParams 
       load_entry(1, oe1, ce1);
       load_row(base + oe0, CROSS ? bsrc : base + oe0, xa0, xb0);
       c0 = ce0;
-      for (int k = 0; k < n_nz; k += 2) {
+      int k = 0;
+      for (; k < n_pairs_one; k += 2) {  // multiplicity 1: no scaling (Gram mode only)
+        load_row(base + oe1, base + oe1, xa1, xb1);
+        load_entry(k + 2, oe0, ce0);
+        accumulate(std::false_type{}, xa0, xb0, 1.0);
+        load_row(base + oe0, base + oe0, xa0, xb0);
+        load_entry(k + 3, oe1, ce1);
+        accumulate(std::false_type{}, xa1, xb1, 1.0);
+      }
+      c0 = ce0;
+      for (; k < n_nz; k += 2) {
         load_row(base + oe1, CROSS ? bsrc + sc_row_bytes : base + oe1, xa1, xb1);
         c1 = ce1;
         load_entry(k + 2, oe0, ce0);
-        accumulate(xa0, xb0, c0);
+        accumulate(std::true_type{}, xa0, xb0, c0);
         bsrc += 2 * sc_row_bytes;
         load_row(base + oe0, CROSS ? bsrc : base + oe0, xa0, xb0);
         c0 = ce0;
         load_entry(k + 3, oe1, ce1);
-        accumulate(xa1, xb1, c1);
+        accumulate(std::true_type{}, xa1, xb1, c1);
       }
       // The loop prefetches one row set past the end (a pad row of this stage).  Make the stage release
       // below depend on that last load, so no shared-memory read of the stage is still in flight when
