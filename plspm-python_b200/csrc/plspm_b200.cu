@@ -218,6 +218,12 @@ struct plspm_data {
   double* dscale = nullptr;  // [Ppad] value of one unit of the least significant digit
   int64_t Npad = 0;
   bool i8_colsum = false;
+  // ... and of the pair products z_i = x~_ip x~_iq of the model's Gram tile set (see zdigits_kernel)
+  int8_t* Z8 = nullptr;      // [I8_DIGITS * n_zcols][Npad]
+  double* zdscale = nullptr; // [n_zcols]
+  int *zdst = nullptr, *zdst2 = nullptr;  // [n_zcols] offsets into a replicate's tile array (mirror or -1)
+  int n_zcols = 0;
+  const plspm_model* z_model = nullptr;   // the tile set the planes were built for
   cudaStream_t stream = nullptr;
   Workspace ws;          // grown on demand, reused across calls
   StageTimer timer;
@@ -476,6 +482,75 @@ __global__ void digits_combine_kernel(const int32_t* __restrict__ S, int64_t nre
     for (int k = I8_DIGITS - 1; k >= 0; --k) v = v * 128.0 + (double)s[(int64_t)k * Ppad];
     v *= dscale[p];
     colsum[e] = accumulate ? colsum[e] + v : v;
+  }
+}
+
+// ---- the weighted Gram of a whole batch as ONE integer GEMM -----------------------------------------
+// G_b[p][q] = sum_i c_bi (x~_ip x~_iq): the bootstrap multiplicities factor out of the second moments, so
+// for all replicates of a batch the Gram tiles are  counts[nb x N] x Z[N x n_zcols],  Z = the pair-product
+// columns of the model's tile set (diagonal tiles: upper triangle).  Z is digitised like x~ above
+// (z 2^(40-e_p-e_q) rounded to an integer, six balanced base-128 digits, int8 planes), the GEMM runs on the
+// tensor cores with exact int32 accumulation, and G = 2^(e_p+e_q-40) sum_k 128^k S_k.  Per element of Z the
+// rounding is <= 2^-41 of the column's bound, random in sign: the sums are at least as accurate as fp64
+// FMA accumulation over the same rows.  The fp64 gram_kernel remains for single fits, for models whose
+// planes exceed the memory budget, and as the fallback for multiplicities above 127.
+__global__ void zscale_kernel(int n_zcols, const int* __restrict__ zp, const int* __restrict__ zq,
+                              const double* __restrict__ qscale, const double* __restrict__ dscale,
+                              double* __restrict__ zqscale, double* __restrict__ zdscale) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_zcols) return;
+  zqscale[c] = qscale[zp[c]] * qscale[zq[c]] * 9.094947017729282e-13;  // 2^-40 (all factors are powers of two)
+  zdscale[c] = dscale[zp[c]] * dscale[zq[c]] * 1099511627776.0;         // 2^40
+}
+__global__ void __launch_bounds__(256) zdigits_kernel(const double* __restrict__ X, int64_t N, int Ppad, int64_t Npad,
+                                                      int n_zcols, const int* __restrict__ zp,
+                                                      const int* __restrict__ zq, const double* __restrict__ zqscale,
+                                                      int8_t* __restrict__ Z8) {
+  __shared__ __align__(4) int8_t sm[I8_DIGITS][32][132];
+  const int c0 = blockIdx.x * 32;
+  const int64_t i0 = (int64_t)blockIdx.y * 128;
+  const int cl = threadIdx.x & 31;
+  const int col = c0 + cl;
+  const bool col_ok = col < n_zcols;
+  const int p = col_ok ? zp[col] : 0, q = col_ok ? zq[col] : 0;
+  const double sc = col_ok ? zqscale[col] : 0.0;
+  for (int il = threadIdx.x >> 5; il < 128; il += 8) {
+    const int64_t i = i0 + il;
+    long long v = 0;
+    if (i < N && col_ok) v = __double2ll_rn(X[i * Ppad + p] * X[i * Ppad + q] * sc);
+#pragma unroll
+    for (int k = 0; k < I8_DIGITS; ++k) {
+      const long long dgt = ((v + 64) & 127) - 64;
+      v = (v - dgt) >> 7;
+      sm[k][cl][il] = (int8_t)dgt;
+    }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < I8_DIGITS * 32 * 32; e += 256) {
+    const int w = e & 31, row = e >> 5, k = row >> 5, c = row & 31;
+    const int64_t i = i0 + 4 * w;
+    if (c0 + c < n_zcols && i < Npad)
+      *reinterpret_cast<uint32_t*>(Z8 + ((int64_t)k * n_zcols + c0 + c) * Npad + i) = *reinterpret_cast<const uint32_t*>(&sm[k][c][4 * w]);
+  }
+}
+// G[b][zdst[c]] (+)= zdscale_c * sum_k 128^k S[b][k*n_zcols + c]   (and the mirrored entry of diagonal tiles)
+__global__ void zcombine_kernel(const int32_t* __restrict__ S, int64_t nrep, int n_zcols, const double* __restrict__ zdscale,
+                                const int* __restrict__ zdst, const int* __restrict__ zdst2, int accumulate,
+                                int64_t g_stride, double* __restrict__ G) {
+  const int64_t total = nrep * n_zcols;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = e / n_zcols;
+    const int c = (int)(e - b * n_zcols);
+    const int32_t* s = S + b * (int64_t)I8_DIGITS * n_zcols + c;
+    double v = 0.0;
+#pragma unroll
+    for (int k = I8_DIGITS - 1; k >= 0; --k) v = v * 128.0 + (double)s[(int64_t)k * n_zcols];
+    v *= zdscale[c];
+    double* g = G + b * g_stride;
+    const int d1 = zdst[c], d2 = zdst2[c];
+    const double out = accumulate ? g[d1] + v : v;
+    g[d1] = out;
+    if (d2 >= 0) g[d2] = out;
   }
 }
 
@@ -1506,9 +1581,55 @@ int plspm_data_create(const plspm_model* m, const double* X, int64_t N, int64_t 
       CK(cudaGetLastError());
       CK(cudaStreamSynchronize(st));
       g_pool.release(amax);
-      g_pool.release(qscale);
       d->i8_colsum = true;
       trace("digit planes");
+      // pair-product planes of the model's tile set, if they fit the budget (PLSPM_I8_GRAM_GB, default 24)
+      static const double z_budget_gb = getenv("PLSPM_I8_GRAM_GB") ? atof(getenv("PLSPM_I8_GRAM_GB")) : 24.0;
+      std::vector<int> zp, zq, zd1, zd2;
+      for (int t = 0; t < h.n_tiles; ++t) {
+        const int sa = h.tile_sa[t], sb = h.tile_sb[t];
+        for (int r = 0; r < SLOT; ++r)
+          for (int c = (sa == sb ? r : 0); c < SLOT; ++c) {
+            const int pp = sa * SLOT + r, qq = sb * SLOT + c;
+            if (h.col_lv[pp] < 0 || h.col_lv[qq] < 0) continue;  // padding columns are zero: their moments stay 0
+            zp.push_back(pp); zq.push_back(qq);
+            zd1.push_back(t * TILE + r * SLOT + c);
+            zd2.push_back(sa == sb && r != c ? t * TILE + c * SLOT + r : -1);
+          }
+      }
+      const double z_bytes = (double)I8_DIGITS * zp.size() * d->Npad;
+      if (!zp.empty() && z_bytes <= z_budget_gb * 1e9 && (int64_t)I8_DIGITS * (int64_t)zp.size() < ((int64_t)1 << 31)) {
+        const int nz = (int)zp.size();
+        int *zp_dev = nullptr, *zq_dev = nullptr;
+        double* zqscale = nullptr;
+        CK(g_pool.alloc((void**)&zp_dev, (size_t)nz * 4));
+        CK(g_pool.alloc((void**)&zq_dev, (size_t)nz * 4));
+        CK(g_pool.alloc((void**)&d->zdst, (size_t)nz * 4));
+        CK(g_pool.alloc((void**)&d->zdst2, (size_t)nz * 4));
+        CK(g_pool.alloc((void**)&zqscale, (size_t)nz * 8));
+        CK(g_pool.alloc((void**)&d->zdscale, (size_t)nz * 8));
+        CK(g_pool.alloc((void**)&d->Z8, (size_t)I8_DIGITS * nz * d->Npad));
+        CK(cudaMemcpyAsync(zp_dev, zp.data(), (size_t)nz * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(zq_dev, zq.data(), (size_t)nz * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d->zdst, zd1.data(), (size_t)nz * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d->zdst2, zd2.data(), (size_t)nz * 4, cudaMemcpyHostToDevice, st));
+        d->timer.begin(ST_UPLOAD, st);
+        zscale_kernel<<<(nz + 127) / 128, 128, 0, st>>>(nz, zp_dev, zq_dev, qscale, d->dscale, zqscale, d->zdscale);
+        d->timer.end(st);
+        d->timer.begin(ST_UPLOAD, st);
+        zdigits_kernel<<<dim3((nz + 31) / 32, (unsigned)((d->Npad + 127) / 128)), 256, 0, st>>>(
+            d->X, N, h.Ppad, d->Npad, nz, zp_dev, zq_dev, zqscale, d->Z8);
+        d->timer.end(st);
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(st));  // (the host vectors above are pageable: copies are done by now)
+        g_pool.release(zp_dev);
+        g_pool.release(zq_dev);
+        g_pool.release(zqscale);
+        d->n_zcols = nz;
+        d->z_model = m;
+        trace("pair-product planes");
+      }
+      g_pool.release(qscale);
     }
     CK(cudaStreamSynchronize(st));
     d->timer.collect();
@@ -1537,6 +1658,10 @@ void plspm_data_destroy(plspm_data* d) {
   if (d->Xh) g_pool.release(d->Xh);
   if (d->inv_sd) g_pool.release(d->inv_sd);
   if (d->D8) g_pool.release(d->D8);
+  if (d->Z8) g_pool.release(d->Z8);
+  if (d->zdscale) g_pool.release(d->zdscale);
+  if (d->zdst) g_pool.release(d->zdst);
+  if (d->zdst2) g_pool.release(d->zdst2);
   if (d->dscale) g_pool.release(d->dscale);
   if (d->blas) blas_release(d->blas_device, d->blas);
   if (d->ws.ptr) g_pool.release(d->ws.ptr);
@@ -1657,7 +1782,7 @@ struct BatchBuffers {
   // numeric non-metric path: per-replicate iteration state
   size_t num_a, num_co, num_cn, num_so, num_sn, num_meta, num_done, num_cpart;
   // tensor-core column sums: int8 multiplicities, int32 digit sums, overflow flag
-  size_t c8, s32, ovf;
+  size_t c8, s32, ovf, zs32;
 };
 static BatchBuffers layout_batch(const plspm_data* d, int64_t nb, const BatchPlan& bp, bool with_counts, bool with_idx,
                                  bool rows_on_device_of_caller, bool single_fit, bool want_scores) {
@@ -1694,6 +1819,7 @@ static BatchBuffers layout_batch(const plspm_data* d, int64_t nb, const BatchPla
   b.c8 = take(i8 ? (size_t)nb * d->Npad : 0);
   b.s32 = take(i8 ? (size_t)nb * I8_DIGITS * h.Ppad * sizeof(int32_t) : 0);
   b.ovf = take(8);
+  b.zs32 = take(i8 && d->Z8 ? (size_t)nb * I8_DIGITS * d->n_zcols * sizeof(int32_t) : 0);
   b.num_cpart = take(numeric ? (size_t)nb * bp.cv_gx * 8 : 0);
   const size_t ldl = (size_t)(nb + 7) / 8 * 8;  // replicate stride of the LV-major score / cross-moment layout
   b.BT = take(fast ? ldl * h.L * FAST_RC * sizeof(__half) : 0);
@@ -1784,14 +1910,43 @@ static int launch_moments(plspm_data* d, int64_t nb, const uint32_t* counts_dev,
   cudaStream_t st = d->stream;
   char* base = (char*)d->ws.ptr;
   auto D = [&](size_t o) { return (double*)(base + o); };
-  if (int rc = launch_stream(d, false, nb, counts_dev, bp.gram, D(bb.G), D(bb.Gpart), nullptr)) return rc;
-  if (d->i8_colsum && counts_dev) {
-    int8_t* c8 = (int8_t*)(base + bb.c8);
-    int32_t* s32 = (int32_t*)(base + bb.s32);
+  const bool i8 = d->i8_colsum && counts_dev;
+  int8_t* c8 = (int8_t*)(base + bb.c8);
+  if (i8) {
     d->timer.begin(ST_COLSUM, st);
     counts8_kernel<<<d->sm_count * 8, 256, 0, st>>>(counts_dev, d->N, d->Npad, nb, c8, (int*)(base + bb.ovf));
     d->timer.end(st);
     CK(cudaGetLastError());
+  }
+  bool gram_done = false;
+  if (i8 && d->Z8 && d->z_model == d->model) {
+    // all Gram tiles of the batch: counts8 [nb x N] x pair-product planes [N x 6 n_zcols], exact int32 sums
+    int32_t* zs = (int32_t*)(base + bb.zs32);
+    const int32_t one = 1, zero = 0;
+    const int gemm_m = I8_DIGITS * d->n_zcols;
+    const int64_t g_stride = (int64_t)h.n_tiles * TILE;
+    CK(cudaMemsetAsync(D(bb.G), 0, (size_t)nb * g_stride * 8, st));
+    gram_done = true;
+    for (int64_t k0 = 0; k0 < d->Npad; k0 += I8_KCHUNK) {
+      const int kc = (int)std::min<int64_t>(I8_KCHUNK, d->Npad - k0);
+      d->timer.begin(ST_GRAM, st);
+      cublasStatus_t cs = cublasGemmEx(d->blas, CUBLAS_OP_T, CUBLAS_OP_N, gemm_m, (int)nb, kc, &one, d->Z8 + k0, CUDA_R_8I,
+                                       (int)d->Npad, c8 + k0, CUDA_R_8I, (int)d->Npad, &zero, zs, CUDA_R_32I, gemm_m,
+                                       CUBLAS_COMPUTE_32I, CUBLAS_GEMM_DEFAULT);
+      d->timer.end(st);
+      if (cs != CUBLAS_STATUS_SUCCESS) { gram_done = false; break; }
+      d->timer.begin(ST_REDUCE, st);
+      zcombine_kernel<<<d->sm_count * 8, 256, 0, st>>>(zs, nb, d->n_zcols, d->zdscale, d->zdst, d->zdst2, k0 > 0 ? 1 : 0,
+                                                      g_stride, D(bb.G));
+      d->timer.end(st);
+      CK(cudaGetLastError());
+    }
+    if (!gram_done) d->z_model = nullptr;  // no int8 GEMM for this shape: fp64 kernel from now on
+  }
+  if (!gram_done)
+    if (int rc = launch_stream(d, false, nb, counts_dev, bp.gram, D(bb.G), D(bb.Gpart), nullptr)) return rc;
+  if (i8) {
+    int32_t* s32 = (int32_t*)(base + bb.s32);
     const int32_t one = 1, zero = 0;
     const int gemm_m = I8_DIGITS * h.Ppad;
     bool ok = true;
@@ -2043,7 +2198,7 @@ int plspm_bootstrap(const plspm_model* m, const plspm_data* dc, int32_t scheme, 
   const bool vote = !h.full && !m->numeric;
   const size_t per_rep = (size_t)N * 4 + ((size_t)h.n_tiles * TILE + (vote ? (size_t)h.n_cross * TILE : 0) +
                                           (m->numeric ? 6 : 2) * h.Ppad + h.ws_doubles + n_out) * 8 +
-                         (idx ? (size_t)N * 4 : 0) + (d->i8_colsum ? (size_t)d->Npad + I8_DIGITS * h.Ppad * 4 : 0) + 64;
+                         (idx ? (size_t)N * 4 : 0) + (d->i8_colsum ? (size_t)d->Npad + I8_DIGITS * ((size_t)h.Ppad + d->n_zcols) * 4 : 0) + 64;
   int64_t nb_max = std::max<int64_t>(1, (int64_t)((size_t)1536 * 1024 * 1024 / per_rep));
   if (getenv("PLSPM_MAX_BATCH")) nb_max = std::max<int64_t>(1, std::min<int64_t>(nb_max, atoll(getenv("PLSPM_MAX_BATCH"))));
   nb_max = std::min<int64_t>(nb_max, rep_count);
