@@ -292,24 +292,34 @@ def run_gpu_arm(args):
     e2e_value = world * reps * e2e_steps / float(e2e_el.item())
 
     if rank == 0:
-        # every kernel that streams X for the batch: the Gram kernel (dominant), the column sums, and the
-        # sign-vote pass (exact fp64 cross moments, or score generation + fp16 GEMMs)
-        stream_stages = ("gram", "cross", "colsum", "scoregen", "conv")
-        gram_ms, gram_n = prof["gram"]
+        # every stage that streams the observations (or their digit planes) for the batch
+        stream_stages = ("gram", "gram_i8", "cross", "colsum", "scoregen", "conv")
+        kernel_names = {
+            "gram": "gram_kernel<false> (fp64 weighted Gram tiles)",
+            "gram_i8": "cuBLAS int8 GEMM counts x pair-product digit planes (exact int32 sums) + zcombine_kernel",
+            "cross": "cuBLAS fp16 GEMM of the sign vote" if prof.get("scoregen", (0, 0))[1] else "gram_kernel<true>",
+            "colsum": "counts8_kernel + cuBLAS int8 GEMM + digits_combine_kernel", "scoregen": "scoregen_kernel",
+            "conv": "conv_kernel", "solve": "solve_kernel", "counts": "counts_kernel", "reduce": "reduce_chunks_kernel"}
         stream_ms = sum(prof.get(k, (0.0, 0))[0] for k in stream_stages)
+        top = max((k for k in prof if prof[k][1]), key=lambda k: prof[k][0])
+        top_ms, top_n = prof[top]
         alg_bytes = float((iters_cat + 2.0).sum()) * N * P * 8.0           # all fits of the timed region, this rank
         peak, peak_src = hbm_peak()
         achieved = alg_bytes / 1e9 / (stream_ms / 1e3) if stream_ms > 0 else 0.0
-        # fp64 FMAs of the Gram kernel (8x8 tiles; ~63.2 % of the rows have non-zero multiplicity)
-        fp64_tflops = 2.0 * model.n_tiles * 64 * 0.632 * N * reps * args.steps / (gram_ms / 1e3) / 1e12 if gram_ms > 0 else 0.0
+        gram_ms, gram_n = prof.get("gram", (0.0, 0))
+        i8_ms, i8_n = prof.get("gram_i8", (0.0, 0))
+        # fp64 FMAs of the fp64 Gram kernel (8x8 tiles; ~63.2 % of the rows have non-zero multiplicity)
+        fp64_tflops = 2.0 * model.n_tiles * 64 * 0.632 * N * reps * args.steps / (gram_ms / 1e3) / 1e12 if gram_ms > 0 else None
+        # int8 multiply-adds of the Gram GEMM: 6 digit planes x pair columns x replicates x rows
+        i8_tops = 2.0 * 6 * model.n_pair_columns * reps * N * args.steps / (i8_ms / 1e3) / 1e12 if i8_ms > 0 else None
         vote = "n/a (non-metric estimator: no sign vote)" if w.get("numeric") else "n/a (full tile set)" if model.full_tiles else (
             "exact fp64 cross moments" if prof.get("scoregen", (0, 0))[1] == 0 else
             "fp16 tensor-core GEMM with error bound, %d replicates redone exactly" % engine.redo_count())
         traffic = None
-        tp = os.path.join(ROOT, "profiles", "gram_traffic.json")
+        tp = os.path.join(ROOT, "profiles", "kernel_traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get(args.workload)
+                traffic = json.load(open(tp)).get(args.workload, {}).get(top)
             except Exception:
                 traffic = None
         launches = int(sum(v[1] for v in prof.values()))
@@ -324,19 +334,22 @@ def run_gpu_arm(args):
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic,
-                         "kernel": "gram_kernel<false>", "kernel_share_of_streaming_time": gram_ms / stream_ms,
-                         "streaming_stages": list(stream_stages),
+                         "kernel": kernel_names.get(top, top), "kernel_stage": top,
+                         "kernel_share_of_step": top_ms / max(sum(v[0] for v in prof.values()), 1e-9),
+                         "kernel_launch_ms": top_ms / max(top_n, 1), "kernel_launches": top_n,
+                         "streaming_stages": [k for k in stream_stages if prof.get(k, (0, 0))[1]],
                          "tile_set": "full" if model.full_tiles else "sparse", "sign_vote": vote,
-                         "fp64_tflops_est": fp64_tflops, "fp64_peak_measured_tflops": 36.9,
+                         "gram_route": "int8 digit-plane GEMM (tensor cores)" if i8_n else "fp64 kernel",
+                         "gram_int8_tops": i8_tops, "gram_fp64_tflops": fp64_tflops, "fp64_peak_measured_tflops": 36.9,
                          "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg_bytes / max(gram_n, 1),
-                         "launch_ms": stream_ms / max(gram_n, 1), "gram_launch_ms": gram_ms / max(gram_n, 1),
-                         "launches": gram_n,
+                         "algorithmic_bytes_per_step": alg_bytes / args.steps,
+                         "streaming_ms_per_step": stream_ms / args.steps,
                          "note": "achieved = algorithmic bytes (n_iter+2)*N*P*8 per fit (SURVEY 8d) over the CUDA-event "
-                                 "time of ALL X-streaming kernels of the batch. The engine reads X once per wave of "
-                                 "replicates per pass instead of (n_iter+2) times per replicate (covariance-domain "
-                                 "solver), so frac exceeds 1; the dominant Gram kernel is bound by the fp64 FMA pipe "
-                                 "(fp64_tflops_est vs the 36.9 TFLOP/s measured by tools/fp64_peak.cu), not by HBM"},
+                                 "time of ALL stages that stream the observations for the batch. The engine never "
+                                 "re-reads X per iteration or per replicate: the iteration runs on second moments, and "
+                                 "the moments of a whole batch are one integer GEMM over digit planes of X (read once per "
+                                 "batch), so frac exceeds 1 by construction; traffic (ncu dram bytes of the dominant "
+                                 "kernel, per launch) is the honest HBM figure"},
             "stages_ms_per_step": {k: v[0] / args.steps for k, v in prof.items() if v[1]},
             "mean_iterations": float(iters_cat.mean()), "failed_replicates": bad,
         }

@@ -51,7 +51,8 @@ int plspm_model_create(int32_t L, const int32_t* block_sizes, const int8_t* mode
                        int32_t scaled, int32_t tile_policy, plspm_model** out);
 void plspm_model_destroy(plspm_model* m);
 /* info[16]: 0 L, 1 P, 2 padded P, 3 tiles, 4 tile groups, 5 LV pairs, 6 effect rows, 7 doubles per
- * bootstrap row (2P + L + 2*effects), 8 full tile set, 9 scaled, 10 cross-moment tiles, 11 numeric */
+ * bootstrap row (2P + L + 2*effects), 8 full tile set, 9 scaled, 10 cross-moment tiles, 11 numeric,
+ * 12 pair-product columns of the tile set (the int8 Gram GEMM has 6x as many rows) */
 int plspm_model_query(const plspm_model* m, int32_t* info);
 /* on != 0 selects the reference's non-metric estimator for data whose manifest variables all carry
  * Scale.NUM or Scale.RAW (config.py:306-319 treatment, weights.py:73-133 `_NonmetricWeights`, mode.py

@@ -54,7 +54,7 @@ static int fail(int code, const std::string& msg) {
                   std::string(#expr) + ": " + cudaGetErrorString(e_));                             \
   } while (0)
 
-enum { ST_COUNTS = 0, ST_GRAM = 1, ST_REDUCE = 2, ST_SOLVE = 3, ST_SCORES = 4, ST_UPLOAD = 5, ST_COLSUM = 6, ST_CROSS = 7, ST_SCOREGEN = 8, ST_CONV = 9, ST_N = 12 };
+enum { ST_COUNTS = 0, ST_GRAM = 1, ST_REDUCE = 2, ST_SOLVE = 3, ST_SCORES = 4, ST_UPLOAD = 5, ST_COLSUM = 6, ST_CROSS = 7, ST_SCOREGEN = 8, ST_CONV = 9, ST_GRAM_I8 = 10, ST_N = 12 };
 struct Profile {
   std::mutex mu;
   double ms[ST_N] = {0};
@@ -1425,6 +1425,12 @@ int plspm_model_query(const plspm_model* m, int32_t* info) {
   const HostModel& h = m->h;
   info[0] = h.L; info[1] = h.P; info[2] = h.Ppad; info[3] = h.n_tiles; info[4] = h.n_tg; info[5] = h.n_pairs;
   info[6] = h.n_eff; info[7] = h.n_out(); info[8] = h.full; info[9] = h.scaled; info[10] = h.n_cross; info[11] = m->numeric ? 1 : 0;
+  int nz = 0;  // pair-product columns of the tile set (rows / 6 of the int8 Gram GEMM)
+  for (int t = 0; t < h.n_tiles; ++t)
+    for (int r = 0; r < SLOT; ++r)
+      for (int c = (h.tile_sa[t] == h.tile_sb[t] ? r : 0); c < SLOT; ++c)
+        nz += (h.col_lv[h.tile_sa[t] * SLOT + r] >= 0 && h.col_lv[h.tile_sb[t] * SLOT + c] >= 0) ? 1 : 0;
+  info[12] = nz;
   return PLSPM_OK;
 }
 
@@ -1929,13 +1935,13 @@ static int launch_moments(plspm_data* d, int64_t nb, const uint32_t* counts_dev,
     gram_done = true;
     for (int64_t k0 = 0; k0 < d->Npad; k0 += I8_KCHUNK) {
       const int kc = (int)std::min<int64_t>(I8_KCHUNK, d->Npad - k0);
-      d->timer.begin(ST_GRAM, st);
+      d->timer.begin(ST_GRAM_I8, st);
       cublasStatus_t cs = cublasGemmEx(d->blas, CUBLAS_OP_T, CUBLAS_OP_N, gemm_m, (int)nb, kc, &one, d->Z8 + k0, CUDA_R_8I,
                                        (int)d->Npad, c8 + k0, CUDA_R_8I, (int)d->Npad, &zero, zs, CUDA_R_32I, gemm_m,
                                        CUBLAS_COMPUTE_32I, CUBLAS_GEMM_DEFAULT);
       d->timer.end(st);
       if (cs != CUBLAS_STATUS_SUCCESS) { gram_done = false; break; }
-      d->timer.begin(ST_REDUCE, st);
+      d->timer.begin(ST_GRAM_I8, st);
       zcombine_kernel<<<d->sm_count * 8, 256, 0, st>>>(zs, nb, d->n_zcols, d->zdscale, d->zdst, d->zdst2, k0 > 0 ? 1 : 0,
                                                       g_stride, D(bb.G));
       d->timer.end(st);

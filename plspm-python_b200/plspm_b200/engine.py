@@ -119,6 +119,7 @@ class Model:
         self.P, self.Ppad, self.n_tiles, self.n_tile_groups = int(info[1]), int(info[2]), int(info[3]), int(info[4])
         self.n_effects, self.n_out, self.full_tiles = int(info[6]), int(info[7]), bool(info[8])
         self.n_cross_tiles = int(info[10])
+        self.n_pair_columns = int(info[12])
         ef = np.zeros(max(self.n_effects, 1), dtype=np.int32)
         et = np.zeros(max(self.n_effects, 1), dtype=np.int32)
         _check(load().plspm_model_effects(self._h, _ptr(ef, _c_i32p), _ptr(et, _c_i32p)))
@@ -238,7 +239,7 @@ def resample_indices(seed: int, replicate: int, N: int) -> np.ndarray:
     return out
 
 
-STAGES = ("counts", "gram", "reduce", "solve", "scores", "upload", "colsum", "cross", "scoregen", "conv")
+STAGES = ("counts", "gram", "reduce", "solve", "scores", "upload", "colsum", "cross", "scoregen", "conv", "gram_i8")
 
 
 def profile_reset():

@@ -387,3 +387,27 @@ def test_tensor_core_column_sums_match_fp64_and_overflow_falls_back(eng):
     data2 = eng.Data(model, X)
     rows3, _, _ = eng.bootstrap(model, data2, "centroid", 0, 2, idx=idx[:2])
     np.testing.assert_allclose(rows3, rows[:2], rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.parametrize("mode,scheme", [(0, "centroid"), (1, "path")])
+def test_tensor_core_gram_route_is_fp64_accurate(eng, mode, scheme):
+    """N >= 4096: the Gram tiles of a bootstrap batch come from the int8 digit-plane GEMM (exact integer sums
+    of x~_p x~_q rounded to 2^-40 of the column bound).  Must be as good as fp64 accumulation: 1e-10 vs the
+    oracle (whose own fp64 rounding is ~1e-12), ragged blocks (padding columns) included."""
+    N, L = 9000, 6
+    sizes = [5, 8, 3, 11, 8, 2]
+    rng = np.random.default_rng(17)
+    Xs, path = make_synthetic(N, L, max(sizes), 23)
+    X = np.column_stack([Xs[:, l * max(sizes):l * max(sizes) + k] for l, k in enumerate(sizes)])
+    X = X * rng.uniform(0.01, 300.0, size=X.shape[1])[None, :] + rng.normal(0, 50, size=X.shape[1])[None, :]
+    model = eng.Model(sizes, [mode] * L, path, True)
+    data = eng.Data(model, X)
+    idx = rng.integers(0, N, size=(6, N)).astype(np.int32)
+    eng.profile_reset()
+    rows, status, iters = eng.bootstrap(model, data, scheme, 0, 6, idx=idx)
+    prof = eng.profile_get()
+    assert prof["gram_i8"][1] > 0 and prof["gram"][1] == 0, prof
+    for b in range(6):
+        ref, it, st = orc.replicate_row(X, idx[b], sizes, [mode] * L, path, scheme, True)
+        assert status[b] == st == 0 and iters[b] == it
+        np.testing.assert_allclose(rows[b], ref, rtol=1e-10, atol=1e-12)
