@@ -219,7 +219,10 @@ struct plspm_data {
   int64_t Npad = 0;
   bool i8_colsum = false;
   // ... and of the pair products z_i = x~_ip x~_iq of the model's Gram tile set (see zdigits_kernel)
-  int8_t* Z8 = nullptr;      // [I8_DIGITS * n_zcols][Npad]
+  int8_t* Z8 = nullptr;      // [I8_DIGITS * n_zcols][Npad] resident planes, or null: generated per row chunk per batch
+  int *zp = nullptr, *zq = nullptr;       // [n_zcols] the two columns of every pair
+  double* zqscale = nullptr;              // [n_zcols] 2^(40 - e_p - e_q)
+  int64_t z_chunk_rows = 0;               // streaming mode: rows per generated chunk
   double* zdscale = nullptr; // [n_zcols]
   int *zdst = nullptr, *zdst2 = nullptr;  // [n_zcols] offsets into a replicate's tile array (mirror or -1)
   int n_zcols = 0;
@@ -502,22 +505,23 @@ __global__ void zscale_kernel(int n_zcols, const int* __restrict__ zp, const int
   zqscale[c] = qscale[zp[c]] * qscale[zq[c]] * 9.094947017729282e-13;  // 2^-40 (all factors are powers of two)
   zdscale[c] = dscale[zp[c]] * dscale[zq[c]] * 1099511627776.0;         // 2^40
 }
-__global__ void __launch_bounds__(256) zdigits_kernel(const double* __restrict__ X, int64_t N, int Ppad, int64_t Npad,
-                                                      int n_zcols, const int* __restrict__ zp,
+// rows [row0, row0 + ld) of the planes go to Z8[(k * n_zcols + col) * ld + (i - row0)]  (ld a multiple of 16)
+__global__ void __launch_bounds__(256) zdigits_kernel(const double* __restrict__ X, int64_t N, int Ppad, int64_t row0,
+                                                      int64_t ld, int n_zcols, const int* __restrict__ zp,
                                                       const int* __restrict__ zq, const double* __restrict__ zqscale,
                                                       int8_t* __restrict__ Z8) {
   __shared__ __align__(4) int8_t sm[I8_DIGITS][32][132];
   const int c0 = blockIdx.x * 32;
-  const int64_t i0 = (int64_t)blockIdx.y * 128;
+  const int64_t i0 = (int64_t)blockIdx.y * 128;  // local row
   const int cl = threadIdx.x & 31;
   const int col = c0 + cl;
   const bool col_ok = col < n_zcols;
   const int p = col_ok ? zp[col] : 0, q = col_ok ? zq[col] : 0;
   const double sc = col_ok ? zqscale[col] : 0.0;
   for (int il = threadIdx.x >> 5; il < 128; il += 8) {
-    const int64_t i = i0 + il;
+    const int64_t i = row0 + i0 + il;
     long long v = 0;
-    if (i < N && col_ok) v = __double2ll_rn(X[i * Ppad + p] * X[i * Ppad + q] * sc);
+    if (i0 + il < ld && i < N && col_ok) v = __double2ll_rn(X[i * Ppad + p] * X[i * Ppad + q] * sc);
 #pragma unroll
     for (int k = 0; k < I8_DIGITS; ++k) {
       const long long dgt = ((v + 64) & 127) - 64;
@@ -529,8 +533,8 @@ __global__ void __launch_bounds__(256) zdigits_kernel(const double* __restrict__
   for (int e = threadIdx.x; e < I8_DIGITS * 32 * 32; e += 256) {
     const int w = e & 31, row = e >> 5, k = row >> 5, c = row & 31;
     const int64_t i = i0 + 4 * w;
-    if (c0 + c < n_zcols && i < Npad)
-      *reinterpret_cast<uint32_t*>(Z8 + ((int64_t)k * n_zcols + c0 + c) * Npad + i) = *reinterpret_cast<const uint32_t*>(&sm[k][c][4 * w]);
+    if (c0 + c < n_zcols && i < ld)
+      *reinterpret_cast<uint32_t*>(Z8 + ((int64_t)k * n_zcols + c0 + c) * ld + i) = *reinterpret_cast<const uint32_t*>(&sm[k][c][4 * w]);
   }
 }
 // G[b][zdst[c]] (+)= zdscale_c * sum_k 128^k S[b][k*n_zcols + c]   (and the mirrored entry of diagonal tiles)
@@ -1604,33 +1608,36 @@ int plspm_data_create(const plspm_model* m, const double* X, int64_t N, int64_t 
           }
       }
       const double z_bytes = (double)I8_DIGITS * zp.size() * d->Npad;
-      if (!zp.empty() && z_bytes <= z_budget_gb * 1e9 && (int64_t)I8_DIGITS * (int64_t)zp.size() < ((int64_t)1 << 31)) {
+      static const double z_chunk_gb = getenv("PLSPM_I8_CHUNK_GB") ? atof(getenv("PLSPM_I8_CHUNK_GB")) : 12.0;
+      if (!zp.empty() && z_budget_gb > 0 && (int64_t)I8_DIGITS * (int64_t)zp.size() < ((int64_t)1 << 31)) {
         const int nz = (int)zp.size();
-        int *zp_dev = nullptr, *zq_dev = nullptr;
-        double* zqscale = nullptr;
-        CK(g_pool.alloc((void**)&zp_dev, (size_t)nz * 4));
-        CK(g_pool.alloc((void**)&zq_dev, (size_t)nz * 4));
+        CK(g_pool.alloc((void**)&d->zp, (size_t)nz * 4));
+        CK(g_pool.alloc((void**)&d->zq, (size_t)nz * 4));
         CK(g_pool.alloc((void**)&d->zdst, (size_t)nz * 4));
         CK(g_pool.alloc((void**)&d->zdst2, (size_t)nz * 4));
-        CK(g_pool.alloc((void**)&zqscale, (size_t)nz * 8));
+        CK(g_pool.alloc((void**)&d->zqscale, (size_t)nz * 8));
         CK(g_pool.alloc((void**)&d->zdscale, (size_t)nz * 8));
-        CK(g_pool.alloc((void**)&d->Z8, (size_t)I8_DIGITS * nz * d->Npad));
-        CK(cudaMemcpyAsync(zp_dev, zp.data(), (size_t)nz * 4, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(zq_dev, zq.data(), (size_t)nz * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d->zp, zp.data(), (size_t)nz * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d->zq, zq.data(), (size_t)nz * 4, cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(d->zdst, zd1.data(), (size_t)nz * 4, cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(d->zdst2, zd2.data(), (size_t)nz * 4, cudaMemcpyHostToDevice, st));
         d->timer.begin(ST_UPLOAD, st);
-        zscale_kernel<<<(nz + 127) / 128, 128, 0, st>>>(nz, zp_dev, zq_dev, qscale, d->dscale, zqscale, d->zdscale);
-        d->timer.end(st);
-        d->timer.begin(ST_UPLOAD, st);
-        zdigits_kernel<<<dim3((nz + 31) / 32, (unsigned)((d->Npad + 127) / 128)), 256, 0, st>>>(
-            d->X, N, h.Ppad, d->Npad, nz, zp_dev, zq_dev, zqscale, d->Z8);
+        zscale_kernel<<<(nz + 127) / 128, 128, 0, st>>>(nz, d->zp, d->zq, qscale, d->dscale, d->zqscale, d->zdscale);
         d->timer.end(st);
         CK(cudaGetLastError());
+        if (z_bytes <= z_budget_gb * 1e9) {  // resident planes: generated once
+          CK(g_pool.alloc((void**)&d->Z8, (size_t)I8_DIGITS * nz * d->Npad));
+          d->timer.begin(ST_UPLOAD, st);
+          zdigits_kernel<<<dim3((nz + 31) / 32, (unsigned)((d->Npad + 127) / 128)), 256, 0, st>>>(
+              d->X, N, h.Ppad, 0, d->Npad, nz, d->zp, d->zq, d->zqscale, d->Z8);
+          d->timer.end(st);
+          CK(cudaGetLastError());
+        } else {  // too large to keep: a chunk of rows is generated per batch, right before its GEMM
+          int64_t rows = (int64_t)(z_chunk_gb * 1e9 / ((double)I8_DIGITS * nz));
+          rows = std::min<int64_t>(rows / 128 * 128, I8_KCHUNK);
+          d->z_chunk_rows = std::max<int64_t>(rows, 4096);
+        }
         CK(cudaStreamSynchronize(st));  // (the host vectors above are pageable: copies are done by now)
-        g_pool.release(zp_dev);
-        g_pool.release(zq_dev);
-        g_pool.release(zqscale);
         d->n_zcols = nz;
         d->z_model = m;
         trace("pair-product planes");
@@ -1666,6 +1673,9 @@ void plspm_data_destroy(plspm_data* d) {
   if (d->D8) g_pool.release(d->D8);
   if (d->Z8) g_pool.release(d->Z8);
   if (d->zdscale) g_pool.release(d->zdscale);
+  if (d->zp) g_pool.release(d->zp);
+  if (d->zq) g_pool.release(d->zq);
+  if (d->zqscale) g_pool.release(d->zqscale);
   if (d->zdst) g_pool.release(d->zdst);
   if (d->zdst2) g_pool.release(d->zdst2);
   if (d->dscale) g_pool.release(d->dscale);
@@ -1788,7 +1798,7 @@ struct BatchBuffers {
   // numeric non-metric path: per-replicate iteration state
   size_t num_a, num_co, num_cn, num_so, num_sn, num_meta, num_done, num_cpart;
   // tensor-core column sums: int8 multiplicities, int32 digit sums, overflow flag
-  size_t c8, s32, ovf, zs32;
+  size_t c8, s32, ovf, zs32, zchunk;
 };
 static BatchBuffers layout_batch(const plspm_data* d, int64_t nb, const BatchPlan& bp, bool with_counts, bool with_idx,
                                  bool rows_on_device_of_caller, bool single_fit, bool want_scores) {
@@ -1825,7 +1835,8 @@ static BatchBuffers layout_batch(const plspm_data* d, int64_t nb, const BatchPla
   b.c8 = take(i8 ? (size_t)nb * d->Npad : 0);
   b.s32 = take(i8 ? (size_t)nb * I8_DIGITS * h.Ppad * sizeof(int32_t) : 0);
   b.ovf = take(8);
-  b.zs32 = take(i8 && d->Z8 ? (size_t)nb * I8_DIGITS * d->n_zcols * sizeof(int32_t) : 0);
+  b.zs32 = take(i8 && d->n_zcols ? (size_t)nb * I8_DIGITS * d->n_zcols * sizeof(int32_t) : 0);
+  b.zchunk = take(i8 && d->n_zcols && !d->Z8 ? (size_t)I8_DIGITS * d->n_zcols * d->z_chunk_rows : 0);
   b.num_cpart = take(numeric ? (size_t)nb * bp.cv_gx * 8 : 0);
   const size_t ldl = (size_t)(nb + 7) / 8 * 8;  // replicate stride of the LV-major score / cross-moment layout
   b.BT = take(fast ? ldl * h.L * FAST_RC * sizeof(__half) : 0);
@@ -1925,19 +1936,29 @@ static int launch_moments(plspm_data* d, int64_t nb, const uint32_t* counts_dev,
     CK(cudaGetLastError());
   }
   bool gram_done = false;
-  if (i8 && d->Z8 && d->z_model == d->model) {
+  if (i8 && d->n_zcols && d->z_model == d->model) {
     // all Gram tiles of the batch: counts8 [nb x N] x pair-product planes [N x 6 n_zcols], exact int32 sums
     int32_t* zs = (int32_t*)(base + bb.zs32);
     const int32_t one = 1, zero = 0;
     const int gemm_m = I8_DIGITS * d->n_zcols;
     const int64_t g_stride = (int64_t)h.n_tiles * TILE;
+    const int64_t step = d->Z8 ? I8_KCHUNK : d->z_chunk_rows;
     CK(cudaMemsetAsync(D(bb.G), 0, (size_t)nb * g_stride * 8, st));
     gram_done = true;
-    for (int64_t k0 = 0; k0 < d->Npad; k0 += I8_KCHUNK) {
-      const int kc = (int)std::min<int64_t>(I8_KCHUNK, d->Npad - k0);
+    for (int64_t k0 = 0; k0 < d->Npad; k0 += step) {
+      const int kc = (int)std::min<int64_t>(step, d->Npad - k0);
+      const int8_t* planes = d->Z8 ? d->Z8 + k0 : (const int8_t*)(base + bb.zchunk);
+      const int64_t ld = d->Z8 ? d->Npad : kc;
+      if (!d->Z8) {
+        d->timer.begin(ST_GRAM_I8, st);
+        zdigits_kernel<<<dim3((d->n_zcols + 31) / 32, (unsigned)((kc + 127) / 128)), 256, 0, st>>>(
+            d->X, d->N, h.Ppad, k0, kc, d->n_zcols, d->zp, d->zq, d->zqscale, (int8_t*)(base + bb.zchunk));
+        d->timer.end(st);
+        CK(cudaGetLastError());
+      }
       d->timer.begin(ST_GRAM_I8, st);
-      cublasStatus_t cs = cublasGemmEx(d->blas, CUBLAS_OP_T, CUBLAS_OP_N, gemm_m, (int)nb, kc, &one, d->Z8 + k0, CUDA_R_8I,
-                                       (int)d->Npad, c8 + k0, CUDA_R_8I, (int)d->Npad, &zero, zs, CUDA_R_32I, gemm_m,
+      cublasStatus_t cs = cublasGemmEx(d->blas, CUBLAS_OP_T, CUBLAS_OP_N, gemm_m, (int)nb, kc, &one, planes, CUDA_R_8I,
+                                       (int)ld, c8 + k0, CUDA_R_8I, (int)d->Npad, &zero, zs, CUDA_R_32I, gemm_m,
                                        CUBLAS_COMPUTE_32I, CUBLAS_GEMM_DEFAULT);
       d->timer.end(st);
       if (cs != CUBLAS_STATUS_SUCCESS) { gram_done = false; break; }
@@ -2205,7 +2226,9 @@ int plspm_bootstrap(const plspm_model* m, const plspm_data* dc, int32_t scheme, 
   const size_t per_rep = (size_t)N * 4 + ((size_t)h.n_tiles * TILE + (vote ? (size_t)h.n_cross * TILE : 0) +
                                           (m->numeric ? 6 : 2) * h.Ppad + h.ws_doubles + n_out) * 8 +
                          (idx ? (size_t)N * 4 : 0) + (d->i8_colsum ? (size_t)d->Npad + I8_DIGITS * ((size_t)h.Ppad + d->n_zcols) * 4 : 0) + 64;
-  int64_t nb_max = std::max<int64_t>(1, (int64_t)((size_t)1536 * 1024 * 1024 / per_rep));
+  // the planes of a chunk are regenerated for every batch in streaming mode: large batches amortise that
+  const size_t ws_budget = d->n_zcols && !d->Z8 ? (size_t)8 << 30 : (size_t)1536 << 20;
+  int64_t nb_max = std::max<int64_t>(1, (int64_t)(ws_budget / per_rep));
   if (getenv("PLSPM_MAX_BATCH")) nb_max = std::max<int64_t>(1, std::min<int64_t>(nb_max, atoll(getenv("PLSPM_MAX_BATCH"))));
   nb_max = std::min<int64_t>(nb_max, rep_count);
   const int64_t wave = (int64_t)d->sm_count * GRAM_WARPS;  // warp items per wave

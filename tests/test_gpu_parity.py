@@ -1,6 +1,8 @@
 """GPU parity tests: the CUDA path (through the C ABI, ctypes) vs the CPU oracle and the golden fixtures.
 Tolerance: 1e-6 relative on outer weights, LV scores and path coefficients (BASELINE.json north_star);
 iteration counts must be identical."""
+import os
+
 import numpy as np
 import pytest
 
@@ -9,6 +11,7 @@ from plspm_b200.synth import make_synthetic
 
 pytestmark = pytest.mark.gpu
 REL = 1e-6
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.fixture(scope="module")
@@ -411,3 +414,41 @@ def test_tensor_core_gram_route_is_fp64_accurate(eng, mode, scheme):
         ref, it, st = orc.replicate_row(X, idx[b], sizes, [mode] * L, path, scheme, True)
         assert status[b] == st == 0 and iters[b] == it
         np.testing.assert_allclose(rows[b], ref, rtol=1e-10, atol=1e-12)
+
+
+def test_streaming_pair_planes_and_fp64_route_agree(tmp_path):
+    """Models whose pair-product planes exceed the memory budget generate them per row chunk per batch; with
+    PLSPM_I8_GRAM_GB=0 the fp64 Gram kernel is used.  Both must reproduce the resident-plane result (the switches
+    are read once per process, hence the subprocesses)."""
+    import subprocess
+    import sys
+    script = tmp_path / "run.py"
+    script.write_text(
+        "import sys, numpy as np\n"
+        "sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "from plspm_b200 import engine\n"
+        "from plspm_b200.synth import make_synthetic\n"
+        "X, path = make_synthetic(21000, 5, 6, 9)\n"
+        "model = engine.Model([6] * 5, [0] * 5, path, True)\n"
+        "data = engine.Data(model, X)\n"
+        "engine.profile_reset()\n"
+        "rows, status, iters = engine.bootstrap(model, data, 'centroid', 0, 12, seed=5)\n"
+        "prof = engine.profile_get()\n"
+        "np.save(sys.argv[1], rows)\n"
+        "print('gram', prof['gram'][1], 'gram_i8', prof['gram_i8'][1], int((status == 0).sum()))\n"
+        % (os.path.join(ROOT, "plspm-python_b200"), ROOT))
+    outs = {}
+    for tag, env in (("resident", {}), ("stream", {"PLSPM_I8_GRAM_GB": "0.000001", "PLSPM_I8_CHUNK_GB": "0.000001"}),
+                     ("fp64", {"PLSPM_I8_GRAM_GB": "0"})):
+        out = tmp_path / (tag + ".npy")
+        r = subprocess.run([sys.executable, str(script), str(out)], env={**os.environ, **env}, capture_output=True,
+                           text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        words = r.stdout.split()
+        outs[tag] = (np.load(out), int(words[1]), int(words[3]), int(words[4]))
+    assert outs["resident"][1] == 0 and outs["resident"][2] == 2          # one GEMM + one combine
+    assert outs["stream"][1] == 0 and outs["stream"][2] == 3 * 6            # 6 chunks of 4096 rows: generate, GEMM, combine
+    assert outs["fp64"][1] >= 1 and outs["fp64"][2] == 0
+    assert outs["resident"][3] == outs["stream"][3] == outs["fp64"][3] == 12
+    np.testing.assert_allclose(outs["stream"][0], outs["resident"][0], rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(outs["fp64"][0], outs["resident"][0], rtol=1e-10, atol=1e-12)
