@@ -209,6 +209,7 @@ struct plspm_data {
   double* mu = nullptr;  // [Ppad]
   // low-precision copy for the tensor-core sign vote (sparse tile sets): xh = x~ / sd (fp16)
   __half* Xh = nullptr;      // [N][Ppad]
+  float* Xf = nullptr;       // [N][Ppad] fp32 copy of x~ (score generation of the sign vote)
   double* inv_sd = nullptr;  // [Ppad]
   cublasHandle_t blas = nullptr;
   int blas_device = 0;
@@ -560,15 +561,22 @@ __global__ void zcombine_kernel(const int32_t* __restrict__ S, int64_t nrep, int
 
 // Scores for the tensor-core sign vote:
 //   B[i - i0][l*ldl + b] = fp16( c_bi * (x~_i . wf_b,l - sh_b,l) )      rows [i0, i0 + rc) of one chunk,
-// ldl = replicates rounded up to 8: a thread's SG_RPT = 4 consecutive replicates are one 8-byte store.
+// ldl = replicates rounded up to 8: a thread's SG_RPT = 8 consecutive replicates are one 16-byte store.
+// Only the SIGN of the resulting cross moments is used, and only where it exceeds a rigorous error bound
+// (solver_core.h, phase 3), so the scores are computed in fp32 from an fp32 copy of x~: half the shared-
+// memory traffic and staging of the fp64 version, twice the replicates per staged row tile.  The bound
+// carries the fp32 term (k+4) 2^-24 sum_k |x_k w_k|.
 // A group of nsl_pad adjacent lanes (power of two >= slots of the widest block) serves one (replicate
 // lane, latent variable) pair: lane `sub` of the group owns slot `sub` of the block, keeps the weights
 // of that slot for SG_RPT replicates in registers, walks the rows of the CTA's tiles reading the slot
-// (8 doubles) once for all of them, and the partial dot products are combined with a shuffle butterfly.
-// t is computed in fp64; only the product with the multiplicity is rounded to fp16.
-constexpr int SG_MAX_ROWS = 32, SG_RPT = 4, SG_THREADS = 256;
+// (8 floats) once for all of them, and the partial dot products are combined with a shuffle butterfly.
+constexpr int SG_MAX_ROWS = 64, SG_RPT = 8, SG_THREADS = 256;
+__global__ void make_float_kernel(const double* __restrict__ X, int64_t total, float* __restrict__ out) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x)
+    out[e] = (float)X[e];
+}
 template <bool SINGLE_SLOT>  // every block fits one slot (nsl_pad == 1): no shuffle butterfly, idle lanes skip the rows
-__global__ void __launch_bounds__(SG_THREADS) scoregen_kernel(const double* __restrict__ X,
+__global__ void __launch_bounds__(SG_THREADS) scoregen_kernel(const float* __restrict__ X,
                                                               const uint32_t* __restrict__ counts,
                                                               const double* __restrict__ wf,
                                                               const double* __restrict__ sh, int64_t N, int Ppad, int L,
@@ -576,15 +584,15 @@ __global__ void __launch_bounds__(SG_THREADS) scoregen_kernel(const double* __re
                                                               const int* __restrict__ lv_k, int nsl_pad, int SG_ROWS,
                                                               int64_t nrep, int64_t ldl, int64_t i0, int rc,
                                                               __half* __restrict__ B) {
-  extern __shared__ __align__(16) double sg_smem[];
-  double* xs = sg_smem;                                     // [SG_ROWS][Ppad]  (SG_ROWS <= 32 rows per tile)
-  double* cs = xs + (size_t)SG_ROWS * Ppad;                 // [SG_ROWS][reps_per_cta] multiplicities as fp64
+  extern __shared__ __align__(16) float sg_smem[];
+  float* xs = sg_smem;                                      // [SG_ROWS][Ppad]
+  float* cs = xs + (size_t)SG_ROWS * Ppad;                  // [SG_ROWS][reps_per_cta] multiplicities
   int nbl = SG_THREADS / (L * nsl_pad);                     // replicate lanes per CTA (same rule on the host)
   if (SINGLE_SLOT && nbl >= 4) nbl = (SG_THREADS / 32 / ((L + 7) >> 3)) * 4;
   const int reps_per_cta = nbl * SG_RPT;
   const int64_t rep0 = (int64_t)blockIdx.y * reps_per_cta;
   // Thread -> (replicate lane bl, latent variable l, slot sub).  Single-slot blocks: a warp is 8 LVs x 4
-  // replicate lanes, so the 32 LDS.128 of a row touch only 8 distinct slots (2 wavefronts instead of 4).
+  // replicate lanes, so the 32 LDS.128 of a row touch only 8 distinct (adjacent) slots.
   int sub, bl, l;
   bool active;
   if (SINGLE_SLOT && nbl >= 4) {
@@ -604,78 +612,67 @@ __global__ void __launch_bounds__(SG_THREADS) scoregen_kernel(const double* __re
   }
   const bool has_slot = sub < ((lv_k[l] + SLOT - 1) >> 3);
   const int slot = (lv_off[l] >> 3) + (has_slot ? sub : 0);
-  const int rot = (slot >> 1) & 3;  // rotated chunk order: the 64-byte slot stride would alias shared-memory banks
-  double w[SG_RPT][8], shv[SG_RPT];
-  // the thread's SG_RPT replicates are adjacent in B (LV-major layout): one 8-byte store per row; replicates
+  float w[SG_RPT][8], shv[SG_RPT];
+  // the thread's SG_RPT replicates are adjacent in B (LV-major layout): one 16-byte store per row; replicates
   // past nrep (but inside the padded stride) get zeros
   const int64_t bb0 = rep0 + bl * SG_RPT;
-  uint2* out = (active && sub == 0 && bb0 < ldl) ? reinterpret_cast<uint2*>(B + l * ldl + bb0) : nullptr;
+  uint4* out = (active && sub == 0 && bb0 < ldl) ? reinterpret_cast<uint4*>(B + l * ldl + bb0) : nullptr;
 #pragma unroll
   for (int j = 0; j < SG_RPT; ++j) {
     const int64_t bb = bb0 + j;
     const bool ok = bb < nrep;
-    shv[j] = (ok && sub == 0) ? sh[bb * L + l] : 0.0;
+    shv[j] = (ok && sub == 0) ? (float)sh[bb * L + l] : 0.f;
 #pragma unroll
-    for (int ch = 0; ch < 4; ++ch) {
-      const int col = slot * SLOT + 2 * ((ch + rot) & 3);
-      w[j][2 * ch] = (ok && has_slot) ? wf[bb * Ppad + col] : 0.0;
-      w[j][2 * ch + 1] = (ok && has_slot) ? wf[bb * Ppad + col + 1] : 0.0;
-    }
+    for (int k = 0; k < 8; ++k) w[j][k] = (ok && has_slot) ? (float)wf[bb * Ppad + slot * SLOT + k] : 0.f;
   }
-  const int64_t ldb = ldl * L / SG_RPT;                      // row stride of B in 8-byte units
-  const double* xcol = xs + slot * SLOT;
-  int xo[4];
-#pragma unroll
-  for (int ch = 0; ch < 4; ++ch) xo[ch] = 2 * ((ch + rot) & 3);
+  const int64_t ldb = ldl * L / SG_RPT;                      // row stride of B in 16-byte units
+  const float* xcol = xs + slot * SLOT;
   // the block weights stay in registers while the CTA walks its share of the chunk's row tiles
   for (int row0 = blockIdx.x * SG_ROWS; row0 < rc; row0 += gridDim.x * SG_ROWS) {
     const int rows = min(SG_ROWS, rc - row0);
     __syncthreads();
-    for (int e = threadIdx.x; e < SG_ROWS * Ppad; e += SG_THREADS) {
-      const int r = e / Ppad;
-      xs[e] = (r < rows) ? X[(i0 + row0) * Ppad + e] : 0.0;
+    {
+      const float4* src = reinterpret_cast<const float4*>(X + (i0 + row0) * Ppad);
+      float4* dst = reinterpret_cast<float4*>(xs);
+      const int n4 = rows * Ppad / 4;
+      for (int e = threadIdx.x; e < n4; e += SG_THREADS) dst[e] = src[e];
     }
     for (int e = threadIdx.x; e < reps_per_cta * SG_ROWS; e += SG_THREADS) {
       const int eb = e / SG_ROWS, r = e - eb * SG_ROWS;     // consecutive threads: consecutive rows of one replicate
       const int64_t bb = rep0 + eb;
-      double c = 0.0;
-      if (r < rows && bb < nrep) c = counts ? (double)counts[bb * N + i0 + row0 + r] : 1.0;
+      float c = 0.f;
+      if (r < rows && bb < nrep) c = counts ? (float)counts[bb * N + i0 + row0 + r] : 1.f;
       cs[r * reps_per_cta + eb] = c;
     }
     __syncthreads();
     if (SINGLE_SLOT && !active) continue;  // (with lane groups everyone runs along: full-mask shuffles below)
-    const double* cr = cs + bl * SG_RPT;
+    const float* cr = cs + bl * SG_RPT;
     int64_t orow = (int64_t)row0 * ldb;
     for (int r = 0; r < rows; ++r, orow += ldb) {
-      double x[8];
+      const float4 xa = *reinterpret_cast<const float4*>(xcol + (size_t)r * Ppad);
+      const float4 xb = *reinterpret_cast<const float4*>(xcol + (size_t)r * Ppad + 4);
+      const float4 ca = *reinterpret_cast<const float4*>(cr + r * reps_per_cta);
+      const float4 cb = *reinterpret_cast<const float4*>(cr + r * reps_per_cta + 4);
+      const float x[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+      const float cj[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
+      uint32_t pk[SG_RPT / 2];
 #pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {
-        const double2 v = *reinterpret_cast<const double2*>(xcol + (size_t)r * Ppad + xo[ch]);
-        x[2 * ch] = v.x; x[2 * ch + 1] = v.y;
-      }
-      const double2 c01 = *reinterpret_cast<const double2*>(cr + r * reps_per_cta);
-      const double2 c23 = *reinterpret_cast<const double2*>(cr + r * reps_per_cta + 2);
-      const double cj[4] = {c01.x, c01.y, c23.x, c23.y};
-      __half hv[SG_RPT];
+      for (int j = 0; j < SG_RPT; j += 2) {
+        float t0 = -shv[j], t1 = -shv[j + 1];
 #pragma unroll
-      for (int j = 0; j < SG_RPT; ++j) {
-        double t0 = -shv[j], t1 = 0.0;                      // two chains: half the dependent-FMA latency
-#pragma unroll
-        for (int k = 0; k < 8; k += 2) {
-          t0 = fma(x[k], w[j][k], t0);
-          t1 = fma(x[k + 1], w[j][k + 1], t1);
+        for (int k = 0; k < 8; ++k) {
+          t0 = fmaf(x[k], w[j][k], t0);
+          t1 = fmaf(x[k], w[j + 1][k], t1);
         }
-        double t = t0 + t1;
         if (!SINGLE_SLOT)
-          for (int o = nsl_pad >> 1; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-        hv[j] = __double2half(cj[j] * t);
+          for (int o = nsl_pad >> 1; o > 0; o >>= 1) {
+            t0 += __shfl_xor_sync(0xffffffffu, t0, o);
+            t1 += __shfl_xor_sync(0xffffffffu, t1, o);
+          }
+        const __half2 h2 = __floats2half2_rn(cj[j] * t0, cj[j + 1] * t1);
+        pk[j / 2] = *reinterpret_cast<const uint32_t*>(&h2);
       }
-      if (out) {
-        uint2 pk;
-        pk.x = (uint32_t)__half_as_ushort(hv[0]) | ((uint32_t)__half_as_ushort(hv[1]) << 16);
-        pk.y = (uint32_t)__half_as_ushort(hv[2]) | ((uint32_t)__half_as_ushort(hv[3]) << 16);
-        out[orow] = pk;
-      }
+      if (out) out[orow] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     }
   }
 }
@@ -1553,6 +1550,10 @@ int plspm_data_create(const plspm_model* m, const double* X, int64_t N, int64_t 
       d->timer.begin(ST_UPLOAD, st);
       make_half_kernel<<<d->sm_count * 8, 256, 0, st>>>(d->X, N, h.Ppad, d->inv_sd, d->Xh);
       d->timer.end(st);
+      CK(g_pool.alloc((void**)&d->Xf, (size_t)N * h.Ppad * sizeof(float)));
+      d->timer.begin(ST_UPLOAD, st);
+      make_float_kernel<<<d->sm_count * 8, 256, 0, st>>>(d->X, N * h.Ppad, d->Xf);
+      d->timer.end(st);
       CK(cudaGetLastError());
       CK(cudaStreamSynchronize(st));
       g_pool.release(sq);
@@ -1669,6 +1670,7 @@ void plspm_data_destroy(plspm_data* d) {
   if (d->X) g_pool.release(d->X);
   if (d->mu) g_pool.release(d->mu);
   if (d->Xh) g_pool.release(d->Xh);
+  if (d->Xf) g_pool.release(d->Xf);
   if (d->inv_sd) g_pool.release(d->inv_sd);
   if (d->D8) g_pool.release(d->D8);
   if (d->Z8) g_pool.release(d->Z8);
@@ -1776,7 +1778,7 @@ static int plan_batch(const plspm_data* d, int64_t nb, BatchPlan& bp) {
     bp.cv_nsl_pad = nsl_pad;
     bp.cv_reps_per_cta = nbl * CV_RPT;
     const size_t fixed = (size_t)SG_THREADS * CV_RPT * 8;
-    bp.cv_rows = (int)std::max<size_t>(1, std::min<size_t>(SG_MAX_ROWS, ((size_t)d->max_smem - 16384 - fixed) /
+    bp.cv_rows = (int)std::max<size_t>(1, std::min<size_t>(32, ((size_t)d->max_smem - 16384 - fixed) /
                                                                            ((size_t)h.Ppad * 8 + bp.cv_reps_per_cta * 8)));
     bp.cv_smem = (size_t)bp.cv_rows * h.Ppad * 8 + (size_t)bp.cv_rows * bp.cv_reps_per_cta * 8 + fixed;
     bp.cv_gy = (unsigned)((nb + bp.cv_reps_per_cta - 1) / bp.cv_reps_per_cta);
@@ -2109,9 +2111,10 @@ static int run_batch(plspm_data* d, int64_t nb, const uint32_t* counts_dev, cons
       int nbl_host = SG_THREADS / (h.L * nsl_pad);
       if (nsl_pad == 1 && nbl_host >= 4) nbl_host = (SG_THREADS / 32 / ((h.L + 7) / 8)) * 4;
       const int reps_per_cta = std::max(1, nbl_host) * SG_RPT;
-      const int SG_ROWS = (int)std::max<size_t>(1, std::min<size_t>(SG_MAX_ROWS, (size_t)(d->max_smem - 16384) /
-                                                                                  ((size_t)h.Ppad * 8 + reps_per_cta * 8)));
-      const size_t sg_smem = (size_t)SG_ROWS * h.Ppad * 8 + (size_t)reps_per_cta * SG_ROWS * 8;
+      // rows per staged tile: at most 64, and small enough for two CTAs per SM
+      const size_t sg_row_bytes = (size_t)h.Ppad * 4 + (size_t)reps_per_cta * 4;
+      const int SG_ROWS = (int)std::max<size_t>(1, std::min<size_t>(SG_MAX_ROWS, (size_t)(d->max_smem / 2 - 8192) / sg_row_bytes));
+      const size_t sg_smem = (size_t)SG_ROWS * sg_row_bytes;
       auto sg_kernel = (nsl_pad == 1) ? scoregen_kernel<true> : scoregen_kernel<false>;
       CK(cudaFuncSetAttribute(sg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sg_smem));
       const float one = 1.f, zero = 0.f;
@@ -2126,7 +2129,7 @@ static int run_batch(plspm_data* d, int64_t nb, const uint32_t* counts_dev, cons
                                                                             (4 * d->sm_count + gy - 1) / gy));
         dim3 grid_sg(gx, gy);
         d->timer.begin(ST_SCOREGEN, st);
-        sg_kernel<<<grid_sg, SG_THREADS, sg_smem, st>>>(d->X, counts_dev, D(bb.wf), D(bb.sh), d->N, h.Ppad, h.L,
+        sg_kernel<<<grid_sg, SG_THREADS, sg_smem, st>>>(d->Xf, counts_dev, D(bb.wf), D(bb.sh), d->N, h.Ppad, h.L,
                                                              m->dv.lv_off, m->dv.lv_k, nsl_pad, SG_ROWS, nb, ldl, i0, rc,
                                                              BT);
         d->timer.end(st);

@@ -358,7 +358,20 @@ PL_HD void solve_replicate(const SolveArgs& A, double* smem) {
       bsum[l] = sh;
     }
   if (A.phase == 3)
-    for (int l = tid; l < L; l += nt) unc[l] = 0;
+    for (int l = tid; l < L; l += nt) {
+      unc[l] = 0;
+      // fp32 score generation: |t^ - t| <= (k+4) 2^-24 (sum_k |x_k w_k| + |sh|) per row, hence (Cauchy-Schwarz
+      // over the rows)  sum_i c_i xh_ip |t^ - t| <= sqrt(sum c xh_p^2) * bsum[l] with
+      // bsum[l] = (k+4) 2^-24 sqrt(2 (|w_l|^2 sum_q G_qq + N sh_l^2))
+      double w2 = 0.0, g = 0.0, sh = 0.0;
+      for (int r = 0; r < M.lv_k[l]; ++r) {
+        const int q = M.lv_off[l] + r;
+        w2 += u[q] * u[q];
+        g += gram_raw(M, A.G, q, q);
+        sh += m[q] * u[q];
+      }
+      bsum[l] = (M.lv_k[l] + 4) * 6.0e-8 * sqrt(2.0 * (w2 * g + N * sh * sh));
+    }
   PL_SYNC();
   // cov(x_p, score_l) for ALL (p, l): every manifest variable votes on every LV (quirk Q6)
   for (int t = tid; t < Ppad * L; t += nt) {
@@ -370,7 +383,7 @@ PL_HD void solve_replicate(const SolveArgs& A, double* smem) {
       // accumulation over <= 4096-row chunks give |fl(E) - E| <= gamma * sqrt(sum c xh^2) * sqrt(sum c t^2)
       // (Cauchy-Schwarz); sum c t^2 = N / iss because the scores have unit variance on the treated scale
       const double v = (double)A.fast_cross[((size_t)p * L + l) * A.fast_nb + A.fast_b];
-      const double bound = 2.0e-3 * sqrt(gram_raw(M, A.G, p, p)) * A.inv_sd[p] * sqrt(N / iss);
+      const double bound = (2.0e-3 * sqrt(N / iss) + bsum[l]) * sqrt(gram_raw(M, A.G, p, p)) * A.inv_sd[p];
       if (v - v == 0.0 && fabs(v) > bound) vote_add(votes, l, v < 0.0 ? -1 : 1);
       else vote_add(unc, l, 1);
       continue;
