@@ -591,6 +591,10 @@ __global__ void __launch_bounds__(SG_THREADS) scoregen_kernel(const float* __res
   if (SINGLE_SLOT && nbl >= 4) nbl = (SG_THREADS / 32 / ((L + 7) >> 3)) * 4;
   const int reps_per_cta = nbl * SG_RPT;
   const int64_t rep0 = (int64_t)blockIdx.y * reps_per_cta;
+  // the staging stores of the multiplicities walk the rows (stride = one row of cs): XOR the group-of-four index
+  // with the row so that they spread over the banks (power-of-two group counts only)
+  const int groups4 = reps_per_cta / 4;
+  const int swz = (groups4 & (groups4 - 1)) == 0 ? min(groups4, 8) - 1 : 0;
   // Thread -> (replicate lane bl, latent variable l, slot sub).  Single-slot blocks: a warp is 8 LVs x 4
   // replicate lanes, so the 32 LDS.128 of a row touch only 8 distinct (adjacent) slots.
   int sub, bl, l;
@@ -612,6 +616,9 @@ __global__ void __launch_bounds__(SG_THREADS) scoregen_kernel(const float* __res
   }
   const bool has_slot = sub < ((lv_k[l] + SLOT - 1) >> 3);
   const int slot = (lv_off[l] >> 3) + (has_slot ? sub : 0);
+  // a slot is two 16-byte chunks; slots 4 apart share shared-memory banks, so odd groups of four slots read
+  // their chunks in the opposite order (the weights are permuted the same way: the dot product does not care)
+  const int rot4 = ((slot >> 2) & 1) * 4;
   float w[SG_RPT][8], shv[SG_RPT];
   // the thread's SG_RPT replicates are adjacent in B (LV-major layout): one 16-byte store per row; replicates
   // past nrep (but inside the padded stride) get zeros
@@ -623,7 +630,7 @@ __global__ void __launch_bounds__(SG_THREADS) scoregen_kernel(const float* __res
     const bool ok = bb < nrep;
     shv[j] = (ok && sub == 0) ? (float)sh[bb * L + l] : 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) w[j][k] = (ok && has_slot) ? (float)wf[bb * Ppad + slot * SLOT + k] : 0.f;
+    for (int k = 0; k < 8; ++k) w[j][k] = (ok && has_slot) ? (float)wf[bb * Ppad + slot * SLOT + (k ^ rot4)] : 0.f;
   }
   const int64_t ldb = ldl * L / SG_RPT;                      // row stride of B in 16-byte units
   const float* xcol = xs + slot * SLOT;
@@ -642,17 +649,17 @@ __global__ void __launch_bounds__(SG_THREADS) scoregen_kernel(const float* __res
       const int64_t bb = rep0 + eb;
       float c = 0.f;
       if (r < rows && bb < nrep) c = counts ? (float)counts[bb * N + i0 + row0 + r] : 1.f;
-      cs[r * reps_per_cta + eb] = c;
+      cs[r * reps_per_cta + (eb ^ (swz ? (r & swz) << 2 : 0))] = c;
     }
     __syncthreads();
     if (SINGLE_SLOT && !active) continue;  // (with lane groups everyone runs along: full-mask shuffles below)
-    const float* cr = cs + bl * SG_RPT;
     int64_t orow = (int64_t)row0 * ldb;
     for (int r = 0; r < rows; ++r, orow += ldb) {
-      const float4 xa = *reinterpret_cast<const float4*>(xcol + (size_t)r * Ppad);
-      const float4 xb = *reinterpret_cast<const float4*>(xcol + (size_t)r * Ppad + 4);
-      const float4 ca = *reinterpret_cast<const float4*>(cr + r * reps_per_cta);
-      const float4 cb = *reinterpret_cast<const float4*>(cr + r * reps_per_cta + 4);
+      const float4 xa = *reinterpret_cast<const float4*>(xcol + (size_t)r * Ppad + rot4);
+      const float4 xb = *reinterpret_cast<const float4*>(xcol + (size_t)r * Ppad + (4 - rot4));
+      const int sw = swz ? (r & swz) << 2 : 0;              // undo the staging swizzle (groups of four replicates)
+      const float4 ca = *reinterpret_cast<const float4*>(cs + r * reps_per_cta + ((bl * SG_RPT) ^ sw));
+      const float4 cb = *reinterpret_cast<const float4*>(cs + r * reps_per_cta + ((bl * SG_RPT + 4) ^ sw));
       const float x[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
       const float cj[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
       uint32_t pk[SG_RPT / 2];
