@@ -425,33 +425,50 @@ __global__ void digit_scale_kernel(const double* __restrict__ partial, int nbloc
   dscale[p] = ldexp(1.0, e - 40);
   qscale[p] = ldexp(1.0, 40 - e);
 }
-// tile = 32 columns x 128 rows; digits go through shared memory so that both the reads of X (along p) and
-// the writes of the planes (along i) are coalesced
+// Balanced base-128 digits without carries: with U = q + sum_k 64 * 128^k (>= 0), digit k of q is
+// ((U >> 7k) & 127) - 64.  digit_bytes() returns the six digits of q as bytes d[0..5].
+constexpr long long I8_OFFSET = 64ll * ((1ll << 42) - 1) / 127;  // sum_{k<6} 64 * 128^k
+__device__ __forceinline__ void digit_bytes(long long q, uint32_t (&d)[I8_DIGITS]) {
+  const unsigned long long U = (unsigned long long)(q + I8_OFFSET);
+  const uint32_t lo = (uint32_t)U, hi = (uint32_t)(U >> 28);  // digits 0..3 from lo, 4..5 from bits 28..41
+  d[0] = ((lo & 127u) - 64u) & 255u;
+  d[1] = (((lo >> 7) & 127u) - 64u) & 255u;
+  d[2] = (((lo >> 14) & 127u) - 64u) & 255u;
+  d[3] = (((lo >> 21) & 127u) - 64u) & 255u;
+  d[4] = ((hi & 127u) - 64u) & 255u;
+  d[5] = (((hi >> 7) & 127u) - 64u) & 255u;
+}
+// tile = 32 columns x 128 rows; a thread digitises 4 consecutive rows of one column and stores one 32-bit word
+// per plane; the planes go through shared memory so that the global writes (along i) are coalesced
 __global__ void __launch_bounds__(256) digits_kernel(const double* __restrict__ X, int64_t N, int Ppad, int64_t Npad,
                                                      const double* __restrict__ qscale, int8_t* __restrict__ D8) {
   __shared__ __align__(4) int8_t sm[I8_DIGITS][32][132];
   const int p0 = blockIdx.x * 32;
   const int64_t i0 = (int64_t)blockIdx.y * 128;
-  for (int e = threadIdx.x; e < 32 * 128; e += 256) {
-    const int pl = e & 31, il = e >> 5;
-    const int64_t i = i0 + il;
-    const int p = p0 + pl;
-    long long q = 0;
-    if (i < N && p < Ppad) q = __double2ll_rn(X[i * Ppad + p] * qscale[p]);
+  const int pl = threadIdx.x & 31;
+  const int p = p0 + pl;
+  const double sc = p < Ppad ? qscale[p] : 0.0;
+  for (int i4 = threadIdx.x >> 5; i4 < 32; i4 += 8) {
+    uint32_t word[I8_DIGITS] = {0, 0, 0, 0, 0, 0};
 #pragma unroll
-    for (int k = 0; k < I8_DIGITS; ++k) {
-      const long long dgt = ((q + 64) & 127) - 64;
-      q = (q - dgt) >> 7;
-      sm[k][pl][il] = (int8_t)dgt;
+    for (int j = 0; j < 4; ++j) {
+      const int64_t i = i0 + 4 * i4 + j;
+      long long q = 0;
+      if (i < N && p < Ppad) q = __double2ll_rn(X[i * Ppad + p] * sc);
+      uint32_t d[I8_DIGITS];
+      digit_bytes(q, d);
+#pragma unroll
+      for (int k = 0; k < I8_DIGITS; ++k) word[k] |= d[k] << (8 * j);
     }
+#pragma unroll
+    for (int k = 0; k < I8_DIGITS; ++k) *reinterpret_cast<uint32_t*>(&sm[k][pl][4 * i4]) = word[k];
   }
   __syncthreads();
   for (int e = threadIdx.x; e < I8_DIGITS * 32 * 32; e += 256) {
-    const int w = e & 31, row = e >> 5, k = row >> 5, pl = row & 31;
-    const int p = p0 + pl;
+    const int w = e & 31, row = e >> 5, k = row >> 5, c = row & 31;
     const int64_t i = i0 + 4 * w;
-    if (p < Ppad && i < Npad)
-      *reinterpret_cast<uint32_t*>(D8 + ((int64_t)k * Ppad + p) * Npad + i) = *reinterpret_cast<const uint32_t*>(&sm[k][pl][4 * w]);
+    if (p0 + c < Ppad && i < Npad)
+      *reinterpret_cast<uint32_t*>(D8 + ((int64_t)k * Ppad + p0 + c) * Npad + i) = *reinterpret_cast<const uint32_t*>(&sm[k][c][4 * w]);
   }
 }
 // multiplicities as int8 [nrep][Npad]; thread = 4 rows
@@ -519,16 +536,20 @@ __global__ void __launch_bounds__(256) zdigits_kernel(const double* __restrict__
   const bool col_ok = col < n_zcols;
   const int p = col_ok ? zp[col] : 0, q = col_ok ? zq[col] : 0;
   const double sc = col_ok ? zqscale[col] : 0.0;
-  for (int il = threadIdx.x >> 5; il < 128; il += 8) {
-    const int64_t i = row0 + i0 + il;
-    long long v = 0;
-    if (i0 + il < ld && i < N && col_ok) v = __double2ll_rn(X[i * Ppad + p] * X[i * Ppad + q] * sc);
+  for (int i4 = threadIdx.x >> 5; i4 < 32; i4 += 8) {  // a thread digitises 4 consecutive rows: one word per plane
+    uint32_t word[I8_DIGITS] = {0, 0, 0, 0, 0, 0};
 #pragma unroll
-    for (int k = 0; k < I8_DIGITS; ++k) {
-      const long long dgt = ((v + 64) & 127) - 64;
-      v = (v - dgt) >> 7;
-      sm[k][cl][il] = (int8_t)dgt;
+    for (int j = 0; j < 4; ++j) {
+      const int64_t il = i0 + 4 * i4 + j, i = row0 + il;
+      long long v = 0;
+      if (il < ld && i < N && col_ok) v = __double2ll_rn(X[i * Ppad + p] * X[i * Ppad + q] * sc);
+      uint32_t d[I8_DIGITS];
+      digit_bytes(v, d);
+#pragma unroll
+      for (int k = 0; k < I8_DIGITS; ++k) word[k] |= d[k] << (8 * j);
     }
+#pragma unroll
+    for (int k = 0; k < I8_DIGITS; ++k) *reinterpret_cast<uint32_t*>(&sm[k][cl][4 * i4]) = word[k];
   }
   __syncthreads();
   for (int e = threadIdx.x; e < I8_DIGITS * 32 * 32; e += 256) {
@@ -2237,7 +2258,7 @@ int plspm_bootstrap(const plspm_model* m, const plspm_data* dc, int32_t scheme, 
                                           (m->numeric ? 6 : 2) * h.Ppad + h.ws_doubles + n_out) * 8 +
                          (idx ? (size_t)N * 4 : 0) + (d->i8_colsum ? (size_t)d->Npad + I8_DIGITS * ((size_t)h.Ppad + d->n_zcols) * 4 : 0) + 64;
   // the planes of a chunk are regenerated for every batch in streaming mode: large batches amortise that
-  const size_t ws_budget = d->n_zcols && !d->Z8 ? (size_t)8 << 30 : (size_t)1536 << 20;
+  const size_t ws_budget = d->n_zcols && !d->Z8 ? (size_t)12 << 30 : (size_t)1536 << 20;
   int64_t nb_max = std::max<int64_t>(1, (int64_t)(ws_budget / per_rep));
   if (getenv("PLSPM_MAX_BATCH")) nb_max = std::max<int64_t>(1, std::min<int64_t>(nb_max, atoll(getenv("PLSPM_MAX_BATCH"))));
   nb_max = std::min<int64_t>(nb_max, rep_count);
