@@ -71,7 +71,7 @@ struct DevPool {
   std::mutex mu;
   std::vector<Block> free_blocks;
   size_t cached = 0;
-  static constexpr size_t kMaxCached = (size_t)12 << 30;
+  static constexpr size_t kMaxCached = (size_t)64 << 30;
   cudaError_t alloc(void** out, size_t bytes) {
     int dev = 0;
     cudaGetDevice(&dev);
