@@ -295,9 +295,13 @@ def run_gpu_arm(args):
     Xp = engine.pinned_empty(X.shape)
     Xp[...] = X
     out_host = engine.pinned_empty((reps, n_out))
-    e2e_steps = max(1, min(args.steps, 5))
+    warm_ms = []
     for s in range(2):  # warm-up: the buffer pool and the library GEMM kernels are populated here
+        ts = time.perf_counter()
         engine.bootstrap_host(model, Xp, w["scheme"], s * reps, reps, seed=1, out=out_host)
+        warm_ms.append(1e3 * (time.perf_counter() - ts))
+    # enough steps for ~2 s of end-to-end work (2 .. 10): a single host hiccup must not decide the figure
+    e2e_steps = int(max(2, min(10, round(2000.0 / max(warm_ms[-1], 1.0)))))
     barrier()
     e2e_each = []
     t0 = time.perf_counter()
