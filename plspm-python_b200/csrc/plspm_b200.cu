@@ -706,12 +706,22 @@ __global__ void __launch_bounds__(SG_THREADS) scoregen_kernel(const float* __res
 }
 
 // Stopping criterion of the non-metric path (weights.py:120), per replicate:
-//   conv[b] = sum_l sum_i c_bi ( |x~_i . coef_old,l - sh_old,l| - |x~_i . coef_new,l - sh_new,l| )^2
-// Same thread mapping and tile walk as scoregen_kernel (lane groups of nsl_pad slots per (replicate
-// lane, LV)), two replicates per thread, both coefficient sets in registers.  Every CTA writes one partial
-// per replicate; num_step_kernel adds the partials in a fixed order.
-constexpr int CV_RPT = 2;
-__global__ void __launch_bounds__(SG_THREADS) conv_kernel(const double* __restrict__ X, const uint32_t* __restrict__ counts,
+//   conv[b] = sum_l sum_i c_bi ( |y_old,il| - |y_new,il| )^2 ,   y = x~_i . coef_l - sh_l .
+// (|a| - |b|)^2 = (a - b)^2 + 4ab [ab < 0]: the first part is a function of second moments and comes from
+// num_step (conv_main); this pass adds  4 sum c y_old y_new  over the (row, LV) pairs whose score changes sign.
+// Same thread mapping and tile walk as scoregen_kernel (lane groups of nsl_pad slots per (replicate lane, LV)).
+// T = float: the scores are screened in fp32 from the fp32 copy of x~ (4 replicates per thread); any score
+// within 8x its fp32 error bound of zero is recomputed in fp64 from X by the lane, so near the tolerance (where
+// the score changes are tiny and every sign change is such a score) the result is the fp64 one; clear sign
+// changes (both scores away from zero) only occur while the criterion is far above the tolerance and use the
+// fp32 products (relative error 1e-5 of a number that is then >> tol).  T = double: everything in fp64 (N < 4096).
+// Every CTA writes one partial per replicate; num_step_kernel adds the partials in a fixed order.
+template <typename T> struct CvTraits;
+template <> struct CvTraits<double> { static constexpr int RPT = 2; };
+template <> struct CvTraits<float> { static constexpr int RPT = 4; };
+template <typename T>
+__global__ void __launch_bounds__(SG_THREADS, 2) conv_kernel(const T* __restrict__ Xs, const double* __restrict__ X,
+                                                          const uint32_t* __restrict__ counts,
                                                           const double* __restrict__ coef_old,
                                                           const double* __restrict__ coef_new,
                                                           const double* __restrict__ sh_old,
@@ -719,82 +729,132 @@ __global__ void __launch_bounds__(SG_THREADS) conv_kernel(const double* __restri
                                                           int64_t N, int Ppad, int L, const int* __restrict__ lv_off,
                                                           const int* __restrict__ lv_k, int nsl_pad, int ROWS,
                                                           int64_t nrep, double* __restrict__ conv_part) {
-  extern __shared__ __align__(16) double cv_smem[];
-  double* xs = cv_smem;                                     // [ROWS][Ppad]
-  double* cs = xs + (size_t)ROWS * Ppad;                    // [ROWS][reps_per_cta]
-  double* part = cs + (size_t)ROWS * (SG_THREADS / (L * nsl_pad)) * CV_RPT;  // [SG_THREADS][CV_RPT]
+  constexpr int RPT = CvTraits<T>::RPT;
+  constexpr bool F32 = sizeof(T) == 4;
+  extern __shared__ __align__(16) unsigned char cv_smem_raw[];
   const int nbl = SG_THREADS / (L * nsl_pad);
-  const int reps_per_cta = nbl * CV_RPT;
+  const int reps_per_cta = nbl * RPT;
+  T* xs = reinterpret_cast<T*>(cv_smem_raw);                // [ROWS][Ppad]
+  T* cs = xs + (size_t)ROWS * Ppad;                         // [ROWS][reps_per_cta]
+  double* part = reinterpret_cast<double*>(cv_smem_raw + (((size_t)ROWS * (Ppad + reps_per_cta) * sizeof(T) + 15) & ~(size_t)15));
   const int64_t rep0 = (int64_t)blockIdx.y * reps_per_cta;
   const int item = threadIdx.x / nsl_pad, sub = threadIdx.x - item * nsl_pad;
   const int bl = min(item / L, nbl - 1), l = item % L;
   const bool active = item < nbl * L;
   const bool has_slot = sub < ((lv_k[l] + SLOT - 1) >> 3);
   const int slot = (lv_off[l] >> 3) + (has_slot ? sub : 0);
-  const int rot = (slot >> 1) & 3;
-  double wo[CV_RPT][8], wn[CV_RPT][8], so[CV_RPT], sn[CV_RPT], acc[CV_RPT];
-  bool live[CV_RPT];
+  // chunk order within the slot, rotated against shared-memory bank aliasing (double: 4 chunks of 2, float: 2 of 4)
+  constexpr int CH = F32 ? 2 : 4, CW = 8 / CH;
+  const int rot = F32 ? (slot >> 2) & 1 : (slot >> 1) & 3;
+  T wo[RPT][8], wn[RPT][8], so[RPT], sn[RPT], nwo[RPT], nwn[RPT];
+  double acc[RPT];
+  bool live[RPT];
 #pragma unroll
-  for (int j = 0; j < CV_RPT; ++j) {
-    const int64_t bb = rep0 + bl * CV_RPT + j;
+  for (int j = 0; j < RPT; ++j) {
+    const int64_t bb = rep0 + bl * RPT + j;
     live[j] = bb < nrep && meta[bb * 4 + 1] == 0;  // finished replicates are skipped
     acc[j] = 0.0;
-    so[j] = (live[j] && sub == 0) ? sh_old[bb * L + l] : 0.0;
-    sn[j] = (live[j] && sub == 0) ? sh_new[bb * L + l] : 0.0;
+    so[j] = (live[j] && sub == 0) ? (T)sh_old[bb * L + l] : (T)0;
+    sn[j] = (live[j] && sub == 0) ? (T)sh_new[bb * L + l] : (T)0;
+    T no = 0, nn = 0;
 #pragma unroll
-    for (int ch = 0; ch < 4; ++ch) {
-      const int col = slot * SLOT + 2 * ((ch + rot) & 3);
-      const bool ld = live[j] && has_slot;
-      wo[j][2 * ch] = ld ? coef_old[bb * Ppad + col] : 0.0;
-      wo[j][2 * ch + 1] = ld ? coef_old[bb * Ppad + col + 1] : 0.0;
-      wn[j][2 * ch] = ld ? coef_new[bb * Ppad + col] : 0.0;
-      wn[j][2 * ch + 1] = ld ? coef_new[bb * Ppad + col + 1] : 0.0;
-    }
+    for (int ch = 0; ch < CH; ++ch)
+#pragma unroll
+      for (int e = 0; e < CW; ++e) {
+        const int col = slot * SLOT + CW * ((ch + rot) % CH) + e;
+        const bool ld = live[j] && has_slot;
+        wo[j][CW * ch + e] = ld ? (T)coef_old[bb * Ppad + col] : (T)0;
+        wn[j][CW * ch + e] = ld ? (T)coef_new[bb * Ppad + col] : (T)0;
+        no += wo[j][CW * ch + e] * wo[j][CW * ch + e];
+        nn += wn[j][CW * ch + e] * wn[j][CW * ch + e];
+      }
+    nwo[j] = sqrt(no); nwn[j] = sqrt(nn);
   }
+  // fp32 screening threshold: 8 x the rounding bound (k+4) 2^-24 (|x_blk| |w_blk| + |sh|) of a score
+  const T gam = (T)(8.0 * (8 * nsl_pad + 4) * 6.0e-8);
   for (int64_t row0 = (int64_t)blockIdx.x * ROWS; row0 < N; row0 += (int64_t)gridDim.x * ROWS) {
     const int rows = (int)min((int64_t)ROWS, N - row0);
     __syncthreads();
-    for (int e = threadIdx.x; e < ROWS * Ppad; e += SG_THREADS) {
-      const int r = e / Ppad;
-      xs[e] = (r < rows) ? X[row0 * Ppad + e] : 0.0;
+    {  // 16-byte copies (rows are multiples of 8 elements)
+      const float4* src = reinterpret_cast<const float4*>(Xs + row0 * Ppad);
+      float4* dst = reinterpret_cast<float4*>(xs);
+      const int n4 = rows * Ppad * (int)sizeof(T) / 16;
+      for (int e = threadIdx.x; e < n4; e += SG_THREADS) dst[e] = src[e];
     }
     for (int e = threadIdx.x; e < reps_per_cta * ROWS; e += SG_THREADS) {
       const int eb = e / ROWS, r = e - eb * ROWS;
       const int64_t bb = rep0 + eb;
-      double c = 0.0;
-      if (r < rows && bb < nrep) c = counts ? (double)counts[bb * N + row0 + r] : 1.0;
+      T c = 0;
+      if (r < rows && bb < nrep) c = counts ? (T)counts[bb * N + row0 + r] : (T)1;
       cs[r * reps_per_cta + eb] = c;
     }
     __syncthreads();
     for (int r = 0; r < rows; ++r) {
-      double x[8];
+      T x[8];
+      if constexpr (F32) {
 #pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {
-        const double2 v = *reinterpret_cast<const double2*>(xs + (size_t)r * Ppad + slot * SLOT + 2 * ((ch + rot) & 3));
-        x[2 * ch] = v.x; x[2 * ch + 1] = v.y;
+        for (int ch = 0; ch < 2; ++ch) {
+          const float4 v = *reinterpret_cast<const float4*>(xs + (size_t)r * Ppad + slot * SLOT + 4 * ((ch + rot) & 1));
+          x[4 * ch] = v.x; x[4 * ch + 1] = v.y; x[4 * ch + 2] = v.z; x[4 * ch + 3] = v.w;
+        }
+      } else {
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          const double2 v = *reinterpret_cast<const double2*>(xs + (size_t)r * Ppad + slot * SLOT + 2 * ((ch + rot) & 3));
+          x[2 * ch] = v.x; x[2 * ch + 1] = v.y;
+        }
+      }
+      T x2 = 0;
+      if constexpr (F32) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x2 = fma(x[k], x[k], x2);
+        x2 = sqrt(x2);
       }
 #pragma unroll
-      for (int j = 0; j < CV_RPT; ++j) {
-        double to = -so[j], tn = -sn[j];
+      for (int j = 0; j < RPT; ++j) {
+        T to = -so[j], tn = -sn[j];
 #pragma unroll
         for (int k = 0; k < 8; ++k) { to = fma(x[k], wo[j][k], to); tn = fma(x[k], wn[j][k], tn); }
+        T bo = F32 ? gam * (x2 * nwo[j] + fabs(so[j])) : (T)0, bn = F32 ? gam * (x2 * nwn[j] + fabs(sn[j])) : (T)0;
         for (int o = nsl_pad >> 1; o > 0; o >>= 1) {
           to += __shfl_xor_sync(0xffffffffu, to, o);
           tn += __shfl_xor_sync(0xffffffffu, tn, o);
+          if constexpr (F32) {
+            bo += __shfl_xor_sync(0xffffffffu, bo, o);
+            bn += __shfl_xor_sync(0xffffffffu, bn, o);
+          }
         }
-        const double df = fabs(to) - fabs(tn);
-        if (sub == 0 && active) acc[j] = fma(cs[r * reps_per_cta + bl * CV_RPT + j] * df, df, acc[j]);
+        if (sub != 0 || !active || !live[j]) continue;
+        const double c = (double)cs[r * reps_per_cta + bl * RPT + j];
+        if constexpr (F32) {
+          if (fabsf(to) > bo && fabsf(tn) > bn) {
+            // both signs are certain.  A clear sign change needs |y_old - y_new| > 2 bound on this row, which only
+            // happens while the criterion is orders of magnitude above the tolerance: fp32 products are enough there
+            if (to * tn < 0.f) acc[j] = fma(4.0 * c * (double)to, (double)tn, acc[j]);
+          } else {  // rare: a score within its fp32 error bound of zero -- exact scores of this (row, LV, replicate)
+            const int64_t bb = rep0 + bl * RPT + j, i = row0 + r;
+            double yo = -sh_old[bb * L + l], yn = -sh_new[bb * L + l];
+            for (int q = lv_off[l]; q < lv_off[l] + lv_k[l]; ++q) {
+              const double xv = X[i * Ppad + q];
+              yo = fma(xv, coef_old[bb * Ppad + q], yo);
+              yn = fma(xv, coef_new[bb * Ppad + q], yn);
+            }
+            if (yo * yn < 0.0) acc[j] = fma(4.0 * c * yo, yn, acc[j]);
+          }
+        } else {
+          if (to * tn < 0.0) acc[j] = fma(4.0 * c * to, tn, acc[j]);
+        }
       }
     }
   }
   __syncthreads();
 #pragma unroll
-  for (int j = 0; j < CV_RPT; ++j) part[threadIdx.x * CV_RPT + j] = (sub == 0 && active && live[j]) ? acc[j] : 0.0;
+  for (int j = 0; j < RPT; ++j) part[threadIdx.x * RPT + j] = (sub == 0 && active && live[j]) ? acc[j] : 0.0;
   __syncthreads();
   if (threadIdx.x < reps_per_cta) {  // fixed-order sum over the threads that served this replicate
-    const int eb = threadIdx.x, ebl = eb / CV_RPT, ej = eb - ebl * CV_RPT;
+    const int eb = threadIdx.x, ebl = eb / RPT, ej = eb - ebl * RPT;
     double s = 0.0;
-    for (int ll = 0; ll < L; ++ll) s += part[((ebl * L + ll) * nsl_pad) * CV_RPT + ej];
+    for (int ll = 0; ll < L; ++ll) s += part[((ebl * L + ll) * nsl_pad) * RPT + ej];
     if (rep0 + eb < nrep) conv_part[(rep0 + eb) * gridDim.x + blockIdx.x] = s;
   }
 }
@@ -806,6 +866,7 @@ struct NumBatch {
   double N;
   int scheme; double tol; int max_iter;
   const double* conv_part; int n_conv_part;
+  double* conv_main;  // [nrep] second-moment part of the criterion, written by num_step
   double* ws;
   double *a, *coef_old, *coef_new, *shift_old, *shift_new;
   int* meta;
@@ -824,9 +885,10 @@ __global__ void __launch_bounds__(128) num_step_kernel(const NumBatch b) {
   A.G = b.G + rep * b.g_stride;
   A.colsum = b.colsum + rep * b.M.Ppad;
   A.N = b.N; A.scheme = b.scheme; A.tol = b.tol; A.max_iter = b.max_iter;
-  double conv = 0.0;
+  double conv = b.conv_main[rep];
   for (int k = 0; k < b.n_conv_part; ++k) conv += b.conv_part[rep * b.n_conv_part + k];
   A.conv_in = conv;
+  A.conv_main = b.conv_main + rep;
   A.ws = b.ws + rep * (int64_t)b.M.ws_doubles;
   A.a = b.a + rep * b.M.Ppad;
   A.meta = b.meta + rep * 4;
@@ -1592,6 +1654,13 @@ int plspm_data_create(const plspm_model* m, const double* X, int64_t N, int64_t 
       d->fast_vote = true;
       trace("fp16 copy + blas");
     }
+    if (!d->Xf && N >= 4096) {  // fp32 copy for the score screening of the non-metric criterion pass
+      CK(g_pool.alloc((void**)&d->Xf, (size_t)N * h.Ppad * sizeof(float)));
+      d->timer.begin(ST_UPLOAD, st);
+      make_float_kernel<<<d->sm_count * 8, 256, 0, st>>>(d->X, N * h.Ppad, d->Xf);
+      d->timer.end(st);
+      CK(cudaGetLastError());
+    }
     // integer digit planes for the tensor-core column sums (PLSPM_COLSUM=fp64 keeps the fp64 kernel)
     static const bool colsum_fp64 = getenv("PLSPM_COLSUM") && std::string(getenv("PLSPM_COLSUM")) == "fp64";
     if (!colsum_fp64 && N >= 4096 && N < ((int64_t)1 << 31) - 16) {
@@ -1729,6 +1798,7 @@ struct BatchPlan {
   int64_t cs_chunk_rows = 0;
   // criterion pass of the numeric non-metric path
   int cv_nsl_pad = 1, cv_reps_per_cta = 1, cv_rows = 1;
+  bool cv_f32 = false;
   unsigned cv_gx = 1, cv_gy = 1;
   size_t cv_smem = 0;
 };
@@ -1804,11 +1874,18 @@ static int plan_batch(const plspm_data* d, int64_t nb, BatchPlan& bp) {
       return fail(PLSPM_ERR_UNSUPPORTED, "numeric non-metric path: L x (padded slots per block) exceeds 256");
     const int nbl = SG_THREADS / (h.L * nsl_pad);
     bp.cv_nsl_pad = nsl_pad;
-    bp.cv_reps_per_cta = nbl * CV_RPT;
-    const size_t fixed = (size_t)SG_THREADS * CV_RPT * 8;
-    bp.cv_rows = (int)std::max<size_t>(1, std::min<size_t>(32, ((size_t)d->max_smem - 16384 - fixed) /
-                                                                           ((size_t)h.Ppad * 8 + bp.cv_reps_per_cta * 8)));
-    bp.cv_smem = (size_t)bp.cv_rows * h.Ppad * 8 + (size_t)bp.cv_rows * bp.cv_reps_per_cta * 8 + fixed;
+    // the fp32-screened variant is correct but not yet faster than the fp64 one (12.6 vs ~10 ms per pass on c3:
+    // branchy inner loop, 128-register cap); opt-in until it is tuned
+    static const bool conv_f32 = getenv("PLSPM_CONV_F32") && atoi(getenv("PLSPM_CONV_F32")) != 0;
+    bp.cv_f32 = conv_f32 && d->Xf != nullptr;
+    const size_t esz = bp.cv_f32 ? 4 : 8;
+    const int rpt = bp.cv_f32 ? CvTraits<float>::RPT : CvTraits<double>::RPT;
+    bp.cv_reps_per_cta = nbl * rpt;
+    const size_t fixed = (size_t)SG_THREADS * rpt * 8 + 16;
+    // at most 64 rows per staged tile, and small enough for two CTAs per SM
+    bp.cv_rows = (int)std::max<size_t>(1, std::min<size_t>(bp.cv_f32 ? 64 : 32, ((size_t)d->max_smem / 2 - 8192 - fixed) /
+                                                                                 (((size_t)h.Ppad + bp.cv_reps_per_cta) * esz)));
+    bp.cv_smem = (size_t)bp.cv_rows * ((size_t)h.Ppad + bp.cv_reps_per_cta) * esz + fixed;
     bp.cv_gy = (unsigned)((nb + bp.cv_reps_per_cta - 1) / bp.cv_reps_per_cta);
     bp.cv_gx = (unsigned)std::max<int64_t>(1, std::min<int64_t>((d->N + bp.cv_rows - 1) / bp.cv_rows,
                                                                  (4 * d->sm_count + bp.cv_gy - 1) / bp.cv_gy));
@@ -1826,7 +1903,7 @@ struct BatchBuffers {
   // single-fit outputs
   size_t weights, loadings, r2, paths, totalfx, crossl, coef, shift, scores;
   // numeric non-metric path: per-replicate iteration state
-  size_t num_a, num_co, num_cn, num_so, num_sn, num_meta, num_done, num_cpart;
+  size_t num_a, num_co, num_cn, num_so, num_sn, num_meta, num_done, num_cpart, num_cmain;
   // tensor-core column sums: int8 multiplicities, int32 digit sums, overflow flag
   size_t c8, s32, ovf, zs32, zchunk;
 };
@@ -1868,6 +1945,7 @@ static BatchBuffers layout_batch(const plspm_data* d, int64_t nb, const BatchPla
   b.zs32 = take(i8 && d->n_zcols ? (size_t)nb * I8_DIGITS * d->n_zcols * sizeof(int32_t) : 0);
   b.zchunk = take(i8 && d->n_zcols && !d->Z8 ? (size_t)I8_DIGITS * d->n_zcols * d->z_chunk_rows : 0);
   b.num_cpart = take(numeric ? (size_t)nb * bp.cv_gx * 8 : 0);
+  b.num_cmain = take(numeric ? (size_t)nb * 8 : 0);
   const size_t ldl = (size_t)(nb + 7) / 8 * 8;  // replicate stride of the LV-major score / cross-moment layout
   b.BT = take(fast ? ldl * h.L * FAST_RC * sizeof(__half) : 0);
   b.Cf = take(fast ? ldl * h.L * h.Ppad * sizeof(float) : 0);
@@ -2057,6 +2135,7 @@ static int run_batch_num(plspm_data* d, int64_t nb, const uint32_t* counts_dev, 
   b.colsum = D(bb.colsum);
   b.N = (double)d->N; b.scheme = scheme; b.tol = tol; b.max_iter = max_iter;
   b.conv_part = D(bb.num_cpart); b.n_conv_part = (int)bp.cv_gx;
+  b.conv_main = D(bb.num_cmain);
   b.ws = D(bb.ws);
   b.a = D(bb.num_a); b.coef_old = D(bb.num_co); b.coef_new = D(bb.num_cn);
   b.shift_old = D(bb.num_so); b.shift_new = D(bb.num_sn);
@@ -2070,10 +2149,12 @@ static int run_batch_num(plspm_data* d, int64_t nb, const uint32_t* counts_dev, 
   CK(cudaMemsetAsync(b.meta, 0, (size_t)nb * 16, st));
   CK(cudaMemsetAsync(b.n_done, 0, 8, st));
   CK(cudaMemsetAsync(D(bb.num_cpart), 0, (size_t)nb * bp.cv_gx * 8, st));
+  CK(cudaMemsetAsync(D(bb.num_cmain), 0, (size_t)nb * 8, st));
   const size_t smem = h.solver_smem_doubles() * sizeof(double);
   if (smem > (size_t)d->max_smem) return fail(PLSPM_ERR_UNSUPPORTED, "model too large for the solver's shared memory");
   CK(cudaFuncSetAttribute(num_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  CK(cudaFuncSetAttribute(conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bp.cv_smem));
+  CK(cudaFuncSetAttribute(conv_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bp.cv_smem));
+  CK(cudaFuncSetAttribute(conv_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bp.cv_smem));
   const unsigned gy = (unsigned)((nb + bp.cv_reps_per_cta - 1) / bp.cv_reps_per_cta);
   int done = 0;
   for (int step = 0; step < max_iter + 4; ++step) {
@@ -2085,9 +2166,14 @@ static int run_batch_num(plspm_data* d, int64_t nb, const uint32_t* counts_dev, 
     CK(cudaStreamSynchronize(st));
     if (done >= nb) break;
     d->timer.begin(ST_CONV, st);
-    conv_kernel<<<dim3(bp.cv_gx, gy), SG_THREADS, bp.cv_smem, st>>>(
-        d->X, counts_dev, b.coef_old, b.coef_new, b.shift_old, b.shift_new, b.meta, d->N, h.Ppad, h.L, m->dv.lv_off,
-        m->dv.lv_k, bp.cv_nsl_pad, bp.cv_rows, nb, D(bb.num_cpart));
+    if (bp.cv_f32)
+      conv_kernel<float><<<dim3(bp.cv_gx, gy), SG_THREADS, bp.cv_smem, st>>>(
+          d->Xf, d->X, counts_dev, b.coef_old, b.coef_new, b.shift_old, b.shift_new, b.meta, d->N, h.Ppad, h.L,
+          m->dv.lv_off, m->dv.lv_k, bp.cv_nsl_pad, bp.cv_rows, nb, D(bb.num_cpart));
+    else
+      conv_kernel<double><<<dim3(bp.cv_gx, gy), SG_THREADS, bp.cv_smem, st>>>(
+          d->X, d->X, counts_dev, b.coef_old, b.coef_new, b.shift_old, b.shift_new, b.meta, d->N, h.Ppad, h.L,
+          m->dv.lv_off, m->dv.lv_k, bp.cv_nsl_pad, bp.cv_rows, nb, D(bb.num_cpart));
     d->timer.end(st);
     CK(cudaGetLastError());
   }

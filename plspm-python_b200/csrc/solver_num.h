@@ -12,6 +12,10 @@
 //     sum is not a function of second moments, so the iteration is driven from the host: one call of
 //     num_step() per outer iteration for all replicates of a batch, followed by one streaming pass
 //     (conv_kernel) that evaluates the criterion from the old and new coefficient vectors.
+//     Since (|a| - |b|)^2 = (a - b)^2 + 4ab [ab < 0], the criterion splits into
+//        N sum_l (a_old - a_new)_l' S_ll (a_old - a_new)_l      -- second moments, computed here (conv_main)
+//      + 4 sum_{i,l : y_old y_new < 0} c_i y_old,il y_new,il    -- only the rows whose score changes sign,
+//     so the streaming pass only has to find the sign changes (scores close to zero).
 //
 // Same dual compilation as solver_core.h (device: one CTA per replicate; host: emulation for tests).
 #pragma once
@@ -28,6 +32,7 @@ struct NumStepArgs {
   double tol;
   int max_iter;
   double conv_in;        // criterion of the previous step (ignored while it == 0)
+  double* conv_main;     // [1] out: the second-moment part of this step's criterion (see below)
   double* ws;            // [M.ws_doubles] global scratch private to this replicate (persists across steps)
   // persistent state of the replicate (global memory)
   double* a;             // [Ppad] current coefficient vectors
@@ -256,6 +261,20 @@ PL_HD void num_step(const NumStepArgs& A, double* smem) {
     for (int r = 0; r < k; ++r) an[o + r] *= s;  // treat_numpy(Y) * correction: unit population variance
   }
   PL_SYNC();
+  // second-moment part of the stopping criterion: N (a - an)_l' S_ll (a - an)_l summed over the LVs
+  for (int l = tid; l < L; l += nt) {
+    int o = M.lv_off[l], k = M.lv_k[l];
+    double q = 0.0;
+    for (int r = 0; r < k; ++r)
+      for (int c = 0; c < k; ++c) q += (a[o + r] - an[o + r]) * PLN_S(o + r, o + c) * (a[o + c] - an[o + c]);
+    r2[l] = q;
+  }
+  PL_SYNC();
+  if (tid == 0 && A.conv_main) {
+    double q = 0.0;
+    for (int l = 0; l < L; ++l) q += r2[l];
+    A.conv_main[0] = N * q;
+  }
   // hand the old / new scores to the criterion pass and persist the state
   for (int p = tid; p < Ppad; p += nt) {
     A.coef_old[p] = a[p] * isd[p];

@@ -70,6 +70,8 @@ def fit(X, block_sizes, modes, path, scheme, scaled, idx=None, tol=1e-6, max_ite
            _p(out["path_coefficients"], d), _p(out["total_effects"], d), _p(out["crossloadings"], d),
            _p(out["scores"], d), _p(iters, ctypes.c_int32), _p(status, ctypes.c_int32))
     assert rc == 0
+    # the criterion's decomposition (second-moment part + sign-change rows) must equal the direct evaluation
+    assert lib().emul_num_decomposition_errors() == 0
     out["iterations"] = int(iters[0])
     out["status"] = int(status[0])
     out["info"] = info
@@ -112,6 +114,8 @@ def fit_num(X, block_sizes, modes, path, scheme, idx=None, tol=1e-6, max_iter=10
            _p(out["path_coefficients"], d), _p(out["total_effects"], d), _p(out["crossloadings"], d),
            _p(out["scores"], d), _p(iters, ctypes.c_int32), _p(status, ctypes.c_int32))
     assert rc == 0
+    # the criterion's decomposition (second-moment part + sign-change rows) must equal the direct evaluation
+    assert lib().emul_num_decomposition_errors() == 0
     out["iterations"] = int(iters[0])
     out["status"] = int(status[0])
     out["info"] = info

@@ -157,6 +157,8 @@ extern "C" int emul_fit(int L, const int32_t* block_sizes, const int8_t* modes, 
 // Non-metric (Scale.NUM / RAW) fit: host-driven outer loop around num_step(), with the score criterion
 // sum_{i,l} c_i (|y_old| - |y_new|)^2 evaluated per observation on the host (the CUDA library does this in
 // conv_kernel).
+static int g_num_decomposition_errors = 0;
+extern "C" int emul_num_decomposition_errors() { return g_num_decomposition_errors; }
 extern "C" int emul_fit_num(int L, const int32_t* block_sizes, const int8_t* modes, const int8_t* path,
                             int tile_policy, const double* X, int64_t N, const int32_t* idx, int scheme, double tol,
                             int max_iter, double* out_row, double* weights, double* loadings, double* r2, double* paths,
@@ -202,20 +204,26 @@ extern "C" int emul_fit_num(int L, const int32_t* block_sizes, const int8_t* mod
   A.crossloadings = crossloadings; A.score_coef = coef.data(); A.score_shift = shift.data();
   A.iters = iters; A.status = status;
   A.conv_in = 0.0;
+  double conv_main = 0.0;
+  A.conv_main = &conv_main;
   for (int guard = 0; guard < max_iter + 5 && !meta[1]; ++guard) {
     num_step(A, smem.data());
     if (meta[1]) break;
-    double conv = 0.0;
+    // criterion = second-moment part (from num_step) + 4 sum c y_old y_new over the rows whose score changes
+    // sign; the direct per-observation evaluation is kept as a cross-check of the decomposition
+    double conv = conv_main, direct = 0.0;
     for (int64_t i = 0; i < N; ++i) {
       if (cnt[i] == 0.0) continue;
       const double* x = &Xs[i * Pp];
       for (int l = 0; l < L; ++l) {
         double yo = -so[l], yn = -sn[l];
         for (int c = m.lv_off[l]; c < m.lv_off[l + 1]; ++c) { yo += x[c] * co[c]; yn += x[c] * cn[c]; }
+        if (yo * yn < 0.0) conv += 4.0 * cnt[i] * yo * yn;
         const double df = std::fabs(yo) - std::fabs(yn);
-        conv += cnt[i] * df * df;
+        direct += cnt[i] * df * df;
       }
     }
+    if (std::fabs(conv - direct) > 1e-9 * (std::fabs(direct) + 1e-12) + 1e-18) g_num_decomposition_errors++;
     A.conv_in = conv;
   }
   if (scores && !idx)
