@@ -72,24 +72,28 @@ struct DevPool {
   std::vector<Block> free_blocks;
   size_t cached = 0;
   static constexpr size_t kMaxCached = (size_t)64 << 30;
+  // Requests are rounded up to a size class and only an exact class match is reused: the allocation pattern
+  // of a call (data handle + workspace) is deterministic, so from the second identical call on every request
+  // hits the cache -- a best-fit policy kept trading blocks between requests for several calls.
+  static size_t size_class(size_t bytes) {
+    const size_t g = bytes <= ((size_t)64 << 10) ? 256 : bytes <= ((size_t)16 << 20) ? ((size_t)64 << 10) : ((size_t)2 << 20);
+    return (bytes + g - 1) / g * g;
+  }
   cudaError_t alloc(void** out, size_t bytes) {
     int dev = 0;
     cudaGetDevice(&dev);
+    bytes = size_class(std::max<size_t>(bytes, 1));
     {
       std::lock_guard<std::mutex> lk(mu);
-      int best = -1;
-      for (int i = 0; i < (int)free_blocks.size(); ++i) {
+      for (int i = (int)free_blocks.size() - 1; i >= 0; --i) {
         const Block& b = free_blocks[i];
-        if (b.device == dev && b.bytes >= bytes && b.bytes <= 2 * bytes + (1 << 20) &&
-            (best < 0 || b.bytes < free_blocks[best].bytes))
-          best = i;
-      }
-      if (best >= 0) {
-        *out = free_blocks[best].p;
-        cached -= free_blocks[best].bytes;
-        sizes.push_back({*out, free_blocks[best].bytes, dev});
-        free_blocks.erase(free_blocks.begin() + best);
-        return cudaSuccess;
+        if (b.device == dev && b.bytes == bytes) {
+          *out = b.p;
+          cached -= b.bytes;
+          sizes.push_back({*out, b.bytes, dev});
+          free_blocks.erase(free_blocks.begin() + i);
+          return cudaSuccess;
+        }
       }
     }
     cudaError_t e = cudaMalloc(out, bytes);
