@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "plspm_b200", "libplspm_b200.so")
 SOURCES = [os.path.join(CSRC, "plspm_b200.cu"), os.path.join(CSRC, "plspm_model.cpp")]
-DEPS = SOURCES + [os.path.join(CSRC, f) for f in ("plspm_model.h", "solver_core.h")] + \
+DEPS = SOURCES + [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".h", ".cuh"))] + \
     [os.path.join(os.path.dirname(HERE), "include", "plspm_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "-shared"]
