@@ -269,11 +269,13 @@ def run_gpu_arm(args):
             torch.cuda.synchronize()
         return status, iters
 
+    # nvidia-smi needs ~100 ms per sample and the timed region can be shorter than that: the sampler runs from
+    # the warm-up through the timed steps and a tail of identical (untimed) steps, all under the same load
+    sampler = ClockSampler(local) if rank == 0 else None
     for _ in range(args.warmup):
         step()
     barrier()
     engine.profile_reset()
-    sampler = ClockSampler(local) if rank == 0 else None
     t0 = time.perf_counter()
     iters_all, bad = [], 0
     for _ in range(args.steps):
@@ -282,12 +284,19 @@ def run_gpu_arm(args):
         bad += int((status != 0).sum())
     barrier()
     elapsed = time.perf_counter() - t0
-    clocks = sampler.stop() if sampler else None
     prof = engine.profile_get()
     el_t = torch.tensor([elapsed], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(el_t, op=dist.ReduceOp.MAX)
     elapsed_max = float(el_t.item())
+    # (the same count on every rank: the steps contain a collective)
+    tail_steps = int(min(200, 0.6 / max(elapsed_max / args.steps, 1e-4) + 1))
+    for _ in range(tail_steps):
+        step()
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    if clocks is not None:
+        clocks["window"] = "warm-up + timed steps + %d identical untimed steps (same load)" % tail_steps
     value = world * reps * args.steps / elapsed_max
     iters_cat = np.concatenate(iters_all)
 
@@ -376,6 +385,10 @@ def run_gpu_arm(args):
                                  "batch), so frac exceeds 1 by construction; traffic (ncu dram bytes of the dominant "
                                  "kernel, per launch) is the honest HBM figure"},
             "stages_ms_per_step": {k: v[0] / args.steps for k, v in prof.items() if v[1]},
+            "timing": "value = replicates / wall clock around the K steps (barrier + synchronize on both sides, max over "
+                      "ranks); every step ends in a stream synchronize inside the library, so this is >= the device time. "
+                      "CUDA-event sum of the step's kernels on the library's stream: %.3f ms per step"
+                      % (sum(v[0] for v in prof.values()) / args.steps),
             "mean_iterations": float(iters_cat.mean()), "failed_replicates": bad,
         }
         if world == 1 and not args.no_cpu:
