@@ -1,4 +1,5 @@
-"""Host-side helpers (reference plspm/util.py).  Only the pieces the metric path needs."""
+"""Host-side helpers (reference plspm/util.py): treatment, imputation, outer design matrix, rank / dummy / group
+means of the ordinal and nominal scales (not accelerated; kept for API completeness), topological sort."""
 import collections
 
 import numpy as np
@@ -31,6 +32,34 @@ def list_to_dummy(data: dict) -> pd.DataFrame:
     for lv, mvs in data.items():
         out.loc[mvs, lv] = 1.0
     return out
+
+
+def treat_numpy(data: np.ndarray) -> np.ndarray:
+    """Centre and scale (sd with ddof = 1) one NumPy column, ignoring NaNs (reference util.py:43-53)."""
+    centred = data - np.nanmean(data)
+    return centred / np.nanstd(centred, axis=0, ddof=1)
+
+
+def rank(data: pd.Series) -> pd.Series:
+    """Dense rank of the distinct values, 1 = smallest, ties share a rank (reference util.py:80-86).  Used by
+    the ordinal / nominal scales, which this package does not accelerate; kept for API completeness."""
+    order = {v: float(r) for r, v in enumerate(sorted(pd.unique(data.dropna())), start=1)}
+    return data.map(order).astype(float)
+
+
+def dummy(data: pd.Series) -> pd.DataFrame:
+    """Indicator matrix of ranked data: column r is 1 where data == r, r = 1..#distinct (reference util.py:89-95)."""
+    levels = range(1, data.unique().size + 1)
+    return pd.DataFrame({r: (data == r).astype(int) for r in levels}, index=data.index, columns=list(levels))
+
+
+def groupby_mean(data: np.ndarray) -> np.ndarray:
+    """Row 0 of `data` holds group keys, row 1 values: returns [sorted keys; group means] (reference
+    util.py:98-112), i.e. pandas' groupby(...).mean() for a 2 x n array."""
+    keys, inverse = np.unique(data[0], return_inverse=True)
+    sums = np.bincount(inverse, weights=data[1], minlength=keys.size)
+    counts = np.bincount(inverse, minlength=keys.size)
+    return np.vstack([keys.astype(np.float64), sums / counts])
 
 
 class TopoSort:

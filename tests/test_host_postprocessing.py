@@ -120,3 +120,22 @@ def test_unidimensionality_vs_r(sat):
     for col in ("mvs", "cronbach_alpha", "dillon_goldstein_rho", "eig_1st", "eig_2nd"):
         np.testing.assert_allclose(u[col].values.astype(float), sat["R/unidim/" + col], rtol=1e-7)
     assert list(u["mode"]) == ["A"] * 6
+
+
+def test_util_helpers_match_the_reference_semantics():
+    """reference tests/test_util.py (impute, rank) + dummy / groupby_mean / treat_numpy restatements"""
+    import plspm.util as util
+    frame = pd.DataFrame({"a": [1, 2, np.nan, 3, np.nan], "b": [1, 2, 3, 4, 5], "c": [1, np.nan, 3, 0, 4]})
+    expected = pd.DataFrame({"a": [1, 2, 2, 3, 2], "b": [1, 2, 3, 4, 5], "c": [1, 2, 3, 0, 4]})
+    np.testing.assert_array_equal(expected, util.impute(frame))
+    data = pd.Series([0.75, -1.5, 3, -1.5, 15])
+    assert util.rank(data).astype(int).equals(pd.Series([2, 1, 3, 1, 4]))
+    d = util.dummy(util.rank(data))
+    assert list(d.columns) == [1, 2, 3, 4]
+    np.testing.assert_array_equal(d.to_numpy(), [[0, 1, 0, 0], [1, 0, 0, 0], [0, 0, 1, 0], [1, 0, 0, 0], [0, 0, 0, 1]])
+    g = util.groupby_mean(np.array([[2.0, 1.0, 2.0, 3.0, 1.0], [10.0, 1.0, 20.0, 5.0, 3.0]]))
+    np.testing.assert_allclose(g, [[1.0, 2.0, 3.0], [2.0, 15.0, 5.0]])
+    y = np.array([1.0, 2.0, np.nan, 4.0])
+    t = util.treat_numpy(y)
+    np.testing.assert_allclose(np.nanmean(t), 0.0, atol=1e-15)
+    np.testing.assert_allclose(np.nanstd(t, ddof=1), 1.0)
