@@ -28,20 +28,6 @@ struct GramParams {
   const int* rep_map;       // optional: item / n_tg -> replicate (exact redo of selected replicates)
 };
 
-__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
-  uint32_t done;
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-      "selp.u32 %0, 1, 0, p;\n"
-      "}\n"
-      : "=r"(done)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return done != 0;
-}
-
 template <bool CROSS>
 __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const GramParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];

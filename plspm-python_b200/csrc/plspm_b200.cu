@@ -1,18 +1,20 @@
-// plspm_b200: sm_100a kernels + C ABI (include/plspm_b200.h).
+// plspm_b200: sm_100a kernels + C ABI (include/plspm_b200.h).  This file holds the handles, the launch plans,
+// the batch drivers and the C ABI; the kernels are in kernels_*.cuh (included below, one translation unit).
 //
 // Data flow of one bootstrap batch (replicates are the batch dimension):
 //
-//   counts_kernel   Philox4x32-10 (or injected) resample indices -> multiplicity c[b][i] (u32)
-//   gram_kernel     weighted second moments per replicate, fp64:
-//                     G_b[p,q] = sum_i c_bi x~_ip x~_iq  (8x8 register tiles),  colsum_b[p]
-//                   X~ row tiles are staged global->shared by the TMA engine (cp.async.bulk +
-//                   mbarrier ring, one producer warp) and shared by every (replicate, tile
-//                   group) warp of the CTA: X is read from HBM once per wave of replicates,
-//                   not once per replicate and iteration.
-//   reduce_kernel   fixed-order sum over row chunks (only when rows are split, e.g. one fit)
-//   solve_kernel    one CTA per replicate: the whole PLS-PM iteration in the covariance
-//                   domain (solver_core.h), inner model, effects, loadings
-//   scores_kernel   single fit only: scores = X~ . coef - shift   (N x L, HBM-bound)
+//   counts_kernel     Philox4x32-10 (or injected) resample indices -> multiplicity c[b][i] (u32)
+//   second moments    N >= 4096: counts8_kernel + ONE int8 GEMM on the tensor cores over digit planes of the
+//                     pair products x~_ip x~_iq (exact int32 sums) + zcombine_kernel; same for the column sums
+//                     (kernels_digits.cuh).  Otherwise gram_kernel / colsum_kernel in fp64 (kernels_gram.cuh):
+//                     8x8 register tiles, X~ row tiles staged by the TMA engine into an mbarrier ring shared by
+//                     the 8 (replicate, tile group) warps of a CTA.
+//   solve_kernel      one CTA per replicate: the whole PLS-PM iteration in the covariance domain
+//                     (solver_core.h), inner model, effects, loadings
+//   sign vote         sparse tile sets: scoregen_kernel (fp32 scores -> fp16) + cuBLAS fp16 GEMM with a rigorous
+//                     error bound, or the exact fp64 cross-moment pass (gram_kernel<true>)
+//   non-metric path   num_step_kernel (solver_num.h) + conv_kernel per outer iteration, driven from the host
+//   scores_kernel     single fit only: scores = X~ . coef - shift   (N x L, HBM-bound)
 //
 // Nothing here falls back to a CPU path: without a CUDA device every entry point fails.
 #include <cublas_v2.h>
