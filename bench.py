@@ -220,6 +220,23 @@ class ClockSampler:
         return out
 
 
+def split_launches(prof, steps, N, n_pair_columns):
+    """(this repo's kernel launches, library cuBLAS GEMM launches) inside the timed region, from the per-stage
+    launch counts.  Per batch the int8 routes launch GEMM + recombination kernel per row chunk (+ the plane
+    generator when the planes are streamed), the column sums one counts8 kernel more, and the fast sign vote
+    one fp16 GEMM per row chunk."""
+    n = lambda k: int(prof.get(k, (0.0, 0))[1])
+    total = sum(int(v[1]) for v in prof.values())
+    npad = (N + 15) // 16 * 16
+    resident = 6.0 * n_pair_columns * npad <= float(os.environ.get("PLSPM_I8_GRAM_GB", "24")) * 1e9
+    lib = n("gram_i8") // (2 if resident else 3)
+    if n("gram_i8"):
+        lib += max(0, n("colsum") - steps) // 2
+    if n("scoregen"):
+        lib += n("cross")
+    return total - lib, lib
+
+
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
@@ -355,7 +372,7 @@ def run_gpu_arm(args):
                 traffic = json.load(open(tp)).get(args.workload, {}).get(top)
             except Exception:
                 traffic = None
-        launches = int(sum(v[1] for v in prof.values()))
+        launches, lib = split_launches(prof, args.steps, N, model.n_pair_columns)
         line = {
             "metric": "bootstrap_fits_per_sec", "value": value, "unit": "fits/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * elapsed_max / args.steps,
@@ -365,7 +382,7 @@ def run_gpu_arm(args):
             "e2e": {"value": e2e_value, "unit": "fits/s", "h2d_bytes_per_step": int(N * P * 8),
                     "d2h_bytes_per_step": int(reps * (n_out * 8 + 8)), "steps": e2e_steps,
                     "ms_each_step_rank0": [round(v, 2) for v in e2e_each]},
-            "gpu_launches": launches,
+            "gpu_launches": launches, "library_gemm_launches": lib,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic,
                          "kernel": kernel_names.get(top, top), "kernel_stage": top,
