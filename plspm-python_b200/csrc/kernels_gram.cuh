@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const GramParams 
       }
       // The loop prefetches one row set past the end (a pad row of this stage).  Make the stage release
       // below depend on that last load, so no shared-memory read of the stage is still in flight when
-      // the producer's next bulk copy may overwrite it.
+      // the refilling bulk copy may overwrite it.
       asm volatile("{\n.reg .b32 lo, hi;\nmov.b64 {lo, hi}, %1;\nand.b32 %0, lo, 0;\n}" : "=r"(release_dep) : "d"(xb0[7]));
     }
     __syncwarp();

@@ -517,7 +517,7 @@ static int plan_stream(const plspm_data* d, int64_t n_items, size_t extra_row_by
   const HostModel& h = d->model->h;
   const size_t row_bytes = (size_t)h.Ppad * 8;
   // stages of <= 64 KB / 32 rows; measured on c3: 32-row stages beat 16-row stages by 10 % (per-tile
-  // handshakes amortise), three stages are enough once the producer refills opportunistically
+  // handshakes amortise), three stages are enough since the last consumer of a stage refills it at once
   static const int stage_kb = getenv("PLSPM_GRAM_STAGE_KB") ? atoi(getenv("PLSPM_GRAM_STAGE_KB")) : 64;
   static const int want_stages = getenv("PLSPM_GRAM_STAGES") ? atoi(getenv("PLSPM_GRAM_STAGES")) : 3;
   const size_t budget = (size_t)d->max_smem - 8 * 1024;  // static shared memory (barriers, row lists) + slack
