@@ -327,7 +327,10 @@ def run_gpu_arm(args):
         engine.bootstrap_host(model, Xp, w["scheme"], s * reps, reps, seed=1, out=out_host)
         warm_ms.append(1e3 * (time.perf_counter() - ts))
     # enough steps for ~2 s of end-to-end work (2 .. 10): a single host hiccup must not decide the figure
-    e2e_steps = int(max(2, min(10, round(2000.0 / max(warm_ms[-1], 1.0)))))
+    warm_t = torch.tensor([warm_ms[-1]], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(warm_t, op=dist.ReduceOp.MAX)  # the same step count on every rank
+    e2e_steps = int(max(2, min(10, round(2000.0 / max(float(warm_t.item()), 1.0)))))
     barrier()
     e2e_each = []
     t0 = time.perf_counter()
