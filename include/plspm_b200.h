@@ -67,7 +67,8 @@ int plspm_model_effects(const plspm_model* m, int32_t* from, int32_t* to);
  * (config.py:269, 299-305): uploads X (row-major N x P doubles, leading dimension ld, host or
  * device pointer) once and keeps it resident for any number of fits / bootstrap calls. */
 /* A data handle depends only on the column layout (block sizes in path order) of the model it was created
- * with; plspm_fit / plspm_bootstrap accept it together with any model of the same layout. */
+ * with; plspm_fit / plspm_bootstrap accept it together with any model of the same layout.  The handle owns
+ * the stream and the workspace of the call in flight: one call at a time per handle (hence non-const). */
 int plspm_data_create(const plspm_model* m, const double* X, int64_t N, int64_t ld, int32_t x_is_device,
                       plspm_data** out);
 void plspm_data_destroy(plspm_data* d);
@@ -78,7 +79,7 @@ void plspm_data_destroy(plspm_data* d);
  * outer_model.py:24-34).  Host output pointers, any may be NULL:
  * weights[P], loadings[P], r_squared[L], paths[L*L] (row = to, col = from), total_effects[L*L],
  * crossloadings[P*L], scores[N*L].  iters = iterate() calls made, status = PLSPM_FIT_*. */
-int plspm_fit(const plspm_model* m, const plspm_data* d, int32_t scheme, double tol, int32_t max_iter,
+int plspm_fit(const plspm_model* m, plspm_data* d, int32_t scheme, double tol, int32_t max_iter,
               double* weights, double* loadings, double* r_squared, double* paths, double* total_effects,
               double* crossloadings, double* scores, int32_t* iters, int32_t* status);
 
@@ -89,7 +90,7 @@ int plspm_fit(const plspm_model* m, const plspm_data* d, int32_t scheme, double 
  * out: [rep_count * info[7]] doubles, each row = weights P | r_squared L | total effects E |
  * direct effects E | loadings P; a host pointer, or a device pointer if out_is_device.
  * status / iters: host int32 [rep_count]. */
-int plspm_bootstrap(const plspm_model* m, const plspm_data* d, int32_t scheme, double tol, int32_t max_iter,
+int plspm_bootstrap(const plspm_model* m, plspm_data* d, int32_t scheme, double tol, int32_t max_iter,
                     int64_t rep_begin, int64_t rep_count, uint64_t seed, const int32_t* idx, double* out,
                     int32_t out_is_device, int32_t* status, int32_t* iters);
 
@@ -114,6 +115,12 @@ int plspm_profile_get(double* ms, int64_t* launches);
 /* Number of bootstrap replicates (since library load) whose low-precision tensor-core sign vote was
  * undecided and which were therefore redone with exact fp64 cross moments. */
 int plspm_redo_count(int64_t* count);
+
+/* Released device buffers (data handles, workspaces) are cached for the next call, up to a limit
+ * (PLSPM_POOL_GB, default 8 GB).  plspm_pool_trim returns every cached buffer to the driver;
+ * plspm_pool_set_limit changes the limit (0 = cache nothing). */
+int plspm_pool_trim(void);
+int plspm_pool_set_limit(int64_t bytes);
 
 /* Pinned host memory for callers that want full-speed host<->device copies. */
 int plspm_host_alloc(void** ptr, int64_t bytes);

@@ -25,7 +25,7 @@ struct Profile {
   int64_t launches[ST_N] = {0};
 };
 static Profile g_prof;
-static int64_t g_redo_count = 0;  // replicates redone exactly after an undecided low-precision vote
+static std::atomic<int64_t> g_redo_count{0};  // replicates redone exactly after an undecided low-precision vote
 
 // Process-wide cache of large device buffers (per device): plspm_bootstrap_host() creates and
 // destroys a data handle per call, and cudaMalloc/cudaFree of the 0.2-1.5 GB buffers would
@@ -35,7 +35,17 @@ struct DevPool {
   std::mutex mu;
   std::vector<Block> free_blocks;
   size_t cached = 0;
-  static constexpr size_t kMaxCached = (size_t)64 << 30;
+  // Released buffers are kept for the next call up to this many bytes (PLSPM_POOL_GB, default 8: enough for the
+  // data handle + workspace of a c3-sized plspm_bootstrap_host call); plspm_pool_set_limit / plspm_pool_trim
+  // let a host that shares the device with other CUDA users (torch, NCCL) lower it or give everything back.
+  size_t max_cached = (size_t)((getenv("PLSPM_POOL_GB") ? atof(getenv("PLSPM_POOL_GB")) : 8.0) * (double)((size_t)1 << 30));
+  void set_limit(size_t bytes) {
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      max_cached = bytes;
+    }
+    if (cached > bytes) trim();
+  }
   // Requests are rounded up to a size class and only an exact class match is reused: the allocation pattern
   // of a call (data handle + workspace) is deterministic, so from the second identical call on every request
   // hits the cache -- a best-fit policy kept trading blocks between requests for several calls.
@@ -78,7 +88,7 @@ struct DevPool {
       if (sizes[i].p == p) {
         Block b = sizes[i];
         sizes.erase(sizes.begin() + i);
-        if (cached + b.bytes <= kMaxCached) {
+        if (cached + b.bytes <= max_cached) {
           free_blocks.push_back(b);
           cached += b.bytes;
         } else {

@@ -16,7 +16,7 @@ struct SolveBatch {
   int phase;                             // see SolveArgs::phase
   double* wf;                            // [nrep][Ppad] (sparse tile sets)
   const double* cross; int64_t cross_stride;
-  const float* fast_cross; const double* inv_sd; int64_t fast_nb;  // phase 3
+  const float* fast_cross; const double* inv_sd; int64_t fast_nb; int fast_uncentred;  // phase 3
   double* sh;                            // [nrep][L] (phase 1 output)
   const int* rep_map;                    // optional: block -> replicate
   double* out_rows; int64_t out_stride;  // may be null
@@ -42,6 +42,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS) solve_kernel(const SolveBatch b
   A.wf_out = b.wf ? b.wf + rep * b.M.Ppad : nullptr;
   A.cross = b.cross ? b.cross + rep * b.cross_stride : nullptr;
   A.fast_cross = b.fast_cross; A.inv_sd = b.inv_sd; A.fast_nb = b.fast_nb; A.fast_b = rep;
+  A.fast_uncentred = b.fast_uncentred;
   A.sh_out = b.sh ? b.sh + rep * b.M.L : nullptr;
   A.ws = b.ws + rep * (int64_t)b.M.ws_doubles;
   A.out_row = b.out_rows ? b.out_rows + rep * b.out_stride : nullptr;

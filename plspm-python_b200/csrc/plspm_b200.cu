@@ -18,6 +18,7 @@
 //
 // Nothing here falls back to a CPU path: without a CUDA device every entry point fails.
 #include <cublas_v2.h>
+#include <cuda.h>
 #include <type_traits>
 #include <chrono>
 #include <map>
@@ -26,6 +27,7 @@
 #include <stdint.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -90,6 +92,11 @@ struct plspm_data {
   cublasHandle_t blas = nullptr;
   int blas_device = 0;
   bool fast_vote = false;    // the fp16 pass is worth trying on this data
+  // fused tcgen05 sign vote (kernels_vote_mma.cuh): xh transposed (K-major B operand) + TMA tensor maps
+  __half* XhT = nullptr;     // [Ppad][ldt]
+  int64_t ldt = 0;
+  bool mma_vote = false;
+  CUtensorMap map_xt, map_xh;
   // exact integer digit planes of x~ for the tensor-core column sums (see digits_kernel)
   int8_t* D8 = nullptr;      // [I8_DIGITS * Ppad][Npad]
   double* dscale = nullptr;  // [Ppad] value of one unit of the least significant digit
@@ -127,6 +134,7 @@ static int upload_vec(plspm_model* m, const std::vector<T>& v, const T** out) {
 #include "kernels_upload.cuh"
 #include "kernels_digits.cuh"
 #include "kernels_vote.cuh"
+#include "kernels_vote_mma.cuh"
 #include "kernels_numstep.cuh"
 #include "kernels_gram.cuh"
 #include "kernels_solve.cuh"
@@ -321,7 +329,10 @@ int plspm_data_create(const plspm_model* m, const double* X, int64_t N, int64_t 
     static const bool vote_exact = getenv("PLSPM_VOTE") && std::string(getenv("PLSPM_VOTE")) == "exact";
     int nsl_pad_chk = 1;
     while (nsl_pad_chk * SLOT < h.kmax) nsl_pad_chk <<= 1;
-    if (!h.full && !vote_exact && N >= 4096 && nsl_pad_chk <= 32 && h.L * nsl_pad_chk <= SG_THREADS) {
+    static const bool vote_legacy_chk = getenv("PLSPM_VOTE") && std::string(getenv("PLSPM_VOTE")) == "cublas";
+    const bool legacy_ok = nsl_pad_chk <= 32 && h.L * nsl_pad_chk <= SG_THREADS;
+    const bool fused_ok = !vote_legacy_chk && h.kmax <= 16 * VM_MAX_K16;
+    if (!h.full && !vote_exact && N >= 4096 && (fused_ok || legacy_ok)) {
       double* sq = nullptr;
       CK(g_pool.alloc((void**)&sq, (size_t)nblocks * h.Ppad * sizeof(double)));
       CK(g_pool.alloc((void**)&d->inv_sd, (size_t)h.Ppad * sizeof(double)));
@@ -335,21 +346,40 @@ int plspm_data_create(const plspm_model* m, const double* X, int64_t N, int64_t 
       d->timer.begin(ST_UPLOAD, st);
       make_half_kernel<<<d->sm_count * 8, 256, 0, st>>>(d->X, N, h.Ppad, d->inv_sd, d->Xh);
       d->timer.end(st);
-      CK(g_pool.alloc((void**)&d->Xf, (size_t)N * h.Ppad * sizeof(float)));
-      d->timer.begin(ST_UPLOAD, st);
-      make_float_kernel<<<d->sm_count * 8, 256, 0, st>>>(d->X, N * h.Ppad, d->Xf);
-      d->timer.end(st);
-      CK(cudaGetLastError());
+      // fused tcgen05 vote (default): blocks of at most 64 manifest variables (four K = 16 score steps)
+      if (fused_ok && N < ((int64_t)1 << 31) - 64) {
+        d->ldt = (N + 63) / 64 * 64;
+        CK(g_pool.alloc((void**)&d->XhT, (size_t)h.Ppad * d->ldt * sizeof(__half)));
+        d->timer.begin(ST_UPLOAD, st);
+        make_half_t_kernel<<<dim3((unsigned)((d->ldt + 31) / 32), (h.Ppad + 31) / 32), 256, 0, st>>>(d->X, N, h.Ppad, d->ldt,
+                                                                                               d->inv_sd, d->XhT);
+        d->timer.end(st);
+        CK(cudaGetLastError());
+        const int np_box = std::min(256, (h.Ppad + 15) / 16 * 16);
+        if (!umma::make_map_2d(&d->map_xt, d->XhT, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (uint64_t)N, (uint64_t)h.Ppad,
+                               (uint64_t)d->ldt * 2, VM_CHUNK, (uint32_t)np_box, CU_TENSOR_MAP_SWIZZLE_128B) ||
+            !umma::make_map_2d(&d->map_xh, d->Xh, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (uint64_t)h.Ppad, (uint64_t)N,
+                               (uint64_t)h.Ppad * 2, 16, VM_CHUNK, CU_TENSOR_MAP_SWIZZLE_32B))
+          return fail(PLSPM_ERR_CUDA, "cuTensorMapEncodeTiled failed (sign-vote operands)");
+        d->mma_vote = true;
+      } else {  // legacy route: fp32 score generation + library fp16 GEMM
+        CK(g_pool.alloc((void**)&d->Xf, (size_t)N * h.Ppad * sizeof(float)));
+        d->timer.begin(ST_UPLOAD, st);
+        make_float_kernel<<<d->sm_count * 8, 256, 0, st>>>(d->X, N * h.Ppad, d->Xf);
+        d->timer.end(st);
+        CK(cudaGetLastError());
+        d->blas = blas_acquire(dev);  // cublasCreate costs milliseconds: handles are recycled per device
+        if (!d->blas) return fail(PLSPM_ERR_CUDA, "cublasCreate failed");
+        d->blas_device = dev;
+        cublasSetStream(d->blas, st);
+      }
       CK(cudaStreamSynchronize(st));
       g_pool.release(sq);
-      d->blas = blas_acquire(dev);  // cublasCreate costs milliseconds: handles are recycled per device
-      if (!d->blas) return fail(PLSPM_ERR_CUDA, "cublasCreate failed");
-      d->blas_device = dev;
-      cublasSetStream(d->blas, st);
       d->fast_vote = true;
-      trace("fp16 copy + blas");
+      trace("fp16 copies");
     }
-    if (!d->Xf && N >= 4096) {  // fp32 copy for the score screening of the non-metric criterion pass
+    static const bool conv_f32_env = getenv("PLSPM_CONV_F32") && atoi(getenv("PLSPM_CONV_F32")) != 0;
+    if (!d->Xf && N >= 4096 && conv_f32_env) {  // fp32 copy for the (opt-in) fp32-screened non-metric criterion pass
       CK(g_pool.alloc((void**)&d->Xf, (size_t)N * h.Ppad * sizeof(float)));
       d->timer.begin(ST_UPLOAD, st);
       make_float_kernel<<<d->sm_count * 8, 256, 0, st>>>(d->X, N * h.Ppad, d->Xf);
@@ -462,6 +492,7 @@ void plspm_data_destroy(plspm_data* d) {
   if (d->X) g_pool.release(d->X);
   if (d->mu) g_pool.release(d->mu);
   if (d->Xh) g_pool.release(d->Xh);
+  if (d->XhT) g_pool.release(d->XhT);
   if (d->Xf) g_pool.release(d->Xf);
   if (d->inv_sd) g_pool.release(d->inv_sd);
   if (d->D8) g_pool.release(d->D8);
@@ -642,7 +673,7 @@ static BatchBuffers layout_batch(const plspm_data* d, int64_t nb, const BatchPla
   b.num_cpart = take(numeric ? (size_t)nb * bp.cv_gx * 8 : 0);
   b.num_cmain = take(numeric ? (size_t)nb * 8 : 0);
   const size_t ldl = (size_t)(nb + 7) / 8 * 8;  // replicate stride of the LV-major score / cross-moment layout
-  b.BT = take(fast ? ldl * h.L * FAST_RC * sizeof(__half) : 0);
+  b.BT = take(fast && !d->mma_vote ? ldl * h.L * FAST_RC * sizeof(__half) : 0);
   b.Cf = take(fast ? ldl * h.L * h.Ppad * sizeof(float) : 0);
   b.rep_map = take((size_t)nb * 4);
   if (single_fit) {
@@ -881,7 +912,10 @@ static int run_batch(plspm_data* d, int64_t nb, const uint32_t* counts_dev, cons
                      double tol, int max_iter, const BatchPlan& bp, double* out_rows, bool single_fit) {
   const plspm_model* m = d->model;
   const HostModel& h = m->h;
-  const bool use_fast = !h.full && d->fast_vote && !single_fit && (int64_t)(nb + 8) * h.L < (1 << 30);
+  const bool want_fast = !h.full && d->fast_vote && !single_fit && (int64_t)(nb + 8) * h.L < (1 << 30);
+  // fused tcgen05 vote: needs the int8 multiplicities of the batch (built by launch_moments)
+  const bool use_mma = want_fast && d->mma_vote && d->i8_colsum && counts_dev != nullptr;
+  const bool use_fast = use_mma || (want_fast && d->Xf && d->blas);
   cudaStream_t st = d->stream;
   char* base = (char*)d->ws.ptr;
   auto D = [&](size_t o) { return (double*)(base + o); };
@@ -908,8 +942,44 @@ static int run_batch(plspm_data* d, int64_t nb, const uint32_t* counts_dev, cons
     d->timer.end(st);
     CK(cudaGetLastError());
     b.sh = nullptr;
-    if (use_fast) {
-      // tensor-core sign vote: E[p][b][l] = sum_i xh_ip * fp16(c_bi t_bil), fp32 accumulate, in chunks
+    if (use_mma) {
+      // fused tensor-core sign vote (kernels_vote_mma.cuh): scores, multiplicity scaling and the P x L contraction
+      // in one kernel; the partial accumulators of the row ranges are added into Cf
+      float* Cf = (float*)(base + bb.Cf);
+      const int64_t ldl = (nb + 7) / 8 * 8;
+      VoteMmaParams vp;
+      vp.wf = D(bb.wf); vp.inv_sd = d->inv_sd; vp.lv_off = m->dv.lv_off; vp.lv_k = m->dv.lv_k; vp.Cf = Cf;
+      vp.nb = nb; vp.ldl = ldl; vp.N = d->N; vp.L = h.L; vp.Ppad = h.Ppad;
+      vp.n_rep_tiles = (int)((nb + 127) / 128);
+      vp.n_pchunks = (h.Ppad + 255) / 256;
+      vp.k16_max = std::max(1, (h.kmax + 15) / 16);
+      // row ranges: at most VM_MAX_ROWS rows per accumulator (truncating fp32 accumulation); among the admissible
+      // splits take the one whose CTA count fills whole waves best
+      const int64_t tiles0 = (int64_t)vp.n_rep_tiles * h.L * vp.n_pchunks;
+      const int kmin = (int)((d->N + VM_MAX_ROWS - 1) / VM_MAX_ROWS);
+      double best = 1e300;
+      for (int k = kmin; k <= kmin + 24; ++k) {
+        const int64_t rows = ((d->N + k - 1) / k + VM_CHUNK - 1) / VM_CHUNK * VM_CHUNK;
+        if ((int64_t)k * rows - d->N >= rows && k > kmin) continue;  // an empty last range
+        const double cost = (double)((tiles0 * k + d->sm_count - 1) / d->sm_count) * (double)(rows + 768);
+        if (cost < best) { best = cost; vp.ksplit = k; vp.rows_per_cta = (int)rows; }
+      }
+      CUtensorMap map_c8;
+      if (!umma::make_map_2d(&map_c8, base + bb.c8, CU_TENSOR_MAP_DATA_TYPE_UINT8, (uint64_t)d->Npad, (uint64_t)nb,
+                             (uint64_t)d->Npad, VM_CHUNK, 128, CU_TENSOR_MAP_SWIZZLE_64B))
+        return fail(PLSPM_ERR_CUDA, "cuTensorMapEncodeTiled failed (multiplicities)");
+      const size_t vm_smem = vm_smem_bytes(vp.k16_max);
+      CK(cudaFuncSetAttribute(vote_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vm_smem));
+      CK(cudaMemsetAsync(Cf, 0, (size_t)ldl * h.L * h.Ppad * sizeof(float), st));
+      const int64_t grid = tiles0 * vp.ksplit;
+      if (grid > 0x7fffffff) return fail(PLSPM_ERR_UNSUPPORTED, "batch too large for one launch");
+      d->timer.begin(ST_CROSS, st);
+      vote_mma_kernel<<<(unsigned)grid, VM_THREADS, vm_smem, st>>>(d->map_xt, d->map_xh, map_c8, vp);
+      d->timer.end(st);
+      CK(cudaGetLastError());
+      b.fast_cross = Cf; b.inv_sd = d->inv_sd; b.fast_nb = ldl; b.fast_uncentred = 1;
+    } else if (use_fast) {
+      // legacy tensor-core sign vote: E[p][b][l] = sum_i xh_ip * fp16(c_bi t_bil), fp32 accumulate, in chunks
       // of FAST_RC rows (cuBLAS: a plain fp16 GEMM, m = nb*L, n = Ppad, k = rows of the chunk)
       __half* BT = (__half*)(base + bb.BT);
       float* Cf = (float*)(base + bb.Cf);
@@ -970,13 +1040,12 @@ static int run_batch(plspm_data* d, int64_t nb, const uint32_t* counts_dev, cons
   return 0;
 }
 
-int plspm_fit(const plspm_model* m, const plspm_data* dc, int32_t scheme, double tol, int32_t max_iter, double* weights,
+int plspm_fit(const plspm_model* m, plspm_data* d, int32_t scheme, double tol, int32_t max_iter, double* weights,
               double* loadings, double* r_squared, double* paths, double* total_effects, double* crossloadings,
               double* scores, int32_t* iters, int32_t* status) {
-  if (!m || !dc || !same_layout(dc->model, m)) return fail(PLSPM_ERR_INVALID, "model/data mismatch");
+  if (!m || !d || !same_layout(d->model, m)) return fail(PLSPM_ERR_INVALID, "model/data mismatch");
   if (scheme < 0 || scheme > 2) return fail(PLSPM_ERR_INVALID, "unknown scheme");
-  plspm_data* d = const_cast<plspm_data*>(dc);
-  d->model = m;
+  d->model = m;  // the handle carries the model of the call in flight (one call at a time per handle)
   const HostModel& h = m->h;
   const int64_t N = d->N;
   const size_t L = h.L, P = h.P;
@@ -1018,14 +1087,13 @@ int plspm_fit(const plspm_model* m, const plspm_data* dc, int32_t scheme, double
   return PLSPM_OK;
 }
 
-int plspm_bootstrap(const plspm_model* m, const plspm_data* dc, int32_t scheme, double tol, int32_t max_iter,
+int plspm_bootstrap(const plspm_model* m, plspm_data* d, int32_t scheme, double tol, int32_t max_iter,
                     int64_t rep_begin, int64_t rep_count, uint64_t seed, const int32_t* idx, double* out,
                     int32_t out_is_device, int32_t* status, int32_t* iters) {
-  if (!m || !dc || !same_layout(dc->model, m)) return fail(PLSPM_ERR_INVALID, "model/data mismatch");
+  if (!m || !d || !same_layout(d->model, m)) return fail(PLSPM_ERR_INVALID, "model/data mismatch");
   if (scheme < 0 || scheme > 2) return fail(PLSPM_ERR_INVALID, "unknown scheme");
   if (rep_count < 0 || !out) return fail(PLSPM_ERR_INVALID, "bad replicate range / null output");
   if (rep_count == 0) return PLSPM_OK;
-  plspm_data* d = const_cast<plspm_data*>(dc);
   d->model = m;
   const HostModel& h = m->h;
   const int64_t N = d->N;
@@ -1152,7 +1220,16 @@ int plspm_profile_get(double* ms, int64_t* launches) {
 
 int plspm_redo_count(int64_t* count) {
   if (!count) return fail(PLSPM_ERR_INVALID, "null argument");
-  *count = g_redo_count;
+  *count = g_redo_count.load();
+  return PLSPM_OK;
+}
+
+int plspm_pool_trim(void) {
+  g_pool.trim();
+  return PLSPM_OK;
+}
+int plspm_pool_set_limit(int64_t bytes) {
+  g_pool.set_limit(bytes < 0 ? 0 : (size_t)bytes);
   return PLSPM_OK;
 }
 

@@ -54,6 +54,8 @@ struct SolveArgs {
                          //    low-precision (fp16 tensor-core) cross moment when it is provably right,
                          //    otherwise the replicate is handed back as STATUS_AMBIGUOUS
   const float* fast_cross;  // [Ppad][L][fast_nb] fp32 sums of xh_ip * (c_i t_il) (phase 3)
+  int fast_uncentred;       // phase 3: the scores behind fast_cross were NOT centred (fused tcgen05 vote kernel,
+                            // fp16 score MMA): remove sh_l * sum_i c_i xh_ip here and use that kernel's error terms
   const double* inv_sd;     // [Ppad] global 1/sd used to scale xh (phase 3)
   int64_t fast_nb, fast_b;  // replicate stride (batch size rounded up to 8) and this replicate's position
   double* sh_out;           // [L] score means sum_q m_q wf_q (phase 1)
@@ -371,6 +373,23 @@ PL_HD void solve_replicate(const SolveArgs& A, double* smem) {
         sh += m[q] * u[q];
       }
       bsum[l] = (M.lv_k[l] + 4) * 6.0e-8 * sqrt(2.0 * (w2 * g + N * sh * sh));
+      if (A.fast_uncentred) {
+        // fused kernel: t'^ = fp32 sum over the block of fp16(xh_q) * fp16(w'_q), xh = x~/sd, w' = wf sd:
+        // |t'^ - t'| <= 1.0e-3 |xh_blk| |w'_blk| per row (two fp16 roundings 2^-11 each, one truncating fp32
+        // accumulation step per 16 columns), hence over the rows (Cauchy-Schwarz)
+        //   sum_i c_i |xh_ip| |t'^ - t'| <= sqrt(sum c xh_p^2) * 1.0e-3 |w'_l| sqrt(sum_q G_qq / sd_q^2)
+        double wp2 = 0.0, gh = 0.0;
+        for (int r = 0; r < M.lv_k[l]; ++r) {
+          const int q = M.lv_off[l] + r;
+          const double isd = A.inv_sd[q];
+          if (isd > 0.0) {
+            wp2 += u[q] * u[q] / (isd * isd);
+            gh += gram_raw(M, A.G, q, q) * isd * isd;
+          }
+        }
+        bsum[l] = 1.0e-3 * sqrt(wp2 * gh);
+        sgn[l] = sh;  // (sgn is free until the votes are counted) mean of the un-centred score
+      }
     }
   PL_SYNC();
   // cov(x_p, score_l) for ALL (p, l): every manifest variable votes on every LV (quirk Q6)
@@ -382,8 +401,16 @@ PL_HD void solve_replicate(const SolveArgs& A, double* smem) {
       // E = sum_i xh_ip (c_i t_il) has the sign of cov(x_p, score_l); fp16 operands + fp32 tensor-core
       // accumulation over <= 4096-row chunks give |fl(E) - E| <= gamma * sqrt(sum c xh^2) * sqrt(sum c t^2)
       // (Cauchy-Schwarz); sum c t^2 = N / iss because the scores have unit variance on the treated scale
-      const double v = (double)A.fast_cross[((size_t)p * L + l) * A.fast_nb + A.fast_b];
-      const double bound = (2.0e-3 * sqrt(N / iss) + bsum[l]) * sqrt(gram_raw(M, A.G, p, p)) * A.inv_sd[p];
+      double v = (double)A.fast_cross[((size_t)p * L + l) * A.fast_nb + A.fast_b];
+      double t2 = N / iss;
+      if (A.fast_uncentred) {
+        // E = E' - sh_l sum_i c_i xh_ip (exact in fp64); the un-centred scores have sum c t'^2 = N/iss + N sh^2.
+        // 2e-3 covers the fp16 roundings of both MMA operands (2^-10), <= 1100 truncating fp32 accumulation steps
+        // per CTA (2^-22 each, measured 1e-7) and the fp32 adds that join the row ranges.
+        v -= sgn[l] * A.colsum[p] * A.inv_sd[p];
+        t2 += N * sgn[l] * sgn[l];
+      }
+      const double bound = (2.0e-3 * sqrt(t2) + bsum[l]) * sqrt(gram_raw(M, A.G, p, p)) * A.inv_sd[p];
       if (v - v == 0.0 && fabs(v) > bound) vote_add(votes, l, v < 0.0 ? -1 : 1);
       else vote_add(unc, l, 1);
       continue;

@@ -51,7 +51,11 @@ def send_buffer(total: int, width: int):
         return None
     import torch
     cap = shard_range(total, 0, dist.get_world_size())[1]
-    return torch.zeros(cap * (width + 2), dtype=torch.float64, device="cuda")
+    buf = torch.zeros(cap * (width + 2), dtype=torch.float64, device="cuda")
+    # the engine writes rows into this buffer on its own (non-blocking) stream: the zero fill on torch's
+    # stream has to be complete before the pointer is handed over
+    torch.cuda.current_stream().synchronize()
+    return buf
 
 
 def allgather_rows(rows, status, iters, total: int, width: int, device_buffer=None):

@@ -23,6 +23,7 @@ EXPORTS = (
     "plspm_model_destroy", "plspm_model_query", "plspm_model_effects", "plspm_data_create", "plspm_data_destroy",
     "plspm_fit", "plspm_bootstrap", "plspm_bootstrap_host", "plspm_resample_indices", "plspm_profile_reset",
     "plspm_profile_get", "plspm_host_alloc", "plspm_host_free", "plspm_redo_count", "plspm_model_set_numeric",
+    "plspm_pool_trim", "plspm_pool_set_limit",
 )
 
 _lib = None
@@ -67,6 +68,7 @@ def load():
     lib.plspm_redo_count.argtypes = [_c_i64p]
     lib.plspm_host_alloc.argtypes = [ctypes.POINTER(vp), i64]
     lib.plspm_host_free.argtypes = [vp]
+    lib.plspm_pool_set_limit.argtypes = [i64]
     _lib = lib
     return lib
 
@@ -258,6 +260,16 @@ def redo_count() -> int:
     n = ctypes.c_int64(0)
     _check(load().plspm_redo_count(ctypes.byref(n)))
     return int(n.value)
+
+
+def pool_trim():
+    """Returns every cached (released) device buffer of the library to the CUDA driver."""
+    _check(load().plspm_pool_trim())
+
+
+def pool_set_limit(nbytes: int):
+    """Upper bound on the bytes of released device buffers the library keeps for the next call."""
+    _check(load().plspm_pool_set_limit(int(nbytes)))
 
 
 def pinned_empty(shape, dtype=np.float64) -> np.ndarray:

@@ -53,8 +53,10 @@ class EngineSession:
         return engine.bootstrap(self.model, self.data, scheme.value.engine_id, rep_begin, rep_count, seed, idx, tol,
                                 iterations, out_device_ptr)
 
-    def close(self):
+    def close(self, trim_pool: bool = True):
         self.data.close()
         if self.fit_model is not self.model:
             self.fit_model.close()
         self.model.close()
+        if trim_pool:  # the process may share the device with torch / NCCL: give the cached buffers back
+            engine.pool_trim()

@@ -85,7 +85,7 @@ def host_only(monkeypatch):
         resample_indices=lambda seed, rep, n: orc.philox_indices(seed, rep, n),
         TILES_AUTO=real.TILES_AUTO, TILES_FULL=real.TILES_FULL, TILES_SPARSE=real.TILES_SPARSE,
         STATUS_OK=real.STATUS_OK, STATUS_NOT_CONVERGED=real.STATUS_NOT_CONVERGED, STATUS_SINGULAR=real.STATUS_SINGULAR,
-        EngineError=real.EngineError)
+        EngineError=real.EngineError, pool_trim=lambda: None)
     monkeypatch.setattr(session, "engine", fake)
     import plspm_b200
     monkeypatch.setattr(plspm_b200, "engine", fake, raising=False)
