@@ -39,6 +39,7 @@ struct VoteMmaParams {
   int n_rep_tiles, n_pchunks, ksplit;
   int rows_per_cta;      // multiple of VM_CHUNK, <= VM_MAX_ROWS
   int k16_max;           // K = 16 steps of the widest block (<= VM_MAX_K16): sizes the ring stages
+  int np_box;            // rows of the XhT TMA box (min(256, Ppad rounded up to 16)): a box is always delivered whole
 };
 
 __host__ __device__ inline uint32_t vm_stage_bytes(int k16_max) { return VM_XT_BYTES + VM_C8_BYTES + (uint32_t)k16_max * VM_XL_BYTES; }
@@ -103,10 +104,11 @@ __global__ void __launch_bounds__(VM_THREADS, 1)
   if (n_chunks > 0) {
     if (warp == 0) {
       if (lane == 0) {  // ---- TMA producer --------------------------------------------------------------------
-        const uint32_t tx = (uint32_t)np * 128u + VM_C8_BYTES + (uint32_t)k16 * VM_XL_BYTES;
+        // (out-of-bounds parts of a box arrive as zeros and count: the byte total never depends on the position)
+        const uint32_t tx = (uint32_t)P.np_box * 128u + VM_C8_BYTES + (uint32_t)k16 * VM_XL_BYTES;
         for (int j = 0; j < n_chunks; ++j) {
           const int s = j % VM_STAGES;
-          bar_wait(&empty[s], ((j / VM_STAGES) & 1) ^ 1);
+          bar_wait(&empty[s], ((j / VM_STAGES) & 1) ^ 1, 1);
           uint8_t* st = smem + (size_t)s * stage_bytes;
           const int i0 = (int)(row_begin + (int64_t)j * VM_CHUNK);
           bar_expect_tx(&full[s], tx);
@@ -122,7 +124,7 @@ __global__ void __launch_bounds__(VM_THREADS, 1)
         const uint64_t wdesc = smem_desc(s32(wtile), 128, 256, SW_NONE);
         auto vote_mma = [&](int j) {  // MMA 2 of chunk j
           const int s = j % VM_STAGES, u = j & 1;
-          bar_wait(&a_full[u], (j >> 1) & 1);
+          bar_wait(&a_full[u], (j >> 1) & 1, 2);
           tc_fence_after();
           const uint64_t bdesc = smem_desc(s32(smem + (size_t)s * stage_bytes), 16, 1024, SW_128B);
 #pragma unroll
@@ -133,8 +135,8 @@ __global__ void __launch_bounds__(VM_THREADS, 1)
         };
         for (int j = 0; j < n_chunks; ++j) {
           const int s = j % VM_STAGES, u = j & 1;
-          bar_wait(&full[s], (j / VM_STAGES) & 1);
-          bar_wait(&d1_empty[u], ((j >> 1) & 1) ^ 1);
+          bar_wait(&full[s], (j / VM_STAGES) & 1, 3);
+          bar_wait(&d1_empty[u], ((j >> 1) & 1) ^ 1, 4);
           tc_fence_after();
           const uint64_t xdesc = smem_desc(s32(smem + (size_t)s * stage_bytes + VM_XT_BYTES + VM_C8_BYTES), 16, 256, SW_32B);
           for (int q = 0; q < k16; ++q)
@@ -151,11 +153,11 @@ __global__ void __launch_bounds__(VM_THREADS, 1)
       const uint32_t lane_addr = tbase + ((uint32_t)(32 * q) << 16);
       for (int j = 0; j < n_chunks; ++j) {
         const int s = j % VM_STAGES, u = j & 1;
-        bar_wait(&d1_full[u], (j >> 1) & 1);
+        bar_wait(&d1_full[u], (j >> 1) & 1, 5);
         tc_fence_after();
         uint32_t tt[32];
         tmem_ld32(lane_addr + VM_COL_D1 + 64 * u + 32 * h, tt);
-        bar_wait(&full[s], (j / VM_STAGES) & 1);  // (complete long ago: acquires the TMA writes for this thread)
+        bar_wait(&full[s], (j / VM_STAGES) & 1, 6);  // (complete long ago: acquires the TMA writes for this thread)
         const uint8_t* c8 = smem + (size_t)s * stage_bytes + VM_XT_BYTES + (size_t)r * 64;
         const int sw = (r >> 1) & 3;
         const uint4 ca = *reinterpret_cast<const uint4*>(c8 + (((2 * h) ^ sw) << 4));
@@ -174,7 +176,7 @@ __global__ void __launch_bounds__(VM_THREADS, 1)
           const __half2 h2 = __floats2half2_rn(c0 * __uint_as_float(tt[e]), c1 * __uint_as_float(tt[e + 1]));
           pk[e >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
         }
-        bar_wait(&a_empty[u], ((j >> 1) & 1) ^ 1);
+        bar_wait(&a_empty[u], ((j >> 1) & 1) ^ 1, 7);
         tc_fence_after();
         tmem_st16(lane_addr + VM_COL_A + 32 * u + 16 * h, pk);
         tmem_wait_st();
@@ -183,7 +185,7 @@ __global__ void __launch_bounds__(VM_THREADS, 1)
         if (lane == 0) bar_arrive(&a_full[u]);
       }
       // ---- the accumulator of this row range joins the others in Cf --------------------------------------------
-      bar_wait(&e_full, 0);
+      bar_wait(&e_full, 0, 8);
       tc_fence_after();
       const int64_t b = b0 + r;
       for (int c0 = 128 * h; c0 < min(np, 128 * h + 128); c0 += 32) {

@@ -953,6 +953,7 @@ static int run_batch(plspm_data* d, int64_t nb, const uint32_t* counts_dev, cons
       vp.n_rep_tiles = (int)((nb + 127) / 128);
       vp.n_pchunks = (h.Ppad + 255) / 256;
       vp.k16_max = std::max(1, (h.kmax + 15) / 16);
+      vp.np_box = std::min(256, (h.Ppad + 15) / 16 * 16);
       // row ranges: at most VM_MAX_ROWS rows per accumulator (truncating fp32 accumulation); among the admissible
       // splits take the one whose CTA count fills whole waves best
       const int64_t tiles0 = (int64_t)vp.n_rep_tiles * h.L * vp.n_pchunks;

@@ -6,6 +6,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 namespace umma {
 
@@ -66,8 +67,19 @@ __device__ __forceinline__ bool bar_try(uint64_t* bar, uint32_t parity) {
       : "memory");
   return done != 0;
 }
-__device__ __forceinline__ void bar_wait(uint64_t* bar, uint32_t parity) {
+// A wait that cannot hang the device: a protocol error (a barrier that never completes) traps after ~2 s with the
+// barrier's tag instead of spinning forever, so the host sees a launch failure and the tests a clear message.
+__device__ __noinline__ void bar_timeout(int tag, uint32_t parity) {
+  printf("plspm_b200: mbarrier wait timed out (tag %d, parity %u, block %d, thread %d)\n", tag, parity, (int)blockIdx.x,
+         (int)threadIdx.x);
+  __trap();
+}
+__device__ __forceinline__ void bar_wait(uint64_t* bar, uint32_t parity, int tag = 0) {
+  if (bar_try(bar, parity)) return;
+  const long long t0 = clock64();
+  uint32_t spins = 0;
   while (!bar_try(bar, parity)) {
+    if ((++spins & 0xfffu) == 0 && clock64() - t0 > 4000000000ll) bar_timeout(tag, parity);
   }
 }
 
