@@ -93,6 +93,16 @@ struct plspm_data {
   int blas_device = 0;
   bool fast_vote = false;    // the fp16 pass is worth trying on this data
   // fused tcgen05 sign vote (kernels_vote_mma.cuh): xh transposed (K-major B operand) + TMA tensor maps
+  // tcgen05 integer Gram (kernels_gram_mma.cuh): pre-scaled transposed fp64 copy, M-tile and output tables
+  double* XsT = nullptr;     // [Ppad][ldx]  x' = x~ 2^(23 - e_p)
+  double* xunit = nullptr;   // [Ppad] 2^(e_p - 23)
+  int64_t ldx = 0;
+  bool gram_mma = false;
+  CUtensorMap map_xs;
+  int4* gm_tiles = nullptr;  // [gm_n_tiles]
+  void* gm_outs = nullptr;   // GramOut [gm_n_outs]
+  int gm_n_tiles = 0, gm_n_outs = 0;
+  const plspm_model* gm_model = nullptr;
   __half* XhT = nullptr;     // [Ppad][ldt]
   int64_t ldt = 0;
   bool mma_vote = false;
@@ -135,6 +145,7 @@ static int upload_vec(plspm_model* m, const std::vector<T>& v, const T** out) {
 #include "kernels_digits.cuh"
 #include "kernels_vote.cuh"
 #include "kernels_vote_mma.cuh"
+#include "kernels_gram_mma.cuh"
 #include "kernels_numstep.cuh"
 #include "kernels_gram.cuh"
 #include "kernels_solve.cuh"
@@ -386,9 +397,66 @@ int plspm_data_create(const plspm_model* m, const double* X, int64_t N, int64_t 
       d->timer.end(st);
       CK(cudaGetLastError());
     }
+    // tcgen05 integer Gram: pre-scaled transposed copy x' (digits are generated on the fly, no resident planes).
+    // PLSPM_GRAM=cublas selects round 1's digit planes + library GEMM, PLSPM_GRAM=fp64 the fp64 kernels.
+    static const std::string gram_env = getenv("PLSPM_GRAM") ? getenv("PLSPM_GRAM") : "";
+    bool gram_heavy_tail = false;
+    if (gram_env != "cublas" && gram_env != "fp64" && N >= 4096 && N < ((int64_t)1 << 31) - 256) {
+      d->Npad = (N + 15) / 16 * 16;
+      d->ldx = (N + 31) / 32 * 32;
+      double *amax = nullptr, *xscale = nullptr;
+      CK(g_pool.alloc((void**)&amax, (size_t)nblocks * h.Ppad * sizeof(double)));
+      CK(g_pool.alloc((void**)&xscale, (size_t)h.Ppad * sizeof(double)));
+      CK(g_pool.alloc((void**)&d->xunit, (size_t)h.Ppad * sizeof(double)));
+      CK(g_pool.alloc((void**)&d->XsT, (size_t)h.Ppad * d->ldx * sizeof(double)));
+      d->timer.begin(ST_UPLOAD, st);
+      colabsmax_partial_kernel<<<nblocks, 256, 0, st>>>(d->X, N, h.Ppad, rpb, amax);
+      d->timer.end(st);
+      d->timer.begin(ST_UPLOAD, st);
+      gram_xunit_kernel<<<(h.Ppad + 127) / 128, 128, 0, st>>>(amax, nblocks, h.Ppad, d->xunit, xscale);
+      d->timer.end(st);
+      d->timer.begin(ST_UPLOAD, st);
+      gram_xst_kernel<<<dim3((unsigned)((d->ldx + 31) / 32), (h.Ppad + 31) / 32), 256, 0, st>>>(d->X, N, h.Ppad, d->ldx, xscale,
+                                                                                            d->XsT);
+      d->timer.end(st);
+      // heavy-tail guard (kernels_gram_mma.cuh): columns whose bound is set by <= 8 gross outliers
+      int *tail_part = nullptr, *tail = nullptr;
+      CK(g_pool.alloc((void**)&tail_part, (size_t)nblocks * h.Ppad * sizeof(int)));
+      CK(g_pool.alloc((void**)&tail, (size_t)h.Ppad * sizeof(int)));
+      d->timer.begin(ST_UPLOAD, st);
+      gram_tailcount_partial_kernel<<<nblocks, 256, 0, st>>>(d->X, N, h.Ppad, rpb, d->xunit, tail_part);
+      d->timer.end(st);
+      d->timer.begin(ST_UPLOAD, st);
+      gram_tailcount_final_kernel<<<(h.Ppad + 127) / 128, 128, 0, st>>>(tail_part, nblocks, h.Ppad, tail);
+      d->timer.end(st);
+      CK(cudaGetLastError());
+      std::vector<int> tail_host(h.Ppad);
+      CK(cudaMemcpyAsync(tail_host.data(), tail, (size_t)h.Ppad * sizeof(int), cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      g_pool.release(amax);
+      g_pool.release(xscale);
+      g_pool.release(tail_part);
+      g_pool.release(tail);
+      bool heavy = false;
+      for (int p = 0; p < h.Ppad; ++p) heavy |= h.col_lv[p] >= 0 && tail_host[p] >= 1 && tail_host[p] <= 8;
+      if (heavy) {  // fp64 kernels for this data (second moments and column sums); the sign vote falls back too
+        g_pool.release(d->XsT);
+        g_pool.release(d->xunit);
+        d->XsT = nullptr; d->xunit = nullptr;
+        trace("heavy-tailed column: fp64 second moments");
+      } else {
+        if (!umma::make_map_2d(&d->map_xs, d->XsT, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, (uint64_t)N, (uint64_t)h.Ppad,
+                               (uint64_t)d->ldx * 8, GM_STAGE_ROWS, 8, CU_TENSOR_MAP_SWIZZLE_NONE))
+          return fail(PLSPM_ERR_CUDA, "cuTensorMapEncodeTiled failed (Gram operands)");
+        d->gram_mma = true;
+        d->i8_colsum = true;  // (the int8 multiplicities of a batch are built for this route)
+        trace("pre-scaled transposed copy");
+      }
+      gram_heavy_tail = heavy;
+    }
     // integer digit planes for the tensor-core column sums (PLSPM_COLSUM=fp64 keeps the fp64 kernel)
-    static const bool colsum_fp64 = getenv("PLSPM_COLSUM") && std::string(getenv("PLSPM_COLSUM")) == "fp64";
-    if (!colsum_fp64 && N >= 4096 && N < ((int64_t)1 << 31) - 16) {
+    static const bool colsum_fp64 = (getenv("PLSPM_COLSUM") && std::string(getenv("PLSPM_COLSUM")) == "fp64") || gram_env == "fp64";
+    if (!d->gram_mma && !gram_heavy_tail && !colsum_fp64 && N >= 4096 && N < ((int64_t)1 << 31) - 16) {
       if (!d->blas) {
         d->blas = blas_acquire(dev);
         if (!d->blas) return fail(PLSPM_ERR_CUDA, "cublasCreate failed");
@@ -493,6 +561,10 @@ void plspm_data_destroy(plspm_data* d) {
   if (d->mu) g_pool.release(d->mu);
   if (d->Xh) g_pool.release(d->Xh);
   if (d->XhT) g_pool.release(d->XhT);
+  if (d->XsT) g_pool.release(d->XsT);
+  if (d->xunit) g_pool.release(d->xunit);
+  if (d->gm_tiles) g_pool.release(d->gm_tiles);
+  if (d->gm_outs) g_pool.release(d->gm_outs);
   if (d->Xf) g_pool.release(d->Xf);
   if (d->inv_sd) g_pool.release(d->inv_sd);
   if (d->D8) g_pool.release(d->D8);
@@ -520,6 +592,8 @@ struct StreamPlan {  // one streaming pass over X (Gram tiles or cross-moment ti
 };
 struct BatchPlan {
   StreamPlan gram, cross;
+  int gm_ksplit = 1, gm_rows = 0, gm_groups = 1;  // tcgen05 integer Gram: row ranges, rows per range, 512-replicate groups
+  int64_t gm_nb_pad = 0;
   int cs_chunks = 1;  // row chunks of the column-sum kernel
   int64_t cs_chunk_rows = 0;
   // criterion pass of the numeric non-metric path
@@ -585,6 +659,89 @@ static int plan_stream(const plspm_data* d, int64_t n_items, size_t extra_row_by
   return 0;
 }
 
+// M tiles and output moments of the tcgen05 integer Gram for the model's tile set (kernels_gram_mma.cuh).
+static int gm_build_tables(plspm_data* d) {
+  const plspm_model* m = d->model;
+  if (d->gm_model == m) return 0;
+  const HostModel& h = m->h;
+  std::vector<int4> tiles;
+  std::vector<GramOut> outs;
+  auto add_pair = [&](int mt_base, int j, int p, int q, int dst1, int dst2) {
+    const int T0 = (6 * j) / 128, T1 = (6 * j + 5) / 128;
+    GramOut go;
+    go.slot0 = (mt_base + T0) * GM_PAIRS_PER_TILE + (j - 21 * T0);
+    go.slot1 = T1 != T0 ? (mt_base + T1) * GM_PAIRS_PER_TILE + (j - 21 * T1) : -1;
+    go.p = p; go.q = q; go.dst1 = dst1; go.dst2 = dst2;
+    outs.push_back(go);
+  };
+  for (int t = 0; t < h.n_tiles; ++t) {
+    const int sa = h.tile_sa[t], sb = h.tile_sb[t];
+    const int base = (int)tiles.size();
+    if (sa != sb) {
+      for (int T = 0; T < 3; ++T) tiles.push_back(make_int4(GM_KIND_OFF, T, sa, sb));
+      for (int r = 0; r < SLOT; ++r)
+        for (int c = 0; c < SLOT; ++c) {
+          const int p = sa * SLOT + r, q = sb * SLOT + c;
+          if (h.col_lv[p] < 0 || h.col_lv[q] < 0) continue;  // padding columns: their moments stay 0
+          add_pair(base, r * SLOT + c, p, q, t * TILE + r * SLOT + c, -1);
+        }
+    } else {
+      for (int T = 0; T < 2; ++T) tiles.push_back(make_int4(GM_KIND_DIAG, T, sa, sa));
+      int j = 0;
+      for (int r = 0; r < SLOT; ++r)
+        for (int c = r; c < SLOT; ++c, ++j) {
+          const int p = sa * SLOT + r, q = sa * SLOT + c;
+          if (h.col_lv[p] < 0 || h.col_lv[q] < 0) continue;
+          add_pair(base, j, p, q, t * TILE + r * SLOT + c, r != c ? t * TILE + c * SLOT + r : -1);
+        }
+    }
+  }
+  for (int sa = 0; sa < h.ns; sa += 2) {  // column sums, two slots per M tile
+    const int sb = sa + 1 < h.ns ? sa + 1 : sa;
+    const int base = (int)tiles.size();
+    tiles.push_back(make_int4(GM_KIND_SUM2, 0, sa, sb));
+    for (int j = 0; j < 2 * SLOT; ++j) {
+      if (j >= SLOT && sb == sa) break;
+      const int p = (j < SLOT ? sa : sb) * SLOT + (j & 7);
+      if (h.col_lv[p] < 0) continue;
+      add_pair(base, j, p, -1, p, -1);
+    }
+  }
+  if (d->gm_tiles) g_pool.release(d->gm_tiles);
+  if (d->gm_outs) g_pool.release(d->gm_outs);
+  d->gm_tiles = nullptr; d->gm_outs = nullptr; d->gm_model = nullptr;
+  CK(g_pool.alloc((void**)&d->gm_tiles, tiles.size() * sizeof(int4)));
+  CK(g_pool.alloc((void**)&d->gm_outs, outs.size() * sizeof(GramOut)));
+  CK(cudaMemcpyAsync(d->gm_tiles, tiles.data(), tiles.size() * sizeof(int4), cudaMemcpyHostToDevice, d->stream));
+  CK(cudaMemcpyAsync(d->gm_outs, outs.data(), outs.size() * sizeof(GramOut), cudaMemcpyHostToDevice, d->stream));
+  CK(cudaStreamSynchronize(d->stream));  // (pageable host vectors)
+  d->gm_n_tiles = (int)tiles.size();
+  d->gm_n_outs = (int)outs.size();
+  d->gm_model = m;
+  return 0;
+}
+static int gm_count_tiles(const HostModel& h) {
+  int n = (h.ns + 1) / 2;
+  for (int t = 0; t < h.n_tiles; ++t) n += h.tile_sa[t] != h.tile_sb[t] ? 3 : 2;
+  return n;
+}
+// row ranges of the integer Gram: among the splits with at most 24 ranges the one whose CTA count fills whole waves best
+static void gm_plan(const plspm_data* d, int64_t nb, BatchPlan& bp) {
+  const int n_mtiles = gm_count_tiles(d->model->h);
+  bp.gm_groups = (int)((nb + 511) / 512);
+  bp.gm_nb_pad = (nb + 31) / 32 * 32;
+  const int64_t tiles0 = (int64_t)n_mtiles * bp.gm_groups;
+  double best = 1e300;
+  for (int k = 1; k <= 24; ++k) {
+    const int64_t rows = ((d->N + k - 1) / k + GM_STAGE_ROWS - 1) / GM_STAGE_ROWS * GM_STAGE_ROWS;
+    if ((int64_t)k * rows - d->N >= rows && k > 1) continue;  // an empty last range
+    // the partial moments of every range are kept until the recombination: at most 1 GB of them
+    if (k > 1 && (double)k * n_mtiles * GM_PAIRS_PER_TILE * bp.gm_nb_pad * sizeof(longlong2) > 1.0e9) break;
+    const double cost = (double)((tiles0 * k + d->sm_count - 1) / d->sm_count) * (double)(rows + 1024);
+    if (cost < best * 0.97) { best = cost; bp.gm_ksplit = k; bp.gm_rows = (int)rows; }  // (prefer fewer partial buffers)
+  }
+}
+
 static int plan_batch(const plspm_data* d, int64_t nb, BatchPlan& bp) {
   const HostModel& h = d->model->h;
   if (int rc = plan_stream(d, nb * h.n_tg, 0, 0, bp.gram)) return rc;
@@ -593,6 +750,7 @@ static int plan_batch(const plspm_data* d, int64_t nb, BatchPlan& bp) {
     if (int rc = plan_stream(d, nb * h.n_tg_cross, per_row, 8 * per_row, bp.cross)) return rc;
   }
   plan_colsum(d, nb, bp);
+  if (d->gram_mma) gm_plan(d, nb, bp);
   if (d->model->numeric) {
     int nsl_pad = 1;
     while (nsl_pad * SLOT < h.kmax) nsl_pad <<= 1;
@@ -631,7 +789,7 @@ struct BatchBuffers {
   // numeric non-metric path: per-replicate iteration state
   size_t num_a, num_co, num_cn, num_so, num_sn, num_meta, num_done, num_cpart, num_cmain;
   // tensor-core column sums: int8 multiplicities, int32 digit sums, overflow flag
-  size_t c8, s32, ovf, zs32, zchunk;
+  size_t c8, s32, ovf, zs32, zchunk, gm_part;
 };
 static BatchBuffers layout_batch(const plspm_data* d, int64_t nb, const BatchPlan& bp, bool with_counts, bool with_idx,
                                  bool rows_on_device_of_caller, bool single_fit, bool want_scores) {
@@ -666,7 +824,8 @@ static BatchBuffers layout_batch(const plspm_data* d, int64_t nb, const BatchPla
   b.num_done = take(8);
   const bool i8 = d->i8_colsum && with_counts;
   b.c8 = take(i8 ? (size_t)nb * d->Npad : 0);
-  b.s32 = take(i8 ? (size_t)nb * I8_DIGITS * h.Ppad * sizeof(int32_t) : 0);
+  b.s32 = take(i8 && !d->gram_mma ? (size_t)nb * I8_DIGITS * h.Ppad * sizeof(int32_t) : 0);
+  b.gm_part = take(i8 && d->gram_mma ? (size_t)bp.gm_ksplit * gm_count_tiles(h) * GM_PAIRS_PER_TILE * bp.gm_nb_pad * sizeof(longlong2) : 0);
   b.ovf = take(8);
   b.zs32 = take(i8 && d->n_zcols ? (size_t)nb * I8_DIGITS * d->n_zcols * sizeof(int32_t) : 0);
   b.zchunk = take(i8 && d->n_zcols && !d->Z8 ? (size_t)I8_DIGITS * d->n_zcols * d->z_chunk_rows : 0);
@@ -768,6 +927,35 @@ static int launch_moments(plspm_data* d, int64_t nb, const uint32_t* counts_dev,
     counts8_kernel<<<d->sm_count * 8, 256, 0, st>>>(counts_dev, d->N, d->Npad, nb, c8, (int*)(base + bb.ovf));
     d->timer.end(st);
     CK(cudaGetLastError());
+  }
+  if (i8 && d->gram_mma) {
+    // tcgen05 integer Gram: Gram tiles AND column sums of the batch in one kernel + the fp64 recombination
+    if (int rc = gm_build_tables(d)) return rc;
+    GramMmaParams gp;
+    gp.mtiles = d->gm_tiles; gp.part = (longlong2*)(base + bb.gm_part);
+    gp.nb = nb; gp.nb_pad = bp.gm_nb_pad; gp.N = d->N;
+    gp.n_mtiles = d->gm_n_tiles; gp.n_groups = (int)((nb + 511) / 512); gp.ksplit = bp.gm_ksplit; gp.rows_per_cta = bp.gm_rows;
+    CUtensorMap map_c8;
+    if (!umma::make_map_2d(&map_c8, c8, CU_TENSOR_MAP_DATA_TYPE_UINT8, (uint64_t)d->Npad, (uint64_t)nb, (uint64_t)d->Npad,
+                           GM_STAGE_ROWS, 256, CU_TENSOR_MAP_SWIZZLE_128B))
+      return fail(PLSPM_ERR_CUDA, "cuTensorMapEncodeTiled failed (multiplicities)");
+    const int64_t g_stride = (int64_t)h.n_tiles * TILE;
+    CK(cudaMemsetAsync(D(bb.G), 0, (size_t)nb * g_stride * 8, st));
+    CK(cudaMemsetAsync(D(bb.colsum), 0, (size_t)nb * h.Ppad * 8, st));
+    const int64_t grid = (int64_t)gp.n_mtiles * gp.n_groups * gp.ksplit;
+    if (grid > 0x7fffffff) return fail(PLSPM_ERR_UNSUPPORTED, "batch too large for one launch");
+    CK(cudaFuncSetAttribute(gram_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gm_smem_bytes()));
+    d->timer.begin(ST_GRAM_I8, st);
+    gram_mma_kernel<<<(unsigned)grid, GM_THREADS, gm_smem_bytes(), st>>>(map_c8, d->map_xs, gp);
+    d->timer.end(st);
+    CK(cudaGetLastError());
+    d->timer.begin(ST_GRAM_I8, st);
+    gram_finalize_kernel<<<d->sm_count * 8, 256, 0, st>>>(gp.part, nb, gp.nb_pad, gp.n_mtiles * GM_PAIRS_PER_TILE, gp.ksplit,
+                                                          (const GramOut*)d->gm_outs, d->gm_n_outs, d->xunit, (double)d->N,
+                                                          g_stride, D(bb.G), h.Ppad, D(bb.colsum));
+    d->timer.end(st);
+    CK(cudaGetLastError());
+    return 0;
   }
   bool gram_done = false;
   if (i8 && d->n_zcols && d->z_model == d->model) {
@@ -1106,7 +1294,10 @@ int plspm_bootstrap(const plspm_model* m, plspm_data* d, int32_t scheme, double 
   const bool vote = !h.full && !m->numeric;
   const size_t per_rep = (size_t)N * 4 + ((size_t)h.n_tiles * TILE + (vote ? (size_t)h.n_cross * TILE : 0) +
                                           (m->numeric ? 6 : 2) * h.Ppad + h.ws_doubles + n_out) * 8 +
-                         (idx ? (size_t)N * 4 : 0) + (d->i8_colsum ? (size_t)d->Npad + I8_DIGITS * ((size_t)h.Ppad + d->n_zcols) * 4 : 0) + 64;
+                         (idx ? (size_t)N * 4 : 0) +
+                         (d->gram_mma ? (size_t)d->Npad + (size_t)gm_count_tiles(h) * GM_PAIRS_PER_TILE * sizeof(longlong2) * 3 +
+                                            (vote ? (size_t)h.L * h.Ppad * 4 : 0)
+                                      : d->i8_colsum ? (size_t)d->Npad + I8_DIGITS * ((size_t)h.Ppad + d->n_zcols) * 4 : 0) + 64;
   // the planes of a chunk are regenerated for every batch in streaming mode: large batches amortise that
   const size_t ws_budget = d->n_zcols && !d->Z8 ? (size_t)12 << 30 : (size_t)1536 << 20;
   int64_t nb_max = std::max<int64_t>(1, (int64_t)(ws_budget / per_rep));
@@ -1114,7 +1305,10 @@ int plspm_bootstrap(const plspm_model* m, plspm_data* d, int32_t scheme, double 
   nb_max = std::min<int64_t>(nb_max, rep_count);
   const int64_t wave = (int64_t)d->sm_count * GRAM_WARPS;  // warp items per wave
   const int64_t items_per_rep = vote ? std::max(h.n_tg, h.n_tg_cross) : h.n_tg;
-  if (nb_max * items_per_rep > wave) {
+  if (d->gram_mma) {
+    // tensor-core kernels: CTAs own 512 (Gram) / 128 (sign vote) replicates; row ranges even out the waves
+    if (nb_max >= 512) nb_max = nb_max / 512 * 512;
+  } else if (nb_max * items_per_rep > wave) {
     int64_t waves = nb_max * items_per_rep / wave;
     nb_max = std::max<int64_t>(1, waves * wave / items_per_rep);
   }

@@ -416,10 +416,10 @@ def test_tensor_core_gram_route_is_fp64_accurate(eng, mode, scheme):
         np.testing.assert_allclose(rows[b], ref, rtol=1e-10, atol=1e-12)
 
 
-def test_streaming_pair_planes_and_fp64_route_agree(tmp_path):
-    """Models whose pair-product planes exceed the memory budget generate them per row chunk per batch; with
-    PLSPM_I8_GRAM_GB=0 the fp64 Gram kernel is used.  Both must reproduce the resident-plane result (the switches
-    are read once per process, hence the subprocesses)."""
+def test_gram_routes_agree(tmp_path):
+    """Second moments of a batch: the tcgen05 integer Gram with on-the-fly digits (default), round 1's resident /
+    streamed digit planes + library GEMM (PLSPM_GRAM=cublas) and the fp64 kernels (PLSPM_GRAM=fp64) must agree
+    (the switches are read once per process, hence the subprocesses)."""
     import subprocess
     import sys
     script = tmp_path / "run.py"
@@ -438,17 +438,42 @@ def test_streaming_pair_planes_and_fp64_route_agree(tmp_path):
         "print('gram', prof['gram'][1], 'gram_i8', prof['gram_i8'][1], int((status == 0).sum()))\n"
         % (os.path.join(ROOT, "plspm-python_b200"), ROOT))
     outs = {}
-    for tag, env in (("resident", {}), ("stream", {"PLSPM_I8_GRAM_GB": "0.000001", "PLSPM_I8_CHUNK_GB": "0.000001"}),
-                     ("fp64", {"PLSPM_I8_GRAM_GB": "0"})):
+    for tag, env in (("mma", {}), ("resident", {"PLSPM_GRAM": "cublas"}),
+                     ("stream", {"PLSPM_GRAM": "cublas", "PLSPM_I8_GRAM_GB": "0.000001", "PLSPM_I8_CHUNK_GB": "0.000001"}),
+                     ("fp64", {"PLSPM_GRAM": "fp64"})):
         out = tmp_path / (tag + ".npy")
         r = subprocess.run([sys.executable, str(script), str(out)], env={**os.environ, **env}, capture_output=True,
                            text=True, timeout=600)
         assert r.returncode == 0, r.stderr[-2000:]
         words = r.stdout.split()
         outs[tag] = (np.load(out), int(words[1]), int(words[3]), int(words[4]))
+    assert outs["mma"][1] == 0 and outs["mma"][2] == 2                    # gram_mma_kernel + gram_finalize_kernel
     assert outs["resident"][1] == 0 and outs["resident"][2] == 2          # one GEMM + one combine
     assert outs["stream"][1] == 0 and outs["stream"][2] == 3 * 6            # 6 chunks of 4096 rows: generate, GEMM, combine
     assert outs["fp64"][1] >= 1 and outs["fp64"][2] == 0
-    assert outs["resident"][3] == outs["stream"][3] == outs["fp64"][3] == 12
+    assert outs["mma"][3] == outs["resident"][3] == outs["stream"][3] == outs["fp64"][3] == 12
     np.testing.assert_allclose(outs["stream"][0], outs["resident"][0], rtol=1e-12, atol=1e-14)
     np.testing.assert_allclose(outs["fp64"][0], outs["resident"][0], rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(outs["mma"][0], outs["fp64"][0], rtol=1e-10, atol=1e-12)
+
+
+@pytest.mark.parametrize("outlier,integer_route", ((1.0e3, True), (1.0e6, False)))
+def test_integer_gram_and_outlier_columns(eng, outlier, integer_route):
+    """The integer Gram rounds every pair product to 2^-47 of the product of the two COLUMN BOUNDS.  A moderate
+    outlier (1000 sd) costs nothing visible; a column whose bound is set by a few gross outliers (1e6 sd) would
+    lose the variance of replicates that miss them (measured 4e-6 on the weights), so the upload detects it
+    (heavy-tail guard) and the fp64 kernels take over.  Either way the rows match the oracle at 1e-6."""
+    N, L, K = 8192, 5, 4
+    X, path = make_synthetic(N, L, K, 31)
+    X[1234, 6] = outlier    # one outlier in a column of unit scale
+    X[:, 13] *= 1.0e-5      # and a column of tiny scale
+    model = eng.Model([K] * L, [0] * L, path, True)
+    data = eng.Data(model, X)
+    eng.profile_reset()
+    rows, status, iters = eng.bootstrap(model, data, "centroid", 0, 6, seed=11)
+    prof = eng.profile_get()
+    assert (prof["gram_i8"][1] > 0) == integer_route and (prof["gram"][1] > 0) == (not integer_route), prof
+    for b in range(6):
+        ref, it, st = orc.replicate_row(X, orc.philox_indices(11, b, N), [K] * L, [0] * L, path, "centroid", True)
+        assert status[b] == st == 0 and iters[b] == it
+        np.testing.assert_allclose(rows[b], ref, rtol=REL, atol=1e-9)
