@@ -34,12 +34,12 @@ for p in (ROOT, os.path.join(ROOT, "plspm-python_b200")):
 
 WORKLOADS = {
     # name: (N, L, K, mode, scheme, replicates per GPU per step, description)
-    "c3": (100_000, 32, 8, 0, "centroid", 1184,
+    "c3": (100_000, 32, 8, 0, "centroid", 1536,
            "synthetic N=100k, 32 LVs x 8 MVs (P=256), Mode A, centroid, bootstrap (north-star headline config)"),
-    "c3f": (100_000, 32, 8, 0, "factorial", 1184, "synthetic N=100k, 32 LVs x 8 MVs, Mode A, factorial, bootstrap"),
-    "c4": (100_000, 32, 8, 1, "path", 1184, "synthetic N=100k, 32 LVs x 8 MVs, Mode B, path scheme, bootstrap"),
-    "c5": (1_000_000, 64, 16, 0, "centroid", 1184, "synthetic N=1M, 64 LVs x 16 MVs (P=1024), Mode A, centroid, bootstrap"),
-    "c3n": (100_000, 32, 8, 0, "centroid", 1184,
+    "c3f": (100_000, 32, 8, 0, "factorial", 1536, "synthetic N=100k, 32 LVs x 8 MVs, Mode A, factorial, bootstrap"),
+    "c4": (100_000, 32, 8, 1, "path", 1536, "synthetic N=100k, 32 LVs x 8 MVs, Mode B, path scheme, bootstrap"),
+    "c5": (1_000_000, 64, 16, 0, "centroid", 512, "synthetic N=1M, 64 LVs x 16 MVs (P=1024), Mode A, centroid, bootstrap"),
+    "c3n": (100_000, 32, 8, 0, "centroid", 1536,
             "synthetic N=100k, 32 LVs x 8 MVs, Scale.NUM (non-metric estimator), Mode A, centroid, bootstrap"),
     "c2": (250, 6, 0, 0, "centroid", 1000, "satisfaction 250x27, 6 LVs, Mode A, centroid, 1000 resamples (latency-bound)"),
 }

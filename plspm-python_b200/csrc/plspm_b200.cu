@@ -94,19 +94,20 @@ struct plspm_data {
   bool fast_vote = false;    // the fp16 pass is worth trying on this data
   // fused tcgen05 sign vote (kernels_vote_mma.cuh): xh transposed (K-major B operand) + TMA tensor maps
   // tcgen05 integer Gram (kernels_gram_mma.cuh): pre-scaled transposed fp64 copy, M-tile and output tables
-  double* XsT = nullptr;     // [Ppad][ldx]  x' = x~ 2^(23 - e_p)
+  int2* XsT = nullptr;       // [Ppad][ldx]  x' = x~ 2^(23 - e_p) as {rint(x'), fp32 bits of the remainder}
   double* xunit = nullptr;   // [Ppad] 2^(e_p - 23)
   int64_t ldx = 0;
   bool gram_mma = false;
-  CUtensorMap map_xs;
   int4* gm_tiles = nullptr;  // [gm_n_tiles]
   void* gm_outs = nullptr;   // GramOut [gm_n_outs]
   int gm_n_tiles = 0, gm_n_outs = 0;
   const plspm_model* gm_model = nullptr;
-  __half* XhT = nullptr;     // [Ppad][ldt]
-  int64_t ldt = 0;
+  uint8_t* xt_img = nullptr;  // XhT tile images [chunk of 64 rows][column chunk of 256] 32 KB (vote_xt_image_kernel)
+  uint8_t* xl_img = nullptr;  // block-column images [chunk][K = 16 block] 2 KB (vote_xl_image_kernel)
+  int* lv_blk = nullptr;      // [L] first K = 16 block of every LV
+  int vm_n_blocks = 0;
+  int64_t n_chunks64 = 0;     // chunks of 64 rows
   bool mma_vote = false;
-  CUtensorMap map_xt, map_xh;
   // exact integer digit planes of x~ for the tensor-core column sums (see digits_kernel)
   int8_t* D8 = nullptr;      // [I8_DIGITS * Ppad][Npad]
   double* dscale = nullptr;  // [Ppad] value of one unit of the least significant digit
@@ -347,33 +348,46 @@ int plspm_data_create(const plspm_model* m, const double* X, int64_t N, int64_t 
       double* sq = nullptr;
       CK(g_pool.alloc((void**)&sq, (size_t)nblocks * h.Ppad * sizeof(double)));
       CK(g_pool.alloc((void**)&d->inv_sd, (size_t)h.Ppad * sizeof(double)));
-      CK(g_pool.alloc((void**)&d->Xh, (size_t)N * h.Ppad * sizeof(__half)));
       d->timer.begin(ST_UPLOAD, st);
       colsq_partial_kernel<<<nblocks, 256, 0, st>>>(d->X, N, h.Ppad, rpb, sq);
       d->timer.end(st);
       d->timer.begin(ST_UPLOAD, st);
       inv_sd_kernel<<<(h.Ppad + 127) / 128, 128, 0, st>>>(sq, nblocks, h.Ppad, N, d->inv_sd);
       d->timer.end(st);
-      d->timer.begin(ST_UPLOAD, st);
-      make_half_kernel<<<d->sm_count * 8, 256, 0, st>>>(d->X, N, h.Ppad, d->inv_sd, d->Xh);
-      d->timer.end(st);
       // fused tcgen05 vote (default): blocks of at most 64 manifest variables (four K = 16 score steps)
-      if (fused_ok && N < ((int64_t)1 << 31) - 64) {
-        d->ldt = (N + 63) / 64 * 64;
-        CK(g_pool.alloc((void**)&d->XhT, (size_t)h.Ppad * d->ldt * sizeof(__half)));
+      if (fused_ok && N < ((int64_t)1 << 31) - 256) {
+        // operand images of the fused vote kernel (kernels_vote_mma.cuh): what its producer fetches with linear bulk copies
+        d->n_chunks64 = (N + 63) / 64;
+        const int n_pchunks = (h.Ppad + 255) / 256;
+        std::vector<int> blk_col, lv_blk(h.L);
+        for (int l = 0; l < h.L; ++l) {
+          lv_blk[l] = (int)blk_col.size();
+          for (int q = 0; q < (h.lv_k[l] + 15) / 16; ++q) blk_col.push_back(h.lv_off[l] + 16 * q);
+        }
+        d->vm_n_blocks = (int)blk_col.size();
+        int* blk_col_dev = nullptr;
+        CK(g_pool.alloc((void**)&blk_col_dev, blk_col.size() * sizeof(int)));
+        CK(g_pool.alloc((void**)&d->lv_blk, lv_blk.size() * sizeof(int)));
+        CK(cudaMemcpyAsync(blk_col_dev, blk_col.data(), blk_col.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d->lv_blk, lv_blk.data(), lv_blk.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+        CK(g_pool.alloc((void**)&d->xt_img, (size_t)d->n_chunks64 * n_pchunks * VM_XT_BYTES));
+        CK(g_pool.alloc((void**)&d->xl_img, (size_t)d->n_chunks64 * d->vm_n_blocks * VM_XL_BYTES));
         d->timer.begin(ST_UPLOAD, st);
-        make_half_t_kernel<<<dim3((unsigned)((d->ldt + 31) / 32), (h.Ppad + 31) / 32), 256, 0, st>>>(d->X, N, h.Ppad, d->ldt,
-                                                                                               d->inv_sd, d->XhT);
+        vote_xt_image_kernel<<<d->sm_count * 16, 256, 0, st>>>(d->X, N, h.Ppad, n_pchunks, d->n_chunks64, d->inv_sd, d->xt_img);
+        d->timer.end(st);
+        d->timer.begin(ST_UPLOAD, st);
+        vote_xl_image_kernel<<<d->sm_count * 8, 256, 0, st>>>(d->X, N, h.Ppad, d->vm_n_blocks, d->n_chunks64, blk_col_dev, d->inv_sd,
+                                                              d->xl_img);
         d->timer.end(st);
         CK(cudaGetLastError());
-        const int np_box = std::min(256, (h.Ppad + 15) / 16 * 16);
-        if (!umma::make_map_2d(&d->map_xt, d->XhT, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (uint64_t)N, (uint64_t)h.Ppad,
-                               (uint64_t)d->ldt * 2, VM_CHUNK, (uint32_t)np_box, CU_TENSOR_MAP_SWIZZLE_128B) ||
-            !umma::make_map_2d(&d->map_xh, d->Xh, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (uint64_t)h.Ppad, (uint64_t)N,
-                               (uint64_t)h.Ppad * 2, 16, VM_CHUNK, CU_TENSOR_MAP_SWIZZLE_32B))
-          return fail(PLSPM_ERR_CUDA, "cuTensorMapEncodeTiled failed (sign-vote operands)");
+        CK(cudaStreamSynchronize(st));  // (pageable host vectors above)
+        g_pool.release(blk_col_dev);
         d->mma_vote = true;
       } else {  // legacy route: fp32 score generation + library fp16 GEMM
+        CK(g_pool.alloc((void**)&d->Xh, (size_t)N * h.Ppad * sizeof(__half)));
+        d->timer.begin(ST_UPLOAD, st);
+        make_half_kernel<<<d->sm_count * 8, 256, 0, st>>>(d->X, N, h.Ppad, d->inv_sd, d->Xh);
+        d->timer.end(st);
         CK(g_pool.alloc((void**)&d->Xf, (size_t)N * h.Ppad * sizeof(float)));
         d->timer.begin(ST_UPLOAD, st);
         make_float_kernel<<<d->sm_count * 8, 256, 0, st>>>(d->X, N * h.Ppad, d->Xf);
@@ -408,7 +422,7 @@ int plspm_data_create(const plspm_model* m, const double* X, int64_t N, int64_t 
       CK(g_pool.alloc((void**)&amax, (size_t)nblocks * h.Ppad * sizeof(double)));
       CK(g_pool.alloc((void**)&xscale, (size_t)h.Ppad * sizeof(double)));
       CK(g_pool.alloc((void**)&d->xunit, (size_t)h.Ppad * sizeof(double)));
-      CK(g_pool.alloc((void**)&d->XsT, (size_t)h.Ppad * d->ldx * sizeof(double)));
+      CK(g_pool.alloc((void**)&d->XsT, (size_t)h.Ppad * d->ldx * sizeof(int2)));
       d->timer.begin(ST_UPLOAD, st);
       colabsmax_partial_kernel<<<nblocks, 256, 0, st>>>(d->X, N, h.Ppad, rpb, amax);
       d->timer.end(st);
@@ -445,9 +459,6 @@ int plspm_data_create(const plspm_model* m, const double* X, int64_t N, int64_t 
         d->XsT = nullptr; d->xunit = nullptr;
         trace("heavy-tailed column: fp64 second moments");
       } else {
-        if (!umma::make_map_2d(&d->map_xs, d->XsT, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, (uint64_t)N, (uint64_t)h.Ppad,
-                               (uint64_t)d->ldx * 8, GM_STAGE_ROWS, 8, CU_TENSOR_MAP_SWIZZLE_NONE))
-          return fail(PLSPM_ERR_CUDA, "cuTensorMapEncodeTiled failed (Gram operands)");
         d->gram_mma = true;
         d->i8_colsum = true;  // (the int8 multiplicities of a batch are built for this route)
         trace("pre-scaled transposed copy");
@@ -560,7 +571,9 @@ void plspm_data_destroy(plspm_data* d) {
   if (d->X) g_pool.release(d->X);
   if (d->mu) g_pool.release(d->mu);
   if (d->Xh) g_pool.release(d->Xh);
-  if (d->XhT) g_pool.release(d->XhT);
+  if (d->xt_img) g_pool.release(d->xt_img);
+  if (d->xl_img) g_pool.release(d->xl_img);
+  if (d->lv_blk) g_pool.release(d->lv_blk);
   if (d->XsT) g_pool.release(d->XsT);
   if (d->xunit) g_pool.release(d->xunit);
   if (d->gm_tiles) g_pool.release(d->gm_tiles);
@@ -707,6 +720,7 @@ static int gm_build_tables(plspm_data* d) {
       add_pair(base, j, p, -1, p, -1);
     }
   }
+  while (tiles.size() % 4) tiles.push_back(make_int4(GM_KIND_NONE, 0, 0, 0));  // whole clusters of up to 4 M tiles
   if (d->gm_tiles) g_pool.release(d->gm_tiles);
   if (d->gm_outs) g_pool.release(d->gm_outs);
   d->gm_tiles = nullptr; d->gm_outs = nullptr; d->gm_model = nullptr;
@@ -723,7 +737,7 @@ static int gm_build_tables(plspm_data* d) {
 static int gm_count_tiles(const HostModel& h) {
   int n = (h.ns + 1) / 2;
   for (int t = 0; t < h.n_tiles; ++t) n += h.tile_sa[t] != h.tile_sb[t] ? 3 : 2;
-  return n;
+  return (n + 3) / 4 * 4;
 }
 // row ranges of the integer Gram: among the splits with at most 24 ranges the one whose CTA count fills whole waves best
 static void gm_plan(const plspm_data* d, int64_t nb, BatchPlan& bp) {
@@ -789,7 +803,7 @@ struct BatchBuffers {
   // numeric non-metric path: per-replicate iteration state
   size_t num_a, num_co, num_cn, num_so, num_sn, num_meta, num_done, num_cpart, num_cmain;
   // tensor-core column sums: int8 multiplicities, int32 digit sums, overflow flag
-  size_t c8, s32, ovf, zs32, zchunk, gm_part;
+  size_t c8, c8img, c8vote, s32, ovf, zs32, zchunk, gm_part;
 };
 static BatchBuffers layout_batch(const plspm_data* d, int64_t nb, const BatchPlan& bp, bool with_counts, bool with_idx,
                                  bool rows_on_device_of_caller, bool single_fit, bool want_scores) {
@@ -823,7 +837,11 @@ static BatchBuffers layout_batch(const plspm_data* d, int64_t nb, const BatchPla
   b.num_meta = take(numeric ? (size_t)nb * 16 : 0);
   b.num_done = take(8);
   const bool i8 = d->i8_colsum && with_counts;
-  b.c8 = take(i8 ? (size_t)nb * d->Npad : 0);
+  b.c8 = take(i8 && !d->gram_mma ? (size_t)nb * d->Npad : 0);  // plain [nb][Npad] (digit-plane GEMMs of round 1)
+  // tile images of the multiplicities for the tensor-core kernels: [stage of 128 rows][group of 512 replicates] 64 KB
+  b.c8img = take(i8 && d->gram_mma ? (size_t)((d->N + 127) / 128) * ((nb + 511) / 512) * 65536 : 0);
+  // ... and for the fused sign vote: [chunk of 64 rows][tile of 128 replicates] 8 KB
+  b.c8vote = take(i8 && d->mma_vote && !h.full && !d->model->numeric ? (size_t)((d->N + 63) / 64) * ((nb + 127) / 128) * 8192 : 0);
   b.s32 = take(i8 && !d->gram_mma ? (size_t)nb * I8_DIGITS * h.Ppad * sizeof(int32_t) : 0);
   b.gm_part = take(i8 && d->gram_mma ? (size_t)bp.gm_ksplit * gm_count_tiles(h) * GM_PAIRS_PER_TILE * bp.gm_nb_pad * sizeof(longlong2) : 0);
   b.ovf = take(8);
@@ -922,9 +940,16 @@ static int launch_moments(plspm_data* d, int64_t nb, const uint32_t* counts_dev,
   auto D = [&](size_t o) { return (double*)(base + o); };
   const bool i8 = d->i8_colsum && counts_dev;
   int8_t* c8 = (int8_t*)(base + bb.c8);
-  if (i8) {
+  if (i8 && !d->gram_mma) {
     d->timer.begin(ST_COLSUM, st);
     counts8_kernel<<<d->sm_count * 8, 256, 0, st>>>(counts_dev, d->N, d->Npad, nb, c8, (int*)(base + bb.ovf));
+    d->timer.end(st);
+    CK(cudaGetLastError());
+  }
+  if (i8 && d->gram_mma) {
+    d->timer.begin(ST_COLSUM, st);
+    counts8_image_kernel<<<d->sm_count * 16, 256, 0, st>>>(counts_dev, d->N, nb, (int)((nb + 511) / 512), (d->N + 127) / 128,
+                                                           (uint8_t*)(base + bb.c8img), (int*)(base + bb.ovf));
     d->timer.end(st);
     CK(cudaGetLastError());
   }
@@ -935,10 +960,13 @@ static int launch_moments(plspm_data* d, int64_t nb, const uint32_t* counts_dev,
     gp.mtiles = d->gm_tiles; gp.part = (longlong2*)(base + bb.gm_part);
     gp.nb = nb; gp.nb_pad = bp.gm_nb_pad; gp.N = d->N;
     gp.n_mtiles = d->gm_n_tiles; gp.n_groups = (int)((nb + 511) / 512); gp.ksplit = bp.gm_ksplit; gp.rows_per_cta = bp.gm_rows;
-    CUtensorMap map_c8;
-    if (!umma::make_map_2d(&map_c8, c8, CU_TENSOR_MAP_DATA_TYPE_UINT8, (uint64_t)d->Npad, (uint64_t)nb, (uint64_t)d->Npad,
-                           GM_STAGE_ROWS, 256, CU_TENSOR_MAP_SWIZZLE_128B))
-      return fail(PLSPM_ERR_CUDA, "cuTensorMapEncodeTiled failed (multiplicities)");
+    gp.XsT = d->XsT; gp.ldx = d->ldx;
+    gp.c8img = (const uint8_t*)(base + bb.c8img);
+    static const bool gstats = getenv("PLSPM_KERNEL_STATS") != nullptr;
+    static unsigned long long* gstats_dev = nullptr;
+    if (gstats && !gstats_dev) CK(cudaMalloc((void**)&gstats_dev, 16 * 8));
+    if (gstats) CK(cudaMemsetAsync(gstats_dev, 0, 16 * 8, st));
+    gp.stats = gstats ? gstats_dev : nullptr;
     const int64_t g_stride = (int64_t)h.n_tiles * TILE;
     CK(cudaMemsetAsync(D(bb.G), 0, (size_t)nb * g_stride * 8, st));
     CK(cudaMemsetAsync(D(bb.colsum), 0, (size_t)nb * h.Ppad * 8, st));
@@ -946,9 +974,19 @@ static int launch_moments(plspm_data* d, int64_t nb, const uint32_t* counts_dev,
     if (grid > 0x7fffffff) return fail(PLSPM_ERR_UNSUPPORTED, "batch too large for one launch");
     CK(cudaFuncSetAttribute(gram_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gm_smem_bytes()));
     d->timer.begin(ST_GRAM_I8, st);
-    gram_mma_kernel<<<(unsigned)grid, GM_THREADS, gm_smem_bytes(), st>>>(map_c8, d->map_xs, gp);
+    gram_mma_kernel<<<(unsigned)grid, GM_THREADS, gm_smem_bytes(), st>>>(gp);
     d->timer.end(st);
     CK(cudaGetLastError());
+    if (gstats) {
+      unsigned long long hs[16];
+      CK(cudaStreamSynchronize(st));
+      CK(cudaMemcpy(hs, gstats_dev, sizeof(hs), cudaMemcpyDeviceToHost));
+      const double ns = (double)std::max<unsigned long long>(hs[9], 1), nc = (double)grid;
+      fprintf(stderr, "[gram_mma] grid %lld, stages/CTA %.0f | per stage: issuer loop %.0f clk (waits: c8 tile %.0f, digits %.0f); "
+              "producer waits %.0f; generator loop %.0f (operand wait %.0f + digits %.0f, buffer wait %.0f) | epilogue %.0f clk per CTA\n",
+              (long long)grid, ns / nc, hs[0] / ns, hs[2] / ns, hs[3] / ns, hs[1] / ns, hs[6] / ns, hs[8] / ns, (hs[5] - hs[8]) / ns,
+              hs[4] / ns, hs[7] / nc);
+    }
     d->timer.begin(ST_GRAM_I8, st);
     gram_finalize_kernel<<<d->sm_count * 8, 256, 0, st>>>(gp.part, nb, gp.nb_pad, gp.n_mtiles * GM_PAIRS_PER_TILE, gp.ksplit,
                                                           (const GramOut*)d->gm_outs, d->gm_n_outs, d->xunit, (double)d->N,
@@ -1136,36 +1174,54 @@ static int run_batch(plspm_data* d, int64_t nb, const uint32_t* counts_dev, cons
       float* Cf = (float*)(base + bb.Cf);
       const int64_t ldl = (nb + 7) / 8 * 8;
       VoteMmaParams vp;
-      vp.wf = D(bb.wf); vp.inv_sd = d->inv_sd; vp.lv_off = m->dv.lv_off; vp.lv_k = m->dv.lv_k; vp.Cf = Cf;
+      vp.wf = D(bb.wf); vp.inv_sd = d->inv_sd; vp.lv_off = m->dv.lv_off; vp.lv_k = m->dv.lv_k; vp.lv_blk = d->lv_blk; vp.Cf = Cf;
+      vp.xt_img = d->xt_img; vp.xl_img = d->xl_img; vp.c8_img = (const uint8_t*)(base + bb.c8vote);
+      vp.n_blocks = d->vm_n_blocks; vp.n_rep_tiles_img = (int)((nb + 127) / 128);
+      d->timer.begin(ST_COLSUM, st);
+      vote_c8_image_kernel<<<d->sm_count * 16, 256, 0, st>>>(counts_dev, d->N, nb, vp.n_rep_tiles_img, d->n_chunks64,
+                                                             (uint8_t*)(base + bb.c8vote));
+      d->timer.end(st);
+      CK(cudaGetLastError());
       vp.nb = nb; vp.ldl = ldl; vp.N = d->N; vp.L = h.L; vp.Ppad = h.Ppad;
-      vp.n_rep_tiles = (int)((nb + 127) / 128);
       vp.n_pchunks = (h.Ppad + 255) / 256;
       vp.k16_max = std::max(1, (h.kmax + 15) / 16);
-      vp.np_box = std::min(256, (h.Ppad + 15) / 16 * 16);
+      vp.n_rep_tiles = (int)((nb + 127) / 128);
       // row ranges: at most VM_MAX_ROWS rows per accumulator (truncating fp32 accumulation); among the admissible
       // splits take the one whose CTA count fills whole waves best
       const int64_t tiles0 = (int64_t)vp.n_rep_tiles * h.L * vp.n_pchunks;
       const int kmin = (int)((d->N + VM_MAX_ROWS - 1) / VM_MAX_ROWS);
       double best = 1e300;
       for (int k = kmin; k <= kmin + 24; ++k) {
-        const int64_t rows = ((d->N + k - 1) / k + VM_CHUNK - 1) / VM_CHUNK * VM_CHUNK;
-        if ((int64_t)k * rows - d->N >= rows && k > kmin) continue;  // an empty last range
+        const int64_t rows = ((d->N + k - 1) / k + VM_STAGE_ROWS - 1) / VM_STAGE_ROWS * VM_STAGE_ROWS;
+        if (rows > VM_MAX_ROWS || ((int64_t)k * rows - d->N >= rows && k > kmin)) continue;  // too long / an empty last range
         const double cost = (double)((tiles0 * k + d->sm_count - 1) / d->sm_count) * (double)(rows + 768);
         if (cost < best) { best = cost; vp.ksplit = k; vp.rows_per_cta = (int)rows; }
       }
-      CUtensorMap map_c8;
-      if (!umma::make_map_2d(&map_c8, base + bb.c8, CU_TENSOR_MAP_DATA_TYPE_UINT8, (uint64_t)d->Npad, (uint64_t)nb,
-                             (uint64_t)d->Npad, VM_CHUNK, 128, CU_TENSOR_MAP_SWIZZLE_64B))
-        return fail(PLSPM_ERR_CUDA, "cuTensorMapEncodeTiled failed (multiplicities)");
+      // PLSPM_KERNEL_STATS=1: cycles every role of the kernel spent waiting on each barrier (printed per launch)
+      static const bool kstats = getenv("PLSPM_KERNEL_STATS") != nullptr;
+      static unsigned long long* kstats_dev = nullptr;
+      if (kstats && !kstats_dev) CK(cudaMalloc((void**)&kstats_dev, 16 * 8));
+      if (kstats) CK(cudaMemsetAsync(kstats_dev, 0, 16 * 8, st));
+      vp.stats = kstats ? kstats_dev : nullptr;
       const size_t vm_smem = vm_smem_bytes(vp.k16_max);
       CK(cudaFuncSetAttribute(vote_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vm_smem));
       CK(cudaMemsetAsync(Cf, 0, (size_t)ldl * h.L * h.Ppad * sizeof(float), st));
       const int64_t grid = tiles0 * vp.ksplit;
       if (grid > 0x7fffffff) return fail(PLSPM_ERR_UNSUPPORTED, "batch too large for one launch");
       d->timer.begin(ST_CROSS, st);
-      vote_mma_kernel<<<(unsigned)grid, VM_THREADS, vm_smem, st>>>(d->map_xt, d->map_xh, map_c8, vp);
+      vote_mma_kernel<<<(unsigned)grid, VM_THREADS, vm_smem, st>>>(vp);
       d->timer.end(st);
       CK(cudaGetLastError());
+      if (kstats) {
+        unsigned long long hs[16];
+        CK(cudaStreamSynchronize(st));
+        CK(cudaMemcpy(hs, kstats_dev, sizeof(hs), cudaMemcpyDeviceToHost));
+        const double nc = (double)std::max<unsigned long long>(hs[9], 1);
+        fprintf(stderr, "[vote_mma] grid %lld, chunks/CTA %.0f | per chunk: score issuer %.0f clk, vote issuer %.0f clk; waits: "
+                "producer(empty) %.0f, vote issuer a_full %.0f, score issuer full %.0f d1_empty %.0f, epilogue (per own chunk) "
+                "d1_full %.0f a_free %.0f\n", (long long)grid, nc / (double)grid, hs[0] / nc, hs[8] / nc, hs[1] / nc, hs[2] / nc,
+                hs[3] / nc, hs[4] / nc, 2.0 * hs[5] / nc, 2.0 * hs[7] / nc);
+      }
       b.fast_cross = Cf; b.inv_sd = d->inv_sd; b.fast_nb = ldl; b.fast_uncentred = 1;
     } else if (use_fast) {
       // legacy tensor-core sign vote: E[p][b][l] = sum_i xh_ip * fp16(c_bi t_bil), fp32 accumulate, in chunks
@@ -1299,15 +1355,20 @@ int plspm_bootstrap(const plspm_model* m, plspm_data* d, int32_t scheme, double 
                                             (vote ? (size_t)h.L * h.Ppad * 4 : 0)
                                       : d->i8_colsum ? (size_t)d->Npad + I8_DIGITS * ((size_t)h.Ppad + d->n_zcols) * 4 : 0) + 64;
   // the planes of a chunk are regenerated for every batch in streaming mode: large batches amortise that
-  const size_t ws_budget = d->n_zcols && !d->Z8 ? (size_t)12 << 30 : (size_t)1536 << 20;
+  const size_t ws_budget = d->n_zcols && !d->Z8 ? (size_t)12 << 30 : d->gram_mma ? (size_t)3 << 30 : (size_t)1536 << 20;
   int64_t nb_max = std::max<int64_t>(1, (int64_t)(ws_budget / per_rep));
   if (getenv("PLSPM_MAX_BATCH")) nb_max = std::max<int64_t>(1, std::min<int64_t>(nb_max, atoll(getenv("PLSPM_MAX_BATCH"))));
   nb_max = std::min<int64_t>(nb_max, rep_count);
   const int64_t wave = (int64_t)d->sm_count * GRAM_WARPS;  // warp items per wave
   const int64_t items_per_rep = vote ? std::max(h.n_tg, h.n_tg_cross) : h.n_tg;
   if (d->gram_mma) {
-    // tensor-core kernels: CTAs own 512 (Gram) / 128 (sign vote) replicates; row ranges even out the waves
+    // tensor-core kernels: CTAs own 512 (Gram) / 128 (sign vote) replicates and row ranges even out the waves.
+    // Batches of equal size (no small tail batch), whole 128-replicate tiles where the run is large enough.
     if (nb_max >= 512) nb_max = nb_max / 512 * 512;
+    const int64_t n_batches = (rep_count + nb_max - 1) / nb_max;
+    int64_t even = (rep_count + n_batches - 1) / n_batches;
+    if (even >= 128) even = (even + 127) / 128 * 128;
+    nb_max = std::min(nb_max, even);
   } else if (nb_max * items_per_rep > wave) {
     int64_t waves = nb_max * items_per_rep / wave;
     nb_max = std::max<int64_t>(1, waves * wave / items_per_rep);

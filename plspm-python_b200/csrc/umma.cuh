@@ -83,6 +83,70 @@ __device__ __forceinline__ void bar_wait(uint64_t* bar, uint32_t parity, int tag
   }
 }
 
+// ---- the same primitives on precomputed 32-bit shared addresses -------------------------------------------
+// The issuing threads of the tensor-core kernels are single threads running long dependent instruction chains; ncu
+// showed them ISSUE-bound (no dominant wait, ~300 instructions per 64-row chunk): the compiler re-derives the
+// cluster-window address of every __shared__ object at each use (S2R SR_CgaCtaId + LEA) and inlines the watchdog
+// into every wait.  Hot loops therefore take their barrier / tile addresses once (s32()) and use these.
+__device__ __forceinline__ bool bar_try_a(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done != 0;
+}
+// (returns the cycles spent waiting: pipeline diagnostics, see PLSPM_KERNEL_STATS)
+__device__ __noinline__ long long bar_wait_slow_a(uint32_t bar, uint32_t parity, int tag) {
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  while (!bar_try_a(bar, parity)) {
+    if ((++spins & 0xfffu) == 0 && clock64() - t0 > 4000000000ll) bar_timeout(tag, parity);
+  }
+  return clock64() - t0;
+}
+__device__ __forceinline__ long long bar_wait_a(uint32_t bar, uint32_t parity, int tag = 0) {
+  if (!bar_try_a(bar, parity)) return bar_wait_slow_a(bar, parity, tag);
+  return 0;
+}
+__device__ __forceinline__ void bar_arrive_a(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void bar_expect_tx_a(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_a(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+               "l"(map), "r"(bar), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc_a(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+// linear bulk copy global -> shared (TMA engine, no tensor map): the operands of the tensor-core kernels are stored
+// in HBM as ready-made shared-memory tile images, so a whole tile is ONE request.  Measured (tools/umma_probe tma_bw):
+// 2-D boxes of 128-byte rows deliver 11 TB/s chip-wide whatever the pitch; linear copies 13 TB/s at 32 KB, 20 TB/s at 64 KB.
+__device__ __forceinline__ void bulk_load_a(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
+               "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void mma_commit_a(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mma_commit_mc_a(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+               : "memory");
+}
+
 // ---- TMA (cp.async.bulk.tensor), 2-D tiles -------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -94,6 +158,25 @@ __device__ __forceinline__ void tma_load_2d(void* dst_smem, const CUtensorMap* m
           s32(dst_smem)),
       "l"(map), "r"(s32(bar)), "r"(c0), "r"(c1)
       : "memory");
+}
+// the same tile delivered to the same shared-memory offset of every CTA of the cluster named in `mask`; each
+// destination's mbarrier (same offset) receives the bytes
+__device__ __forceinline__ void tma_load_2d_mc(void* dst_smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
+          s32(dst_smem)),
+      "l"(map), "r"(s32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+// ---- thread-block clusters ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 // generic-proxy writes (st.shared) that the tensor core / TMA (async proxy) will read
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -114,6 +197,13 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 // all previously issued tcgen05.mma of this thread done -> one arrival on the mbarrier
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(bar)) : "memory");
+}
+
+// ... one arrival on the mbarrier at this offset in EVERY CTA of the cluster named in `mask`
+__device__ __forceinline__ void mma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(s32(bar)),
+               "h"(mask)
+               : "memory");
 }
 
 // ---- tcgen05.mma (issued by ONE thread) ----------------------------------------------------------------

@@ -354,11 +354,115 @@ static int run_gemm(const std::string& name, const Opts& o) {
   return bad != 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// TMA delivery rate: every CTA (one per SM) keeps `depth` tile loads in flight from an L2-resident buffer.
+//   mode 0: 2-D tensor map, box = rows x 128 B, source rows `pitch` bytes apart (strided, like XhT / c8)
+//   mode 1: 1-D bulk copy of the same number of bytes from a contiguous tile
+__global__ void __launch_bounds__(128) k_tma_bw(const __grid_constant__ CUtensorMap map, const uint8_t* __restrict__ src, int mode,
+                                                int iters, uint32_t tile_bytes, int tiles_x, int tiles_y, int box_rows, int box_cols,
+                                                int depth, int waitmode, unsigned long long* cycles) {
+  extern __shared__ uint8_t bw_raw[];
+  __shared__ uint64_t full[8];
+  uint8_t* smem = bw_raw + ((1024u - (s32(bw_raw) & 1023u)) & 1023u);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 8; ++s) bar_init(&full[s], 1);
+    bar_fence_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const long long t0 = clock64();
+    const int n_tiles = tiles_x * tiles_y;
+    for (int it = 0; it < iters + depth; ++it) {
+      const int s = it % depth;
+      if (it >= depth) {
+        const uint32_t par = ((it / depth) - 1) & 1, ba = s32(&full[s]);
+        if (waitmode == 0) bar_wait(&full[s], par);
+        else if (waitmode == 1) {  // non-blocking test_wait in a spin loop
+          uint32_t done = 0;
+          while (!done)
+            asm volatile("{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                         : "=r"(done) : "r"(ba), "r"(par) : "memory");
+        } else {  // try_wait with a short suspend-time hint (ns)
+          uint32_t done = 0;
+          while (!done)
+            asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.u32 %0, 1, 0, p;\n}\n"
+                         : "=r"(done) : "r"(ba), "r"(par), "r"(20u) : "memory");
+        }
+      }
+      if (it < iters) {
+        const int tile = (int)(((long long)it * gridDim.x + blockIdx.x) % n_tiles);
+        bar_expect_tx(&full[s], tile_bytes);
+        if (mode == 0) tma_load_2d(smem + (size_t)s * tile_bytes, &map, &full[s], (tile % tiles_x) * box_cols, (tile / tiles_x) * box_rows);
+        else if (mode >= 2) {  // the tile as `mode` linear pieces on the same barrier
+          const uint32_t piece = tile_bytes / mode;
+          for (int q = 0; q < mode; ++q)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             s32(smem + (size_t)s * tile_bytes + q * piece)),
+                         "l"(src + (size_t)tile * tile_bytes + q * piece), "r"(piece), "r"(s32(&full[s]))
+                         : "memory");
+        } else
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                           s32(smem + (size_t)s * tile_bytes)),
+                       "l"(src + (size_t)tile * tile_bytes), "r"(tile_bytes), "r"(s32(&full[s]))
+                       : "memory");
+      }
+    }
+    cycles[blockIdx.x] = (unsigned long long)(clock64() - t0);
+  }
+}
+
+static int run_tma_bw(int mode, int box_rows, int row_bytes, long pitch, int depth, int swz_b, int waitmode) {
+  int sms = 0;
+  CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
+  const uint32_t tile_bytes = (uint32_t)box_rows * row_bytes;
+  // a 64 MB (L2-resident) source: rows of `pitch` bytes
+  const size_t total = (size_t)64 << 20;
+  const long rows = (long)(total / pitch);
+  const int tiles_x = (int)(pitch / row_bytes), tiles_y = (int)(rows / box_rows);
+  uint8_t* src;
+  CK(cudaMalloc(&src, total + 4096));
+  CK(cudaMemset(src, 1, total));
+  unsigned long long* cyc;
+  CK(cudaMalloc(&cyc, sms * 8));
+  CUtensorMap map;
+  memset(&map, 0, sizeof(map));
+  CUtensorMapSwizzle sw = swz_b == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : swz_b == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                          : swz_b == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
+  if (mode == 0 && !make_map_2d(&map, src, CU_TENSOR_MAP_DATA_TYPE_UINT8, (uint64_t)pitch, (uint64_t)rows, (uint64_t)pitch,
+                                (uint32_t)row_bytes, (uint32_t)box_rows, sw)) {
+    printf("tma_bw: map failed FAIL\n");
+    return 1;
+  }
+  const int iters = 2000;
+  const size_t smem = (size_t)depth * tile_bytes + 2048;
+  CK(cudaFuncSetAttribute(k_tma_bw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  k_tma_bw<<<sms, 128, smem>>>(map, src, mode, 200, tile_bytes, tiles_x, tiles_y, box_rows, row_bytes, depth, waitmode, cyc);
+  CK(cudaEventRecord(e0));
+  k_tma_bw<<<sms, 128, smem>>>(map, src, mode, iters, tile_bytes, tiles_x, tiles_y, box_rows, row_bytes, depth, waitmode, cyc);
+  CK(cudaEventRecord(e1));
+  CK(cudaDeviceSynchronize());
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  std::vector<unsigned long long> h(sms);
+  CK(cudaMemcpy(h.data(), cyc, sms * 8, cudaMemcpyDeviceToHost));
+  double mean = 0;
+  for (auto v : h) mean += (double)v / sms;
+  const double bytes = (double)sms * iters * tile_bytes;
+  printf("tma_bw mode=%d wait=%d box=%dx%dB pitch=%ld depth=%d swz=%d: %.2f TB/s, %.1f B/clk/SM, %.0f clk per tile (%u B) INFO\n", mode, waitmode, box_rows,
+         row_bytes, pitch, depth, swz_b, bytes / (ms * 1e-3) / 1e12, (double)iters * tile_bytes / mean, mean / iters, tile_bytes);
+  return 0;
+}
+
 int main(int argc, char** argv) {
   if (argc < 2) return 1;
   const std::string cmd = argv[1];
   if (cmd == "tmem") return run_tmem();
   if (cmd == "dump" && argc >= 6) return run_dump(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]));
+  if (cmd == "tma_bw" && argc >= 8)
+    return run_tma_bw(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atol(argv[5]), atoi(argv[6]), atoi(argv[7]), argc > 8 ? atoi(argv[8]) : 0);
   if (cmd == "gemm" && argc >= 3) {
     Opts o;
     for (int i = 3; i < argc; ++i) {
