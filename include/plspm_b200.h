@@ -106,9 +106,10 @@ int plspm_resample_indices(uint64_t seed, int64_t replicate, int64_t N, int32_t*
 
 /* Instrumentation of the library's own stream since the last reset: device milliseconds per
  * stage measured with CUDA events around every launch, and kernel launch counts.
- * ms[12] / launches[12]: 0 counts, 1 gram, 2 chunk reduce, 3 solve, 4 scores, 5 upload kernels, 6 column
- * sums, 7 cross moments (exact fp64 pass, or the fp16 GEMMs of the fast sign vote), 8 score generation
- * for the fast sign vote. */
+ * ms[12] / launches[12]: 0 counts (resample multiplicities), 1 gram (fp64 Gram kernel), 2 chunk reduce, 3 solve,
+ * 4 scores, 5 upload kernels, 6 column sums / int8 multiplicity images, 7 sign vote (fused tcgen05 kernel, or the
+ * exact fp64 cross-moment pass), 8 score generation (legacy vote), 9 non-metric criterion pass, 10 integer Gram
+ * (tcgen05 kernel; legacy: library GEMM + combine), 11 fp64 recombination of the integer Gram. */
 int plspm_profile_reset(void);
 int plspm_profile_get(double* ms, int64_t* launches);
 

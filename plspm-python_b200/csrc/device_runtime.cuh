@@ -18,7 +18,7 @@ static int fail(int code, const std::string& msg) {
                   std::string(#expr) + ": " + cudaGetErrorString(e_));                             \
   } while (0)
 
-enum { ST_COUNTS = 0, ST_GRAM = 1, ST_REDUCE = 2, ST_SOLVE = 3, ST_SCORES = 4, ST_UPLOAD = 5, ST_COLSUM = 6, ST_CROSS = 7, ST_SCOREGEN = 8, ST_CONV = 9, ST_GRAM_I8 = 10, ST_N = 12 };
+enum { ST_COUNTS = 0, ST_GRAM = 1, ST_REDUCE = 2, ST_SOLVE = 3, ST_SCORES = 4, ST_UPLOAD = 5, ST_COLSUM = 6, ST_CROSS = 7, ST_SCOREGEN = 8, ST_CONV = 9, ST_GRAM_I8 = 10, ST_FINALIZE = 11, ST_N = 12 };
 struct Profile {
   std::mutex mu;
   double ms[ST_N] = {0};

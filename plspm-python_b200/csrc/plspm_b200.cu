@@ -987,7 +987,7 @@ static int launch_moments(plspm_data* d, int64_t nb, const uint32_t* counts_dev,
               (long long)grid, ns / nc, hs[0] / ns, hs[2] / ns, hs[3] / ns, hs[1] / ns, hs[6] / ns, hs[8] / ns, (hs[5] - hs[8]) / ns,
               hs[4] / ns, hs[7] / nc);
     }
-    d->timer.begin(ST_GRAM_I8, st);
+    d->timer.begin(ST_FINALIZE, st);
     gram_finalize_kernel<<<d->sm_count * 8, 256, 0, st>>>(gp.part, nb, gp.nb_pad, gp.n_mtiles * GM_PAIRS_PER_TILE, gp.ksplit,
                                                           (const GramOut*)d->gm_outs, d->gm_n_outs, d->xunit, (double)d->N,
                                                           g_stride, D(bb.G), h.Ppad, D(bb.colsum));

@@ -241,7 +241,7 @@ def resample_indices(seed: int, replicate: int, N: int) -> np.ndarray:
     return out
 
 
-STAGES = ("counts", "gram", "reduce", "solve", "scores", "upload", "colsum", "cross", "scoregen", "conv", "gram_i8")
+STAGES = ("counts", "gram", "reduce", "solve", "scores", "upload", "colsum", "cross", "scoregen", "conv", "gram_i8", "finalize")
 
 
 def profile_reset():

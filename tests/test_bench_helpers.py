@@ -10,17 +10,22 @@ bench = importlib.util.module_from_spec(spec)
 spec.loader.exec_module(bench)
 
 
-def test_split_launches_separates_library_gemms():
-    # c3, 5 steps: counts 5, solve 10, colsum 3 per step (counts8 + GEMM + combine), 25 vote chunks per step
-    prof = {"counts": (3.0, 5), "solve": (5.6, 10), "colsum": (1.7, 15), "cross": (10.3, 125), "scoregen": (17.5, 125),
-            "gram_i8": (10.9, 10), "gram": (0.0, 0)}
-    assert bench.split_launches(prof, 5, 100_000, 5056) == (155, 135)
-    # small data: fp64 kernels only, no library launches
-    prof = {"counts": (0.05, 5), "gram": (0.3, 5), "reduce": (0.05, 5), "solve": (0.3, 5), "colsum": (0.3, 5)}
-    assert bench.split_launches(prof, 5, 250, 1000) == (25, 0)
-    # c5, streamed planes: generator + GEMM + combine per chunk
-    prof = {"counts": (6, 2), "solve": (40, 4), "colsum": (17, 18), "cross": (200, 490), "scoregen": (300, 490), "gram_i8": (580, 126)}
-    assert bench.split_launches(prof, 2, 1_000_000, 40704) == (590, 540)
+def test_library_launches_only_on_ab_switches(monkeypatch):
+    # default routes: both contractions are this repo's tcgen05 kernels -> no library GEMM whatever the profile says
+    prof = {"counts": (3.0, 5), "solve": (5.6, 10), "colsum": (1.7, 10), "cross": (10.3, 5), "gram_i8": (10.9, 5), "finalize": (0.9, 5)}
+    monkeypatch.delenv("PLSPM_GRAM", raising=False)
+    monkeypatch.delenv("PLSPM_VOTE", raising=False)
+    assert bench.library_launches(prof) == 0
+    # A/B switches bring cuBLAS back and the count says so
+    monkeypatch.setenv("PLSPM_VOTE", "cublas")
+    assert bench.library_launches({"cross": (10.0, 125)}) == 125
+    monkeypatch.setenv("PLSPM_GRAM", "cublas")
+    assert bench.library_launches({"gram_i8": (10.0, 10), "colsum": (1.0, 15)}) > 0
+
+
+def test_kernel_names_cover_every_stage():
+    for st in ("counts", "gram", "reduce", "solve", "scores", "upload", "colsum", "cross", "scoregen", "conv", "gram_i8", "finalize"):
+        assert st in bench.KERNEL_NAMES
 
 
 def test_cpu_workload_subsamples_large_inputs():

@@ -447,7 +447,7 @@ def test_gram_routes_agree(tmp_path):
         assert r.returncode == 0, r.stderr[-2000:]
         words = r.stdout.split()
         outs[tag] = (np.load(out), int(words[1]), int(words[3]), int(words[4]))
-    assert outs["mma"][1] == 0 and outs["mma"][2] == 2                    # gram_mma_kernel + gram_finalize_kernel
+    assert outs["mma"][1] == 0 and outs["mma"][2] == 1                    # one gram_mma_kernel launch (finalize is its own stage)
     assert outs["resident"][1] == 0 and outs["resident"][2] == 2          # one GEMM + one combine
     assert outs["stream"][1] == 0 and outs["stream"][2] == 3 * 6            # 6 chunks of 4096 rows: generate, GEMM, combine
     assert outs["fp64"][1] >= 1 and outs["fp64"][2] == 0

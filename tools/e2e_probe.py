@@ -11,13 +11,13 @@ from plspm_b200 import engine  # noqa: E402
 from plspm_b200.synth import make_synthetic  # noqa: E402
 
 engine.set_device(0)
-N, L, K, B = 100000, 32, 8, 1184
+N, L, K, B = 100000, 32, 8, 1536
 X, path = make_synthetic(N, L, K, seed=0)
 model = engine.Model([K] * L, [0] * L, path, True)
 Xp = engine.pinned_empty(X.shape)
 Xp[...] = X
 out = engine.pinned_empty((B, model.n_out))
-for r in range(4):
+for r in range(6):
     t0 = time.perf_counter()
     data = engine.Data(model, Xp)
     t1 = time.perf_counter()
