@@ -313,6 +313,18 @@ def tensor_peaks():
     return out
 
 
+def ncu_metric(stage, metric, tag="r02"):
+    """One metric of the committed ncu --set full capture of a stage's kernel (profiles/<stage>_<tag>_details.csv), or None."""
+    try:
+        for line in open(os.path.join(ROOT, "profiles", "%s_%s_details.csv" % (stage, tag))):
+            f = line.rstrip("\n").split(",")
+            if f[0] == metric:
+                return float(f[-1])
+    except Exception:
+        pass
+    return None
+
+
 KERNEL_NAMES = {
     "gram": "gram_kernel<false> (fp64 weighted Gram tiles)",
     "gram_i8": "gram_mma_kernel (tcgen05 kind::i8: multiplicities x on-the-fly 48-bit digits of the pair products)",
@@ -478,7 +490,11 @@ def run_gpu_arm(args):
         n_moments = model.n_pair_columns + P
         gram_ops = 2.0 * 6 * n_moments * reps * N * args.steps           # u8 digits x s8 multiplicities, 2 ops per MAC
         vote_ops = 2.0 * reps * len(w["blocks"]) * N * P * args.steps    # fp16 vote MMA (the score MMA adds 1/16 of it)
-        i8_peak = float(peaks.get("int8_tops", 2.0 * float(peaks.get("bf16_tflops_sustained", 1402.0))))
+        # int8 denominator: the NOMINAL dense 8-bit tensor peak (B200_PROFILING.md: 4.5 P op/s).  MEASURED_PEAKS.json has bf16
+        # only, and the library int8 GEMM measured by tools/tc_peak.py (2.7 P sustained / 3.3 P burst) is SLOWER than this
+        # kernel, so it cannot serve as a peak; it is reported beside it (int8_library_tops).
+        i8_lib = float(peaks.get("int8_tops", 2.0 * float(peaks.get("bf16_tflops_sustained", 1402.0))))
+        i8_peak = 4500.0
         f16_peak = float(peaks.get("fp16_tflops", peaks.get("bf16_tflops_sustained", 1402.0)))
         mma_route = model.n_pair_columns > 0 and os.environ.get("PLSPM_GRAM") not in ("cublas", "fp64") and gram_ms > 0
         if top == "cross" and not model.full_tiles:
@@ -486,7 +502,7 @@ def run_gpu_arm(args):
                     "peak_source": "measured fp16 library GEMM (profiles/measured_tc_peaks.json), else MEASURED_PEAKS.json bf16 sustained"}
         elif top == "gram_i8" and mma_route:
             roof = {"bound": "tensor", "achieved": gram_ops / (gram_ms / 1e3) / 1e12, "peak": i8_peak, "unit": "TFLOP/s",
-                    "peak_source": "measured int8 library GEMM in TOP/s (profiles/measured_tc_peaks.json), else 2 x bf16 sustained of MEASURED_PEAKS.json"}
+                    "peak_source": "NOMINAL dense 8-bit tensor peak, T op/s (B200_PROFILING.md); the measured library int8 GEMM (int8_library_tops, tools/tc_peak.py) is slower than this kernel"}
         else:
             roof = {"bound": "hbm", "achieved": survey_gbs, "peak": peak_hbm, "unit": "GB/s", "peak_source": peak_src}
         roof["frac"] = roof["achieved"] / roof["peak"] if roof["peak"] else None
@@ -496,7 +512,8 @@ def run_gpu_arm(args):
             "kernel_launch_ms": top_ms / max(top_n, 1), "kernel_launches": top_n,
             "gram_int8_tops": gram_ops / (gram_ms / 1e3) / 1e12 if mma_route else None,
             "vote_fp16_tflops": vote_ops / (vote_ms / 1e3) / 1e12 if vote_ms > 0 and not model.full_tiles else None,
-            "int8_peak_tops": i8_peak, "fp16_peak_tflops": f16_peak,
+            "int8_peak_tops": i8_peak, "int8_library_tops": i8_lib, "fp16_peak_tflops": f16_peak,
+            "tensor_pipe_active_pct_ncu": ncu_metric(top, "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"),
             "hbm": {"frac_hw": frac_hw, "dram_bytes_per_step": step_traffic or None, "peak": peak_hbm, "peak_source": peak_src,
                     "survey_8d_achieved_gbs": survey_gbs, "survey_8d_frac": survey_gbs / peak_hbm,
                     "algorithmic_bytes_per_step": alg_bytes / args.steps,

@@ -70,6 +70,7 @@ struct DevPool {
         }
       }
     }
+    ++misses;
     cudaError_t e = cudaMalloc(out, bytes);
     if (e != cudaSuccess) {  // release the cache and retry once
       trim();
@@ -92,6 +93,7 @@ struct DevPool {
           free_blocks.push_back(b);
           cached += b.bytes;
         } else {
+          ++evictions;
           cudaFree(p);
         }
         return;
@@ -105,6 +107,7 @@ struct DevPool {
     cached = 0;
   }
   std::vector<Block> sizes;  // live blocks handed out
+  std::atomic<int64_t> misses{0}, evictions{0};  // cudaMalloc / cudaFree calls the cache did not absorb (PLSPM_TRACE)
 };
 static DevPool g_pool;
 

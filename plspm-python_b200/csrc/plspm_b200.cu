@@ -281,13 +281,14 @@ int plspm_data_create(const plspm_model* m, const double* X, int64_t N, int64_t 
   d->model = m;
   d->N = N;
   int dev = 0;
-  cudaDeviceProp prop;
-  if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
+  // (two attribute queries, not cudaGetDeviceProperties: that call costs 2.5 ms -- and now and then 40 ms -- and
+  //  plspm_bootstrap_host creates a data handle per call)
+  if (cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&d->sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&d->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) {
     delete d;
     return fail(PLSPM_ERR_CUDA, "no CUDA device: plspm_b200 has no CPU path");
   }
-  d->sm_count = prop.multiProcessorCount;
-  d->max_smem = (int)prop.sharedMemPerBlockOptin;
   auto bail = [&](int rc) { plspm_data_destroy(d); return rc; };
   static const bool tracing = getenv("PLSPM_TRACE") != nullptr;
   const auto t_begin = std::chrono::steady_clock::now();
@@ -1440,11 +1441,25 @@ int plspm_bootstrap(const plspm_model* m, plspm_data* d, int32_t scheme, double 
 int plspm_bootstrap_host(const plspm_model* m, const double* X, int64_t N, int64_t ld, int32_t scheme, double tol,
                          int32_t max_iter, int64_t rep_begin, int64_t rep_count, uint64_t seed, const int32_t* idx,
                          double* out, int32_t* status, int32_t* iters) {
+  static const bool trace = getenv("PLSPM_TRACE") != nullptr;
+  const auto t0 = std::chrono::steady_clock::now();
+  const int64_t miss0 = g_pool.misses.load(), ev0 = g_pool.evictions.load();
   plspm_data* d = nullptr;
   int rc = plspm_data_create(m, X, N, ld, 0, &d);
   if (rc) return rc;
+  const auto t1 = std::chrono::steady_clock::now();
   rc = plspm_bootstrap(m, d, scheme, tol, max_iter, rep_begin, rep_count, seed, idx, out, 0, status, iters);
+  const auto t2 = std::chrono::steady_clock::now();
   plspm_data_destroy(d);
+  if (trace) {
+    const auto t3 = std::chrono::steady_clock::now();
+    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+      return std::chrono::duration<double, std::milli>(b - a).count();
+    };
+    fprintf(stderr, "[plspm trace] bootstrap_host: create %.2f ms, bootstrap %.2f ms, destroy %.2f ms; pool misses %lld evictions %lld cached %.2f GB\n",
+            ms(t0, t1), ms(t1, t2), ms(t2, t3), (long long)(g_pool.misses.load() - miss0), (long long)(g_pool.evictions.load() - ev0),
+            (double)g_pool.cached / 1073741824.0);
+  }
   return rc;
 }
 

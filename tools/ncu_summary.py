@@ -31,29 +31,47 @@ def raw_rows(path):
     return list(csv.reader(io.StringIO(text)))
 
 
+STAGE_OF = (("gram_mma_kernel", "gram_i8"), ("vote_mma_kernel", "cross"), ("gram_finalize_kernel", "finalize"), ("solve_kernel", "solve"),
+            ("counts8_image_kernel", "colsum"), ("vote_c8_image_kernel", "colsum_vote"), ("counts_kernel", "counts"),
+            ("gram_kernel", "gram"), ("reduce_chunks_kernel", "reduce"), ("scoregen_kernel", "scoregen"))
+
+
+def num(v, u):
+    return float(v.replace(",", "")) * UNIT.get(u, 1.0)
+
+
 def main():
+    """stage=report pairs name the stage of the LAST launch in each report; a bare report path holds several kernels and
+    the last launch of each known kernel name is taken (STAGE_OF)."""
     tag, workload, reps = sys.argv[1], sys.argv[2], int(sys.argv[3])
     tp = os.path.join(ROOT, "profiles", "kernel_traffic.json")
     table = json.load(open(tp)) if os.path.exists(tp) else {}
     entry = {"_replicates_per_launch": reps, "_tag": tag}
+    picked = {}
     for spec in sys.argv[4:]:
-        stage, path = spec.split("=", 1)
+        stage, path = spec.split("=", 1) if "=" in spec else (None, spec)
         rows = raw_rows(path)
-        hdr, units, vals = rows[0], rows[1], rows[-1]
-        rec = {h: (v, u) for h, u, v in zip(hdr, units, vals)}
+        hdr, units = rows[0], rows[1]
+        kcol = hdr.index("Kernel Name")
+        for vals in rows[2:]:
+            st = stage
+            if st is None:
+                st = next((s_ for k_, s_ in STAGE_OF if vals[kcol].startswith(k_)), None)
+            if st:
+                picked[st] = {h: (v, u) for h, u, v in zip(hdr, units, vals)}
+    for stage, rec in sorted(picked.items()):
         with open(os.path.join(ROOT, "profiles", "%s_%s_details.csv" % (stage, tag)), "w") as f:
             f.write("metric,unit,value\n")
-            f.write("kernel,,%s\n" % rec.get("Kernel Name", ("?", ""))[0].replace(",", ";"))
-            for k in hdr:
-                if any(k == m or k.startswith(m) for m in KEEP) or "stalled" in k and "per_issue_active" in k:
+            f.write("kernel,,%s\n" % rec["Kernel Name"][0].replace(",", ";"))
+            for k in rec:
+                if any(k == m or k.startswith(m) for m in KEEP) or ("stalled" in k and "per_warp_active" in k):
                     f.write("%s,%s,%s\n" % (k, rec[k][1], rec[k][0]))
-        tot = 0.0
-        for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-            v, u = rec[k]
-            tot += float(v.replace(",", "")) * UNIT.get(u, 1.0)
+        tot = sum(num(*rec[k]) for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
         entry[stage] = tot
-        print(stage, rec.get("Kernel Name", ("?",))[0][:60], "dram bytes per launch %.3e" % tot, "duration", rec["gpu__time_duration.sum"])
-    table[workload] = {**table.get(workload, {}), **entry}
+        print("%-12s %-50s dram %.3e B/launch  %s %s" % (stage, rec["Kernel Name"][0][:50], tot, rec["gpu__time_duration.sum"][0], rec["gpu__time_duration.sum"][1]))
+    if "colsum_vote" in entry:  # both image builders run under the bench stage "colsum"
+        entry["colsum"] = entry.get("colsum", 0.0) + entry.pop("colsum_vote")
+    table[workload] = entry
     json.dump(table, open(tp, "w"), indent=1, sort_keys=True)
 
 
