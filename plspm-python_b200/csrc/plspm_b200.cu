@@ -126,6 +126,7 @@ struct plspm_data {
   Workspace ws;          // grown on demand, reused across calls
   StageTimer timer;
   int sm_count = 148;
+  bool img_ready = false;  // the multiplicity images of the batch in flight were written by resample_images_kernel
   int max_smem = 227 * 1024;
 };
 
@@ -947,7 +948,7 @@ static int launch_moments(plspm_data* d, int64_t nb, const uint32_t* counts_dev,
     d->timer.end(st);
     CK(cudaGetLastError());
   }
-  if (i8 && d->gram_mma) {
+  if (i8 && d->gram_mma && !d->img_ready) {
     d->timer.begin(ST_COLSUM, st);
     counts8_image_kernel<<<d->sm_count * 16, 256, 0, st>>>(counts_dev, d->N, nb, (int)((nb + 511) / 512), (d->N + 127) / 128,
                                                            (uint8_t*)(base + bb.c8img), (int*)(base + bb.ovf));
@@ -1178,11 +1179,13 @@ static int run_batch(plspm_data* d, int64_t nb, const uint32_t* counts_dev, cons
       vp.wf = D(bb.wf); vp.inv_sd = d->inv_sd; vp.lv_off = m->dv.lv_off; vp.lv_k = m->dv.lv_k; vp.lv_blk = d->lv_blk; vp.Cf = Cf;
       vp.xt_img = d->xt_img; vp.xl_img = d->xl_img; vp.c8_img = (const uint8_t*)(base + bb.c8vote);
       vp.n_blocks = d->vm_n_blocks; vp.n_rep_tiles_img = (int)((nb + 127) / 128);
-      d->timer.begin(ST_COLSUM, st);
-      vote_c8_image_kernel<<<d->sm_count * 16, 256, 0, st>>>(counts_dev, d->N, nb, vp.n_rep_tiles_img, d->n_chunks64,
-                                                             (uint8_t*)(base + bb.c8vote));
-      d->timer.end(st);
-      CK(cudaGetLastError());
+      if (!d->img_ready) {
+        d->timer.begin(ST_COLSUM, st);
+        vote_c8_image_kernel<<<d->sm_count * 16, 256, 0, st>>>(counts_dev, d->N, nb, vp.n_rep_tiles_img, d->n_chunks64,
+                                                               (uint8_t*)(base + bb.c8vote));
+        d->timer.end(st);
+        CK(cudaGetLastError());
+      }
       vp.nb = nb; vp.ldl = ldl; vp.N = d->N; vp.L = h.L; vp.Ppad = h.Ppad;
       vp.n_pchunks = (h.Ppad + 255) / 256;
       vp.k16_max = std::max(1, (h.kmax + 15) / 16);
@@ -1386,16 +1389,42 @@ int plspm_bootstrap(const plspm_model* m, plspm_data* d, int32_t scheme, double 
     // a short last batch reuses the plan (and therefore the workspace layout) of a full one
     uint32_t* cnt = (uint32_t*)(base + bb.counts);
     int32_t* idx_dev = nullptr;
-    CK(cudaMemsetAsync(cnt, 0, (size_t)nb * N * 4, st));
     if (idx) {
       idx_dev = (int32_t*)(base + bb.idx);
       CK(cudaMemcpyAsync(idx_dev, idx + b0 * N, (size_t)nb * N * 4, cudaMemcpyHostToDevice, st));
     }
-    const int64_t threads = ((N + 3) / 4) * nb;
-    d->timer.begin(ST_COUNTS, st);
-    counts_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(cnt, idx_dev, N, nb, rep_begin + b0, seed);
-    d->timer.end(st);
-    CK(cudaGetLastError());
+    // the [nb x N] uint32 multiplicity table: what the fp64 kernels, the legacy routes and the exact redo read.  The
+    // tensor-core routes take their int8 tile images straight from resample_images_kernel and never build it.
+    bool have_counts = false;
+    auto ensure_counts = [&]() -> int {
+      if (have_counts) return 0;
+      CK(cudaMemsetAsync(cnt, 0, (size_t)nb * N * 4, st));
+      const int64_t threads = ((N + 3) / 4) * nb;
+      d->timer.begin(ST_COUNTS, st);
+      counts_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(cnt, idx_dev, N, nb, rep_begin + b0, seed);
+      d->timer.end(st);
+      CK(cudaGetLastError());
+      have_counts = true;
+      return 0;
+    };
+    static const bool counts_split = getenv("PLSPM_COUNTS") && std::string(getenv("PLSPM_COUNTS")) == "split";
+    d->img_ready = false;
+    if (!counts_split && !m->numeric && d->gram_mma && d->i8_colsum && (!vote || (d->mma_vote && d->fast_vote))) {
+      const int64_t n_pad = (N + 127) / 128 * 128;
+      const int64_t n_ranges = (n_pad + RI_MAX_ROWS - 1) / RI_MAX_ROWS;
+      const int64_t range_rows = ((n_pad + n_ranges - 1) / n_ranges + 127) / 128 * 128;
+      const int n_groups = (int)((nb + 511) / 512);
+      CK(cudaFuncSetAttribute(resample_images_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)range_rows));
+      d->timer.begin(ST_COUNTS, st);
+      resample_images_kernel<<<dim3((unsigned)n_groups * 512, (unsigned)n_ranges), RI_THREADS, (size_t)range_rows, st>>>(
+          idx_dev, N, nb, rep_begin + b0, seed, range_rows, n_groups, vote ? (int)((nb + 127) / 128) : 0, d->n_chunks64,
+          (uint8_t*)(base + bb.c8img), (uint8_t*)(base + bb.c8vote), (int*)(base + bb.ovf));
+      d->timer.end(st);
+      CK(cudaGetLastError());
+      d->img_ready = true;
+    } else if (int rc = ensure_counts()) {
+      return rc;
+    }
     double* rows = out_is_device ? out + (size_t)b0 * n_out : (double*)(base + bb.out);
     for (int attempt = 0; attempt < 2; ++attempt) {
       if (m->numeric) {
@@ -1411,6 +1440,8 @@ int plspm_bootstrap(const plspm_model* m, plspm_data* d, int32_t scheme, double 
       if (!ovf) break;
       CK(cudaMemsetAsync(base + bb.ovf, 0, 8, st));
       d->i8_colsum = false;
+      d->img_ready = false;
+      if (int rc = ensure_counts()) return rc;
     }
     if (vote && d->fast_vote) {
       // replicates whose low-precision sign vote was undecided are redone with exact fp64 cross moments
@@ -1423,6 +1454,7 @@ int plspm_bootstrap(const plspm_model* m, plspm_data* d, int32_t scheme, double 
       if (!redo.empty()) {
         int* map_dev = (int*)(base + bb.rep_map);
         CK(cudaMemcpyAsync(map_dev, redo.data(), redo.size() * 4, cudaMemcpyHostToDevice, st));
+        if (int rc = ensure_counts()) return rc;
         if (int rc = redo_exact(d, (int64_t)redo.size(), map_dev, cnt, bb, scheme, tol, max_iter, bp, rows)) return rc;
         g_redo_count += (int64_t)redo.size();
         if ((int64_t)redo.size() * 2 > nb) d->fast_vote = false;  // this data does not suit the fp16 vote
@@ -1434,6 +1466,7 @@ int plspm_bootstrap(const plspm_model* m, plspm_data* d, int32_t scheme, double 
     if (status) CK(cudaMemcpyAsync(status + b0, base + bb.status, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     d->timer.collect();
+    d->img_ready = false;
   }
   return PLSPM_OK;
 }

@@ -438,7 +438,7 @@ def test_gram_routes_agree(tmp_path):
         "print('gram', prof['gram'][1], 'gram_i8', prof['gram_i8'][1], int((status == 0).sum()))\n"
         % (os.path.join(ROOT, "plspm-python_b200"), ROOT))
     outs = {}
-    for tag, env in (("mma", {}), ("resident", {"PLSPM_GRAM": "cublas"}),
+    for tag, env in (("mma", {}), ("split", {"PLSPM_COUNTS": "split"}), ("resident", {"PLSPM_GRAM": "cublas"}),
                      ("stream", {"PLSPM_GRAM": "cublas", "PLSPM_I8_GRAM_GB": "0.000001", "PLSPM_I8_CHUNK_GB": "0.000001"}),
                      ("fp64", {"PLSPM_GRAM": "fp64"})):
         out = tmp_path / (tag + ".npy")
@@ -455,6 +455,58 @@ def test_gram_routes_agree(tmp_path):
     np.testing.assert_allclose(outs["stream"][0], outs["resident"][0], rtol=1e-12, atol=1e-14)
     np.testing.assert_allclose(outs["fp64"][0], outs["resident"][0], rtol=1e-10, atol=1e-12)
     np.testing.assert_allclose(outs["mma"][0], outs["fp64"][0], rtol=1e-10, atol=1e-12)
+    # multiplicity images written straight by resample_images_kernel (default) vs uint32 table + two image builders
+    assert np.array_equal(outs["mma"][0], outs["split"][0])
+
+
+def test_fused_multiplicity_images_over_several_row_ranges(eng):
+    """More rows than one CTA's shared memory holds as bytes (204800): the replicate's draws are scanned once per row range."""
+    N, L, K = 2 * 204800 + 333, 3, 3
+    X, path = make_synthetic(N, L, K, 43)
+    model = eng.Model([K] * L, [0] * L, path, True)
+    data = eng.Data(model, X)
+    eng.profile_reset()
+    rows, status, iters = eng.bootstrap(model, data, "centroid", 11, 3, seed=9)
+    prof = eng.profile_get()
+    assert prof["gram_i8"][1] == 1 and prof["gram"][1] == 0 and prof["colsum"][1] == 0, prof
+    for b in (0, 2):
+        idx = orc.philox_indices(9, 11 + b, N)
+        ref, it, st = orc.replicate_row(X, idx, [K] * L, [0] * L, path, "centroid", True)
+        assert status[b] == st == 0 and iters[b] == it
+        np.testing.assert_allclose(rows[b], ref, rtol=1e-6, atol=1e-9)
+
+
+def test_fused_multiplicity_images_with_user_indices_and_overflow(eng):
+    """resample_images_kernel counts a replicate's draws as packed bytes in shared memory: user-supplied indices take
+    the same kernel, rows at the image padding edge (N not a multiple of 64 / 128) must land right, and a row drawn
+    more than 127 times is flagged before its byte can carry -- the batch is then redone on the fp64 route."""
+    N, L, K = 8192 + 77, 4, 5
+    X, path = make_synthetic(N, L, K, 41)
+    model = eng.Model([K] * L, [0] * L, path, True)
+    data = eng.Data(model, X)
+    rng = np.random.default_rng(5)
+    idx = rng.integers(0, N, size=(5, N)).astype(np.int32)
+    idx[1, :300] = N - 1            # 300 copies of the last row: above the int8 range, and past 255
+    idx[3, 1000:1100] = 4242        # 100 copies: fits
+    eng.profile_reset()
+    rows, status, iters = eng.bootstrap(model, data, "centroid", 0, 5, idx=idx)
+    prof = eng.profile_get()
+    assert prof["gram_i8"][1] == 1 and prof["gram"][1] >= 1, prof   # tensor-core attempt, then the fp64 redo
+    for b in range(5):
+        ref, it, st = orc.replicate_row(X, idx[b], [K] * L, [0] * L, path, "centroid", True)
+        assert status[b] == st == 0 and iters[b] == it
+        np.testing.assert_allclose(rows[b], ref, rtol=1e-6, atol=1e-9)
+    # without the overflow the batch stays on the tensor-core route (a fresh handle: the fallback is sticky per handle)
+    data = eng.Data(model, X)
+    idx[1, :300] = rng.integers(0, N, size=300)
+    eng.profile_reset()
+    rows, status, iters = eng.bootstrap(model, data, "centroid", 0, 5, idx=idx)
+    prof = eng.profile_get()
+    assert prof["gram_i8"][1] == 1 and prof["gram"][1] == 0 and prof["colsum"][1] == 0, prof
+    for b in range(5):
+        ref, it, st = orc.replicate_row(X, idx[b], [K] * L, [0] * L, path, "centroid", True)
+        assert status[b] == st == 0 and iters[b] == it
+        np.testing.assert_allclose(rows[b], ref, rtol=1e-6, atol=1e-9)
 
 
 @pytest.mark.parametrize("outlier,integer_route", ((1.0e3, True), (1.0e6, False)))
