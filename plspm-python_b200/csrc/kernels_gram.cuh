@@ -448,8 +448,15 @@ __global__ void reduce_chunks_kernel(const double* __restrict__ part, int64_t nr
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     const int64_t b = e / per_rep, k = e - b * per_rep;
     const double* src = part + (b * n_chunks) * per_rep + k;
-    double s = 0.0;
-    for (int c = 0; c < n_chunks; ++c) s += src[(int64_t)c * per_rep];
-    out[e] = s;
+    // eight independent chains (eight loads in flight per thread: a single fit has few outputs and ~100 chunks,
+    // one dependent chain made this kernel pure load latency), combined in a fixed order
+    double a[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    int c = 0;
+    for (; c + 8 <= n_chunks; c += 8) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) a[u] += src[(int64_t)(c + u) * per_rep];
+    }
+    for (int u = 0; c < n_chunks; ++c, ++u) a[u] += src[(int64_t)c * per_rep];
+    out[e] = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
   }
 }

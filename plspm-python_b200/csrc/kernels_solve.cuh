@@ -13,6 +13,7 @@ struct SolveBatch {
   double N;
   int scheme; double tol; int max_iter;
   double* ws;
+  double* state; int64_t state_stride; int resume;  // phase 1 -> phases 2 / 3 (see SolveArgs::state)
   int phase;                             // see SolveArgs::phase
   double* wf;                            // [nrep][Ppad] (sparse tile sets)
   const double* cross; int64_t cross_stride;
@@ -45,6 +46,8 @@ __global__ void __launch_bounds__(SOLVE_THREADS) solve_kernel(const SolveBatch b
   A.fast_uncentred = b.fast_uncentred;
   A.sh_out = b.sh ? b.sh + rep * b.M.L : nullptr;
   A.ws = b.ws + rep * (int64_t)b.M.ws_doubles;
+  A.state = b.state ? b.state + rep * b.state_stride : nullptr;
+  A.resume = b.resume;
   A.out_row = b.out_rows ? b.out_rows + rep * b.out_stride : nullptr;
   A.weights = b.weights; A.loadings = b.loadings; A.r2 = b.r2; A.paths = b.paths; A.total = b.total;
   A.crossloadings = b.crossloadings; A.score_coef = b.score_coef; A.score_shift = b.score_shift;

@@ -85,6 +85,7 @@ struct plspm_data {
   int64_t N = 0;
   double* X = nullptr;   // [N][Ppad] slot layout, globally centred
   double* mu = nullptr;  // [Ppad]
+  double* colsum0 = nullptr;  // [Ppad] column sums of the centred matrix (rounding residue of the centring): a single fit's column sums
   // low-precision copy for the tensor-core sign vote (sparse tile sets): xh = x~ / sd (fp16)
   __half* Xh = nullptr;      // [N][Ppad]
   float* Xf = nullptr;       // [N][Ppad] fp32 copy of x~ (score generation of the sign vote)
@@ -338,6 +339,16 @@ int plspm_data_create(const plspm_model* m, const double* X, int64_t N, int64_t 
     relayout_kernel<<<d->sm_count * 8, 256, 0, st>>>(Xd, N, ld, h.Ppad, m->dv.col_src, d->mu, d->X);
     d->timer.end(st);
     CK(cudaGetLastError());
+    double* partial0 = nullptr;
+    CK(g_pool.alloc((void**)&partial0, (size_t)nblocks * h.Ppad * sizeof(double)));
+    CK(g_pool.alloc((void**)&d->colsum0, (size_t)h.Ppad * sizeof(double)));
+    d->timer.begin(ST_UPLOAD, st);
+    colsum_partial_kernel<<<nblocks, 256, 0, st>>>(d->X, N, h.Ppad, h.Ppad, rpb, partial0);
+    d->timer.end(st);
+    d->timer.begin(ST_UPLOAD, st);
+    reduce_chunks_kernel<<<(h.Ppad + 255) / 256, 256, 0, st>>>(partial0, 1, nblocks, h.Ppad, d->colsum0);
+    d->timer.end(st);
+    CK(cudaGetLastError());
     trace("relayout done");
     // fp16 copy for the tensor-core sign vote of sparse tile sets (PLSPM_VOTE=exact disables it)
     static const bool vote_exact = getenv("PLSPM_VOTE") && std::string(getenv("PLSPM_VOTE")) == "exact";
@@ -558,6 +569,7 @@ int plspm_data_create(const plspm_model* m, const double* X, int64_t N, int64_t 
         if (!std::isfinite(v)) return fail(PLSPM_ERR_INVALID, "non-finite values in the observation matrix");
     }
     g_pool.release(partial);
+    g_pool.release(partial0);
     g_pool.release(src_col);
     return 0;
   };
@@ -572,6 +584,7 @@ void plspm_data_destroy(plspm_data* d) {
   if (!d) return;
   if (d->X) g_pool.release(d->X);
   if (d->mu) g_pool.release(d->mu);
+  if (d->colsum0) g_pool.release(d->colsum0);
   if (d->Xh) g_pool.release(d->Xh);
   if (d->xt_img) g_pool.release(d->xt_img);
   if (d->xl_img) g_pool.release(d->xl_img);
@@ -799,7 +812,7 @@ static size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 constexpr int FAST_RC = 4096;  // rows per tensor-core GEMM chunk (bounds the fp32 accumulation error)
 struct BatchBuffers {
   size_t total = 0;
-  size_t counts, idx, G, Gpart, colsum, cspart, ws, out, iters, status, wf, CG, CGpart, sh, BT, Cf, rep_map;
+  size_t counts, idx, G, Gpart, colsum, cspart, ws, out, iters, status, wf, CG, CGpart, sh, BT, Cf, rep_map, state;
   // single-fit outputs
   size_t weights, loadings, r2, paths, totalfx, crossl, coef, shift, scores;
   // numeric non-metric path: per-replicate iteration state
@@ -830,6 +843,7 @@ static BatchBuffers layout_batch(const plspm_data* d, int64_t nb, const BatchPla
   b.CG = take(vote ? (size_t)nb * csz : 0);
   b.CGpart = take(vote && bp.cross.n_chunks > 1 ? (size_t)nb * csz * bp.cross.n_chunks : 0);
   b.sh = take(vote ? (size_t)nb * h.L * 8 : 0);
+  b.state = take(vote ? (size_t)nb * plspm::solver_state_doubles(d->model->dv) * 8 : 0);
   const bool fast = vote && d->fast_vote && !single_fit;
   b.num_a = take(numeric ? (size_t)nb * h.Ppad * 8 : 0);
   b.num_co = take(numeric ? (size_t)nb * h.Ppad * 8 : 0);
@@ -924,6 +938,7 @@ static int redo_exact(plspm_data* d, int64_t n_list, const int* rep_map_dev, con
   b.iters = (int*)(base + bb.iters); b.status = (int*)(base + bb.status);
   b.cross = D(bb.CG); b.cross_stride = (int64_t)h.n_cross * TILE;
   b.phase = 2; b.rep_map = rep_map_dev;
+  b.state = D(bb.state); b.state_stride = (int64_t)plspm::solver_state_doubles(m->dv); b.resume = 1;
   b.out_rows = out_rows; b.out_stride = h.n_out();
   const size_t smem = h.solver_smem_doubles() * sizeof(double);
   d->timer.begin(ST_SOLVE, st);
@@ -1055,6 +1070,10 @@ static int launch_moments(plspm_data* d, int64_t nb, const uint32_t* counts_dev,
     if (ok) return 0;
     d->i8_colsum = false;  // this cuBLAS build has no int8 GEMM for the shape: fp64 kernel from now on
   }
+  if (!counts_dev && nb == 1 && d->colsum0) {  // unweighted fit: the sums of the centred columns are a by-product of the upload
+    CK(cudaMemcpyAsync(D(bb.colsum), d->colsum0, (size_t)h.Ppad * 8, cudaMemcpyDeviceToDevice, st));
+    return 0;
+  }
   dim3 grid_cs((h.Ppad + CS_COLS - 1) / CS_COLS, (unsigned)((nb + CS_REPS - 1) / CS_REPS), bp.cs_chunks);
   d->timer.begin(ST_COLSUM, st);
   const size_t cs_smem_bytes = (size_t)(CS_ROWS * CS_COLS + CS_ROWS * CS_REPS) * 8;
@@ -1156,6 +1175,7 @@ static int run_batch(plspm_data* d, int64_t nb, const uint32_t* counts_dev, cons
   b.mu = d->mu; b.N = (double)d->N; b.scheme = scheme; b.tol = tol; b.max_iter = max_iter;
   b.ws = D(bb.ws);
   b.iters = (int*)(base + bb.iters); b.status = (int*)(base + bb.status);
+  if (!h.full) { b.state = D(bb.state); b.state_stride = (int64_t)plspm::solver_state_doubles(m->dv); }
   b.wf = h.full ? nullptr : D(bb.wf);
   b.cross = h.full ? nullptr : D(bb.CG); b.cross_stride = (int64_t)h.n_cross * TILE;
   const size_t smem = h.solver_smem_doubles() * sizeof(double);
@@ -1277,6 +1297,7 @@ static int run_batch(plspm_data* d, int64_t nb, const uint32_t* counts_dev, cons
     }
   }
   b.phase = h.full ? 0 : (use_fast ? 3 : 2);
+  b.resume = h.full ? 0 : 1;  // phase 1 of this batch left the converged state in bb.state
   b.out_rows = out_rows; b.out_stride = h.n_out();
   if (single_fit) {
     b.weights = D(bb.weights); b.loadings = D(bb.loadings); b.r2 = D(bb.r2); b.paths = D(bb.paths);

@@ -62,6 +62,8 @@ struct SolveArgs {
   const double* cross;   // [n_cross*64] raw sum_i c_i x~_ip (x~_i . wf_l) tiles (phase 2)
   double* wf_out;        // [Ppad] final normalised weights, padded layout (phase 1)
   double* ws;            // [M.ws_doubles] global scratch private to this CTA
+  double* state;         // [solver_state_doubles(M)] optional: phase 1 stores the converged iteration state here ...
+  int resume;            // ... and phases 2 / 3 with resume != 0 continue from it instead of iterating again
   // outputs; any pointer may be null
   double* out_row;        // [2P+L+2n_eff] weights | r_squared | total effects | direct effects | loadings
   double* weights;        // [P]
@@ -75,6 +77,9 @@ struct SolveArgs {
   int* iters;
   int* status;
 };
+
+// iteration state handed from phase 1 to phases 2 / 3: w | V | dinv | R | {1/scale^2, iterations, status}
+inline size_t solver_state_doubles(const ModelView& M) { return (size_t)M.Ppad + M.n_v + M.L + (size_t)M.L * M.L + 4; }
 
 PL_HD double block_sum(double v, double* red) {
 #if PL_DEVICE_BUILD
@@ -180,8 +185,25 @@ PL_HD void solve_replicate(const SolveArgs& A, double* smem) {
   if (tid == 0) { flag[0] = STATUS_OK; flag[1] = 0; }
   PL_SYNC();
 
+  double iss = 1.0;  // 1 / pooled scale^2
+#define PL_S(p, q) ((gram_raw(M, A.G, (p), (q)) * invN - m[p] * m[q]) * iss)
+  double* ols = A.ws + (M.ws_doubles - L * (M.max_deg * M.max_deg + 2 * M.max_deg));
+  const int ols_stride = M.max_deg * M.max_deg + 2 * M.max_deg;
+  int iteration = 0, status = STATUS_OK;
+  if (A.resume && A.state && A.phase != 1) {
+    // the weights converged in phase 1 (same replicate, same moments): take w, V, dinv, R as they were left
+    const double* S = A.state;
+    for (int p = tid; p < Ppad; p += nt) w[p] = S[p];
+    for (int v = tid; v < M.n_v; v += nt) V[v] = S[Ppad + v];
+    for (int l = tid; l < L; l += nt) dinv[l] = S[Ppad + M.n_v + l];
+    for (int e = tid; e < L * L; e += nt) R[e] = S[Ppad + M.n_v + L + e];
+    const double* misc = S + Ppad + M.n_v + L + (size_t)L * L;
+    iss = misc[0];
+    iteration = (int)misc[1];
+    status = (int)misc[2];
+    PL_SYNC();
+  } else {
   // pooled scale (config.py:302-303): sd over all N*P raw values, ddof=1, times sqrt((N-1)/N)
-  double iss = 1.0;
   if (M.scaled) {
     double ss = 0.0, gs = 0.0;
     for (int p = tid; p < Ppad; p += nt)
@@ -201,7 +223,6 @@ PL_HD void solve_replicate(const SolveArgs& A, double* smem) {
     double var1 = (ss + N * dev) / (N * (double)M.P - 1.0);
     iss = 1.0 / (var1 * a_fac);
   }
-#define PL_S(p, q) ((gram_raw(M, A.G, (p), (q)) * invN - m[p] * m[q]) * iss)
 
   // ---- initial weights (weights.py:28-34): 1/sd of the block sum (correction cancels) ----------
   for (int l = tid; l < L; l += nt) {
@@ -225,10 +246,6 @@ PL_HD void solve_replicate(const SolveArgs& A, double* smem) {
   }
   PL_SYNC();
 
-  double* ols = A.ws + (M.ws_doubles - L * (M.max_deg * M.max_deg + 2 * M.max_deg));
-  const int ols_stride = M.max_deg * M.max_deg + 2 * M.max_deg;
-
-  int iteration = 0;
   bool finalize = false;
   for (;;) {
     // ---- V_d = S_lj w_j for every needed directed LV pair  (Y = X W, weights.py:43) -----------
@@ -328,8 +345,9 @@ PL_HD void solve_replicate(const SolveArgs& A, double* smem) {
     // weights.py:183  (a NaN criterion keeps iterating until the cap, like the reference)
     if ((conv < A.tol) || (iteration > A.max_iter) || flag[0] != STATUS_OK) finalize = true;
   }
-  int status = flag[0];
+  status = flag[0];
   if (status == STATUS_OK && iteration > A.max_iter) status = STATUS_NOT_CONVERGED;  // weights.py:185 (Q4)
+  }  // (not resumed)
 
   // ---- final normalisation, sign vote (weights.py:56-68) --------------------------------------------
   // after the loop V, dinv and R hold the values for the final weights
@@ -347,6 +365,19 @@ PL_HD void solve_replicate(const SolveArgs& A, double* smem) {
         for (int r = 0; r < M.lv_k[l]; ++r) sh += m[M.lv_off[l] + r] * u[M.lv_off[l] + r];
         A.sh_out[l] = sh;
       }
+    if (A.state) {
+      double* S = A.state;
+      for (int p = tid; p < Ppad; p += nt) S[p] = w[p];
+      for (int v = tid; v < M.n_v; v += nt) S[Ppad + v] = V[v];
+      for (int l = tid; l < L; l += nt) S[Ppad + M.n_v + l] = dinv[l];
+      for (int e = tid; e < L * L; e += nt) S[Ppad + M.n_v + L + e] = R[e];
+      if (tid == 0) {
+        double* misc = S + Ppad + M.n_v + L + (size_t)L * L;
+        misc[0] = iss;
+        misc[1] = (double)iteration;
+        misc[2] = (double)status;
+      }
+    }
     if (tid == 0) {
       if (A.iters) *A.iters = iteration;
       if (A.status) *A.status = status;
@@ -359,7 +390,9 @@ PL_HD void solve_replicate(const SolveArgs& A, double* smem) {
       for (int r = 0; r < M.lv_k[l]; ++r) sh += m[M.lv_off[l] + r] * u[M.lv_off[l] + r];
       bsum[l] = sh;
     }
-  if (A.phase == 3)
+  if (A.phase == 3) {
+    // per-column factor of the vote's error bound (wold is free after the iteration)
+    for (int p = tid; p < Ppad; p += nt) wold[p] = M.col_lv[p] >= 0 ? sqrt(gram_raw(M, A.G, p, p)) * A.inv_sd[p] : 0.0;
     for (int l = tid; l < L; l += nt) {
       unc[l] = 0;
       // fp32 score generation: |t^ - t| <= (k+4) 2^-24 (sum_k |x_k w_k| + |sh|) per row, hence (Cauchy-Schwarz
@@ -391,6 +424,7 @@ PL_HD void solve_replicate(const SolveArgs& A, double* smem) {
         sgn[l] = sh;  // (sgn is free until the votes are counted) mean of the un-centred score
       }
     }
+  }
   PL_SYNC();
   // cov(x_p, score_l) for ALL (p, l): every manifest variable votes on every LV (quirk Q6)
   for (int t = tid; t < Ppad * L; t += nt) {
@@ -410,7 +444,7 @@ PL_HD void solve_replicate(const SolveArgs& A, double* smem) {
         v -= sgn[l] * A.colsum[p] * A.inv_sd[p];
         t2 += N * sgn[l] * sgn[l];
       }
-      const double bound = (2.0e-3 * sqrt(t2) + bsum[l]) * sqrt(gram_raw(M, A.G, p, p)) * A.inv_sd[p];
+      const double bound = (2.0e-3 * sqrt(t2) + bsum[l]) * wold[p];
       if (v - v == 0.0 && fabs(v) > bound) vote_add(votes, l, v < 0.0 ? -1 : 1);
       else vote_add(unc, l, 1);
       continue;

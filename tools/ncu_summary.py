@@ -32,7 +32,7 @@ def raw_rows(path):
 
 
 STAGE_OF = (("gram_mma_kernel", "gram_i8"), ("vote_mma_kernel", "cross"), ("gram_finalize_kernel", "finalize"), ("solve_kernel", "solve"),
-            ("counts8_image_kernel", "colsum"), ("vote_c8_image_kernel", "colsum_vote"), ("counts_kernel", "counts"),
+            ("resample_images_kernel", "counts"), ("counts8_image_kernel", "colsum"), ("vote_c8_image_kernel", "colsum_vote"), ("counts_kernel", "counts"),
             ("gram_kernel", "gram"), ("reduce_chunks_kernel", "reduce"), ("scoregen_kernel", "scoregen"))
 
 
