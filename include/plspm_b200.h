@@ -100,6 +100,15 @@ int plspm_bootstrap_host(const plspm_model* m, const double* X, int64_t N, int64
                          int32_t max_iter, int64_t rep_begin, int64_t rep_count, uint64_t seed, const int32_t* idx,
                          double* out, int32_t* status, int32_t* iters);
 
+/* Bootstrap on data with missing values (replaces the per-replicate re-imputation of bootstrap.py:57 ->
+ * estimator.py:33 -> config.py:299-305 -> util.py:61-68, column means of the replicate's observed rows).
+ * `d` must hold the AUGMENTED matrix [x0 | m] under an augmented model: block l = the base block's columns with
+ * missing entries set to 0, followed by one 0/1 missing indicator per column of the block that has missing entries.
+ * base: the model without indicators.  Both models need PLSPM_TILES_FULL and the metric estimator.
+ * has_missing: host int8 [base P] in base column order.  After this call plspm_bootstrap(augmented model, d, ...)
+ * returns rows of the BASE model (base info[7] doubles per replicate).  base must outlive d. */
+int plspm_data_set_imputation(plspm_data* d, const plspm_model* base, const int8_t* has_missing);
+
 /* The resample index stream of one replicate (replaces numpy.random.randint at
  * bootstrap.py:56, which is unseeded in the reference).  idx_out: host int32 [N]. */
 int plspm_resample_indices(uint64_t seed, int64_t replicate, int64_t N, int32_t* idx_out);

@@ -80,6 +80,16 @@ struct Workspace {
   size_t bytes = 0;
 };
 
+// Bootstrap with missing values (kernels_impute.cuh): the handle holds the AUGMENTED matrix [x0 | m] under an augmented
+// model; replicates are solved under the base model on the moments of the imputed data.
+struct ImputeCtx {
+  const plspm_model* base = nullptr;
+  int *ax = nullptr, *am = nullptr;  // [base Ppad] augmented padded column of x0_p and of its missing indicator (-1: none)
+  double* mu_base = nullptr;         // [base Ppad] upload mean of the zero-filled column (the base moments are taken about it)
+  double *G = nullptr, *colsum = nullptr, *ws = nullptr;  // moments of the imputed replicates + solver scratch, base layout
+  int64_t cap = 0;                   // replicates the three buffers hold
+};
+
 struct plspm_data {
   const plspm_model* model = nullptr;
   int64_t N = 0;
@@ -127,6 +137,7 @@ struct plspm_data {
   Workspace ws;          // grown on demand, reused across calls
   StageTimer timer;
   int sm_count = 148;
+  ImputeCtx* imp = nullptr;
   bool img_ready = false;  // the multiplicity images of the batch in flight were written by resample_images_kernel
   int max_smem = 227 * 1024;
 };
@@ -152,6 +163,7 @@ static int upload_vec(plspm_model* m, const std::vector<T>& v, const T** out) {
 #include "kernels_numstep.cuh"
 #include "kernels_gram.cuh"
 #include "kernels_solve.cuh"
+#include "kernels_impute.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // C ABI
@@ -585,6 +597,11 @@ void plspm_data_destroy(plspm_data* d) {
   if (d->X) g_pool.release(d->X);
   if (d->mu) g_pool.release(d->mu);
   if (d->colsum0) g_pool.release(d->colsum0);
+  if (d->imp) {
+    for (void* q : {(void*)d->imp->ax, (void*)d->imp->am, (void*)d->imp->mu_base, (void*)d->imp->G, (void*)d->imp->colsum, (void*)d->imp->ws})
+      if (q) g_pool.release(q);
+    delete d->imp;
+  }
   if (d->Xh) g_pool.release(d->Xh);
   if (d->xt_img) g_pool.release(d->xt_img);
   if (d->xl_img) g_pool.release(d->xl_img);
@@ -1169,6 +1186,43 @@ static int run_batch(plspm_data* d, int64_t nb, const uint32_t* counts_dev, cons
   if (int rc = launch_moments(d, nb, counts_dev, bb, bp)) return rc;
   SolveBatch b;
   std::memset(&b, 0, sizeof(b));
+  if (d->imp && !single_fit) {
+    // missing values: moments of the augmented matrix -> moments of the per-replicate imputed data -> base-model solve
+    ImputeCtx& ic = *d->imp;
+    const HostModel& hb = ic.base->h;
+    if (ic.cap < nb) {
+      for (void* q : {(void*)ic.G, (void*)ic.colsum, (void*)ic.ws})
+        if (q) g_pool.release(q);
+      ic.G = ic.colsum = ic.ws = nullptr;
+      ic.cap = 0;
+      CK(g_pool.alloc((void**)&ic.G, (size_t)nb * hb.n_tiles * TILE * 8));
+      CK(g_pool.alloc((void**)&ic.colsum, (size_t)nb * hb.Ppad * 8));
+      CK(g_pool.alloc((void**)&ic.ws, (size_t)nb * std::max(hb.ws_doubles, 1) * 8));
+      ic.cap = nb;
+    }
+    d->timer.begin(ST_FINALIZE, st);
+    impute_moments_kernel<<<(unsigned)nb, 256, (size_t)4 * hb.Ppad * 8, st>>>(
+        m->dv, ic.base->dv, D(bb.G), (int64_t)h.n_tiles * TILE, D(bb.colsum), h.Ppad, d->mu, ic.ax, ic.am, (double)d->N, ic.G,
+        (int64_t)hb.n_tiles * TILE, ic.colsum, hb.Ppad);
+    d->timer.end(st);
+    CK(cudaGetLastError());
+    b.M = ic.base->dv;
+    b.G = ic.G; b.g_stride = (int64_t)hb.n_tiles * TILE;
+    b.colsum = ic.colsum; b.cs_stride = hb.Ppad;
+    b.mu = ic.mu_base; b.N = (double)d->N; b.scheme = scheme; b.tol = tol; b.max_iter = max_iter;
+    b.ws = ic.ws;
+    b.iters = (int*)(base + bb.iters); b.status = (int*)(base + bb.status);
+    b.phase = 0;
+    b.out_rows = out_rows; b.out_stride = hb.n_out();
+    const size_t smem_b = hb.solver_smem_doubles() * sizeof(double);
+    if (smem_b > (size_t)d->max_smem) return fail(PLSPM_ERR_UNSUPPORTED, "model too large for the solver's shared memory");
+    CK(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+    d->timer.begin(ST_SOLVE, st);
+    solve_kernel<<<(unsigned)nb, SOLVE_THREADS, smem_b, st>>>(b);
+    d->timer.end(st);
+    CK(cudaGetLastError());
+    return 0;
+  }
   b.M = m->dv;
   b.G = D(bb.G); b.g_stride = (int64_t)h.n_tiles * TILE;
   b.colsum = D(bb.colsum); b.cs_stride = h.Ppad;
@@ -1367,7 +1421,8 @@ int plspm_bootstrap(const plspm_model* m, plspm_data* d, int32_t scheme, double 
   d->model = m;
   const HostModel& h = m->h;
   const int64_t N = d->N;
-  const size_t n_out = h.n_out();
+  if (d->imp && (m->numeric || !h.full)) return fail(PLSPM_ERR_INVALID, "imputation needs the metric estimator and full tile sets");
+  const size_t n_out = d->imp ? d->imp->base->h.n_out() : h.n_out();  // (rows of the BASE model when the handle is augmented)
   if (idx)
     for (int64_t e = 0; e < rep_count * N; ++e)
       if (idx[e] < 0 || idx[e] >= N) return fail(PLSPM_ERR_INVALID, "resample index out of range");
@@ -1515,6 +1570,41 @@ int plspm_bootstrap_host(const plspm_model* m, const double* X, int64_t N, int64
             (double)g_pool.cached / 1073741824.0);
   }
   return rc;
+}
+
+int plspm_data_set_imputation(plspm_data* d, const plspm_model* base, const int8_t* has_missing) {
+  if (!d || !base || !has_missing) return fail(PLSPM_ERR_INVALID, "null argument");
+  const HostModel& ha = d->model->h;
+  const HostModel& hb = base->h;
+  if (d->imp) return fail(PLSPM_ERR_INVALID, "imputation already set on this handle");
+  if (!ha.full || !hb.full || d->model->numeric || base->numeric)
+    return fail(PLSPM_ERR_INVALID, "imputation needs metric models with the full tile set (PLSPM_TILES_FULL)");
+  if (ha.L != hb.L) return fail(PLSPM_ERR_INVALID, "augmented and base model have different latent variables");
+  std::vector<int> ax(hb.Ppad, -1), am(hb.Ppad, -1);
+  int src = 0;
+  for (int l = 0; l < hb.L; ++l) {
+    int n_miss = 0;
+    for (int r = 0; r < hb.lv_k[l]; ++r, ++src) {
+      // base source column `src` = column r of block l; has_missing is in base source order
+      const int pb = hb.lv_off[l] + r;
+      ax[pb] = ha.lv_off[l] + r;
+      if (has_missing[src]) am[pb] = ha.lv_off[l] + hb.lv_k[l] + n_miss++;
+    }
+    if (ha.lv_k[l] != hb.lv_k[l] + n_miss)
+      return fail(PLSPM_ERR_INVALID, "augmented block must be the base block followed by one indicator per column with missing values");
+  }
+  ImputeCtx* ic = new ImputeCtx();
+  ic->base = base;
+  d->imp = ic;
+  CK(g_pool.alloc((void**)&ic->ax, (size_t)hb.Ppad * 4));
+  CK(g_pool.alloc((void**)&ic->am, (size_t)hb.Ppad * 4));
+  CK(g_pool.alloc((void**)&ic->mu_base, (size_t)hb.Ppad * 8));
+  CK(cudaMemcpyAsync(ic->ax, ax.data(), (size_t)hb.Ppad * 4, cudaMemcpyHostToDevice, d->stream));
+  CK(cudaMemcpyAsync(ic->am, am.data(), (size_t)hb.Ppad * 4, cudaMemcpyHostToDevice, d->stream));
+  gather_kernel<<<(hb.Ppad + 127) / 128, 128, 0, d->stream>>>(d->mu, ic->ax, hb.Ppad, ic->mu_base);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(d->stream));
+  return PLSPM_OK;
 }
 
 int plspm_resample_indices(uint64_t seed, int64_t replicate, int64_t N, int32_t* idx_out) {

@@ -23,7 +23,7 @@ EXPORTS = (
     "plspm_model_destroy", "plspm_model_query", "plspm_model_effects", "plspm_data_create", "plspm_data_destroy",
     "plspm_fit", "plspm_bootstrap", "plspm_bootstrap_host", "plspm_resample_indices", "plspm_profile_reset",
     "plspm_profile_get", "plspm_host_alloc", "plspm_host_free", "plspm_redo_count", "plspm_model_set_numeric",
-    "plspm_pool_trim", "plspm_pool_set_limit",
+    "plspm_pool_trim", "plspm_pool_set_limit", "plspm_data_set_imputation",
 )
 
 _lib = None
@@ -69,6 +69,7 @@ def load():
     lib.plspm_host_alloc.argtypes = [ctypes.POINTER(vp), i64]
     lib.plspm_host_free.argtypes = [vp]
     lib.plspm_pool_set_limit.argtypes = [i64]
+    lib.plspm_data_set_imputation.argtypes = [vp, vp, _c_i8p]
     _lib = lib
     return lib
 
@@ -170,6 +171,15 @@ class Data:
                     raise NotImplementedError("missing / non-finite values are not supported by the CUDA path yet")
                 raise
 
+    def set_imputation(self, base: Model, has_missing):
+        """This handle holds the augmented matrix [x0 | missing indicators] (see include/plspm_b200.h): bootstrap
+        replicates are re-imputed with the column means of their own observed rows and solved under `base`."""
+        hm = np.ascontiguousarray(has_missing, dtype=np.int8)
+        if hm.shape != (base.P,):
+            raise ValueError("has_missing must be [%d]" % base.P)
+        _check(load().plspm_data_set_imputation(self._h, base._h, _ptr(hm, _c_i8p)))
+        self.rows_model = base  # keeps the base model alive; bootstrap rows have ITS layout
+
     def close(self):
         if self._h:
             load().plspm_data_destroy(self._h)
@@ -212,7 +222,7 @@ def bootstrap(model: Model, data: Data, scheme, rep_begin: int, rep_count: int, 
     if out_device_ptr:
         rows, optr, dev = None, ctypes.c_void_p(out_device_ptr), 1
     else:
-        rows = np.empty((rep_count, model.n_out), dtype=np.float64)
+        rows = np.empty((rep_count, getattr(data, "rows_model", model).n_out), dtype=np.float64)
         optr, dev = rows.ctypes.data_as(ctypes.c_void_p), 0
     _check(load().plspm_bootstrap(model._h, data._h, scheme_id(scheme), float(tol), int(max_iter), int(rep_begin),
                                   int(rep_count), int(seed), _ptr(idx_a, _c_i32p), optr, dev, _ptr(status, _c_i32p),

@@ -23,8 +23,10 @@ class EngineSession:
         frame = data.loc[:, self.mvs]
         if self.missing and self.numeric:
             raise NotImplementedError("non-metric data with missing values are outside the accelerated path")
+        self.raw = None
         if self.missing:
-            frame = frame.fillna(frame.mean(skipna=True))  # util.impute (util.py:61-68), single fit only
+            self.raw = np.ascontiguousarray(frame.to_numpy(dtype=np.float64))  # (with NaN: the bootstrap re-imputes per replicate)
+            frame = frame.fillna(frame.mean(skipna=True))  # util.impute (util.py:61-68): the single fit
         X = np.ascontiguousarray(frame.to_numpy(dtype=np.float64))
         self.scaled = config.scaled() if scaled is None else bool(scaled)
         spec = ([len(self.blocks[lv]) for lv in self.lvs], [config.mode(lv).value.engine_id for lv in self.lvs],
@@ -37,6 +39,34 @@ class EngineSession:
             self.fit_model = engine.Model(*spec, engine.TILES_FULL, numeric=True)
         self.data = engine.Data(self.model, X)
         self.N = self.data.N
+        self.spec = spec
+        self.aug = None  # (base model, augmented model, augmented data) of the bootstrap with missing values
+
+    def _augmented(self):
+        """Handles for the bootstrap on data with missing values: the matrix [x0 | m] (missing entries as 0, one 0/1
+        indicator per column that has missing entries, appended to its block) under full-tile models.  Every moment
+        of a replicate imputed with ITS observed column means (util.py:61-68 under bootstrap.py:57) is a closed form
+        in the moments of this matrix (csrc/kernels_impute.cuh)."""
+        if self.aug is None:
+            sizes, modes, path, scaled = self.spec
+            nan = np.isnan(self.raw)
+            has = nan.any(axis=0)
+            cols, aug_sizes, o = [], [], 0
+            for k in sizes:
+                block = list(range(o, o + k))
+                miss = [p for p in block if has[p]]
+                cols.append(np.where(nan[:, block], 0.0, self.raw[:, block]))
+                if miss:
+                    cols.append(nan[:, miss].astype(np.float64))
+                aug_sizes.append(k + len(miss))
+                o += k
+            Xa = np.ascontiguousarray(np.concatenate(cols, axis=1))
+            base = engine.Model(sizes, modes, path, scaled, engine.TILES_FULL)
+            aug_model = engine.Model(aug_sizes, modes, path, scaled, engine.TILES_FULL)
+            aug_data = engine.Data(aug_model, Xa)
+            aug_data.set_imputation(base, has)
+            self.aug = (base, aug_model, aug_data)
+        return self.aug
 
     def fit(self, scheme, tol: float, iterations: int, want_scores: bool = True):
         res = engine.fit(self.fit_model, self.data, scheme.value.engine_id, tol, iterations, want_scores)
@@ -49,11 +79,18 @@ class EngineSession:
     def bootstrap(self, scheme, tol: float, iterations: int, rep_begin: int, rep_count: int, seed: int = 0, idx=None,
                   out_device_ptr: int = 0):
         if self.missing:
-            raise NotImplementedError("bootstrap with missing values is not supported by the CUDA path yet")
+            base, aug_model, aug_data = self._augmented()
+            return engine.bootstrap(aug_model, aug_data, scheme.value.engine_id, rep_begin, rep_count, seed, idx, tol,
+                                    iterations, out_device_ptr)
         return engine.bootstrap(self.model, self.data, scheme.value.engine_id, rep_begin, rep_count, seed, idx, tol,
                                 iterations, out_device_ptr)
 
     def close(self, trim_pool: bool = True):
+        if self.aug is not None:
+            self.aug[2].close()
+            self.aug[1].close()
+            self.aug[0].close()
+            self.aug = None
         self.data.close()
         if self.fit_model is not self.model:
             self.fit_model.close()

@@ -394,9 +394,39 @@ def make_hoc():
     print("wrote hoc.npz")
 
 
+def make_missing():
+    """Bootstrap replicates of data WITH missing values: the reference re-imputes each resample with the column means
+    of its own observed rows (bootstrap.py:57 -> estimator.py:33 -> config.py:299-305 -> util.py:61-68)."""
+    sat = pd.read_csv(os.path.join(REF, "tests", "data", "satisfaction.csv"), index_col=0)
+    path = satisfaction_structure()
+    lvs = list(path)
+    blocks = {lv: [m for m in sat.columns if m.startswith(SAT_PREFIX[lv])] for lv in lvs}
+    mvs = [m for lv in lvs for m in blocks[lv]]
+    X = sat.loc[:, mvs].astype(np.float64).copy()
+    rng = np.random.default_rng(77)
+    holes = [(int(r), int(cix)) for r, cix in zip(rng.integers(0, X.shape[0], 40), rng.integers(0, X.shape[1], 40))]
+    holes += [(int(r), 3) for r in rng.integers(0, X.shape[0], 25)]  # one column with many holes
+    for r, cix in holes:
+        X.iat[r, cix] = np.nan
+    idx = rng.integers(0, X.shape[0], (16, X.shape[0]), dtype=np.int32)
+    out = {"X": X.to_numpy(), "idx": idx, "lvs": np.array(lvs), "mvs": np.array(mvs),
+           "block_sizes": np.array([len(blocks[lv]) for lv in lvs], dtype=np.int32),
+           "path": path.loc[lvs, lvs].to_numpy(dtype=np.int8)}
+    for sname, mname, scaled in (("centroid", "A", True), ("path", "B", True), ("factorial", "A", False)):
+        mode = Mode.A if mname == "A" else Mode.B
+        tag = "boot/%s/%s/%s" % (sname, mname, "scaled" if scaled else "unscaled")
+        r = run_reference_replicates(X, path, blocks, {lv: mode for lv in lvs}, SCHEMES[sname], scaled, idx)
+        print(tag, "ok", int(r["ok"].sum()), "iters", np.bincount(r["iterations"]))
+        out.update(flatten(tag, r))
+    np.savez_compressed(os.path.join(HERE, "missing.npz"), **out)
+
+
 if __name__ == "__main__":
     if "--only-hoc" in sys.argv:
         make_hoc()
+    elif "--only-missing" in sys.argv:
+        make_missing()
     else:
         main()
         make_hoc()
+        make_missing()

@@ -165,3 +165,57 @@ def test_missing_values_single_fit_is_mean_imputed(sat):
     np.testing.assert_allclose(calc.outer_model().loc[[str(v) for v in sat["mvs"]], "weight"].values, ref["weights"],
                                rtol=1e-6)
 
+
+
+@pytest.mark.parametrize("case", ("centroid/A/scaled", "path/B/scaled", "factorial/A/unscaled"))
+def test_bootstrap_with_missing_values_reproduces_reference_replicates(sat, case):
+    """Bootstrap on data with missing values (the reference re-imputes every resample with the means of its own
+    observed rows): moments of the augmented matrix [x0 | m] on the device, closed-form imputation, base-model
+    solve (csrc/kernels_impute.cuh) against replicates of the REFERENCE (tests/golden/missing.npz)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "missing.npz"))
+    scheme, mode, sc = case.split("/")
+    mvs = [str(v) for v in g["mvs"]]
+    df = pd.DataFrame(g["X"], columns=mvs)
+    config = make_config(df, Mode.A if mode == "A" else Mode.B, scaled=(sc == "scaled"))
+    idx = g["idx"]
+    calc = Plspm(df, config, {"centroid": Scheme.CENTROID, "path": Scheme.PATH, "factorial": Scheme.FACTORIAL}[scheme],
+                 bootstrap=True, bootstrap_iterations=len(idx), processes=1, bootstrap_indices=idx)
+    boot = calc.bootstrap()
+    status, iters = boot.replicate_status()
+    tag = "boot/%s/" % case
+    assert (status == 0).all()
+    np.testing.assert_array_equal(iters, g[tag + "iterations"])
+    s = boot.samples()
+    np.testing.assert_allclose(s["weights"].loc[:, mvs].values, g[tag + "weights"], rtol=1e-6)
+    np.testing.assert_allclose(s["loadings"].loc[:, mvs].values, g[tag + "loadings"], rtol=1e-6, atol=1e-9)
+    lvs = [str(v) for v in g["lvs"]]
+    np.testing.assert_allclose(s["r_squared"].loc[:, lvs].values, g[tag + "r_squared"], rtol=1e-6, atol=1e-9)
+    for col in s["paths"].columns:
+        f, t = col.split(" -> ")
+        np.testing.assert_allclose(s["paths"][col].values, g[tag + "path_coefficients"][:, lvs.index(t), lvs.index(f)],
+                                   rtol=1e-6, atol=1e-9)
+        np.testing.assert_allclose(s["total_effects"][col].values, g[tag + "total_effects"][:, lvs.index(t), lvs.index(f)],
+                                   rtol=1e-6, atol=1e-9)
+
+
+def test_bootstrap_with_missing_values_philox_replicates_vs_oracle(sat):
+    """Same path with the library's own resample stream and a larger batch, against the CPU oracle."""
+    import os
+    from oracle import plspm_oracle as orc
+    from plspm_b200 import engine
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "missing.npz"))
+    mvs = [str(v) for v in g["mvs"]]
+    df = pd.DataFrame(g["X"], columns=mvs)
+    calc = Plspm(df, make_config(df, Mode.A, scaled=True), bootstrap=True, bootstrap_iterations=200, processes=1,
+                 bootstrap_seed=11)
+    boot = calc.bootstrap()
+    status, iters = boot.replicate_status()
+    assert (status == 0).all()
+    w = boot.samples()["weights"].loc[:, mvs].values
+    L = len(g["block_sizes"])
+    for b in (0, 57, 199):
+        idx = orc.philox_indices(11, b, g["X"].shape[0])
+        ref, it, st = orc.replicate_row(g["X"], idx, g["block_sizes"], [0] * L, g["path"], "centroid", True)
+        assert st == 0 and it == iters[b]
+        np.testing.assert_allclose(w[b], ref[:len(mvs)], rtol=1e-6)

@@ -3,6 +3,8 @@
      (/root/reference/tests/data/satisfaction.*.csv, test_regression_metric.py:43-94), and
  (2) outputs of the reference itself (tests/golden/make_golden.py).
 CPU only."""
+import os
+
 import numpy as np
 import pytest
 
@@ -130,6 +132,31 @@ def test_bootstrap_replicates_vs_reference(sat, case):
     np.testing.assert_allclose(out[:, P + L:P + L + ne], tot, rtol=tol, atol=1e-12)
     np.testing.assert_allclose(out[:, P + L + ne:P + L + 2 * ne], direct, rtol=tol, atol=1e-12)
     np.testing.assert_allclose(out[:, P + L + 2 * ne:], sat[tag + "loadings"], rtol=tol, atol=1e-12)
+
+
+@pytest.mark.parametrize("case", ("centroid/A/scaled", "path/B/scaled", "factorial/A/unscaled"))
+def test_bootstrap_with_missing_values_vs_reference(case):
+    """Data with missing values: every replicate is re-imputed with the column means of its own observed rows
+    (reference bootstrap.py:57 -> estimator.py:33 -> config.py:299-305 -> util.py:61-68); fixture generated by
+    running the reference (tests/golden/make_golden.py --only-missing)."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "missing.npz"))
+    scheme, mode, sc = case.split("/")
+    L = len(g["block_sizes"])
+    assert np.isnan(g["X"]).sum() > 40
+    out, iters, status = orc.bootstrap(g["X"], g["idx"], g["block_sizes"], [orc.MODE_A if mode == "A" else orc.MODE_B] * L,
+                                       g["path"], scheme, sc == "scaled")
+    tag = "boot/%s/" % case
+    assert (status == 0).all() and g[tag + "ok"].all()
+    np.testing.assert_array_equal(iters, g[tag + "iterations"])
+    P = int(g["block_sizes"].sum())
+    tol = 1e-8 if mode == "A" else 1e-7
+    np.testing.assert_allclose(out[:, :P], g[tag + "weights"], rtol=tol)
+    np.testing.assert_allclose(out[:, P:P + L], g[tag + "r_squared"], rtol=tol, atol=1e-12)
+    pairs = orc.effect_pairs(g["path"])
+    ne = len(pairs)
+    direct = np.array([[g[tag + "path_coefficients"][b, t, f] for f, t in pairs] for b in range(len(g["idx"]))])
+    np.testing.assert_allclose(out[:, P + L + ne:P + L + 2 * ne], direct, rtol=tol, atol=1e-12)
+    np.testing.assert_allclose(out[:, P + L + 2 * ne:], g[tag + "loadings"], rtol=tol, atol=1e-12)
 
 
 def test_effect_pairs_match_reference_effects_index(sat):
