@@ -1411,6 +1411,38 @@ int plspm_fit(const plspm_model* m, plspm_data* d, int32_t scheme, double tol, i
   return PLSPM_OK;
 }
 
+// Small page-locked staging buffers for the per-batch read-back (status, iterations, overflow flag): cached
+// process-wide, because plspm_bootstrap_host creates a handle per call and cudaMallocHost costs ~0.1 ms.
+struct PinnedStage {
+  int* ints = nullptr;
+  size_t bytes = 0;
+  static std::mutex& mu() { static std::mutex m; return m; }
+  static std::vector<std::pair<void*, size_t>>& cache() { static std::vector<std::pair<void*, size_t>> c; return c; }
+  explicit PinnedStage(size_t need) {
+    need = std::max<size_t>((need + 65535) / 65536 * 65536, 65536);
+    {
+      std::lock_guard<std::mutex> lk(mu());
+      auto& c = cache();
+      for (size_t i = 0; i < c.size(); ++i)
+        if (c[i].second >= need) {
+          ints = (int*)c[i].first; bytes = c[i].second;
+          c.erase(c.begin() + i);
+          return;
+        }
+    }
+    if (cudaMallocHost((void**)&ints, need) == cudaSuccess) bytes = need;
+    else ints = nullptr;
+  }
+  ~PinnedStage() {
+    if (!ints) return;
+    std::lock_guard<std::mutex> lk(mu());
+    if (cache().size() < 16) cache().push_back({(void*)ints, bytes});
+    else cudaFreeHost(ints);
+  }
+  PinnedStage(const PinnedStage&) = delete;
+  PinnedStage& operator=(const PinnedStage&) = delete;
+};
+
 int plspm_bootstrap(const plspm_model* m, plspm_data* d, int32_t scheme, double tol, int32_t max_iter,
                     int64_t rep_begin, int64_t rep_count, uint64_t seed, const int32_t* idx, double* out,
                     int32_t out_is_device, int32_t* status, int32_t* iters) {
@@ -1460,6 +1492,8 @@ int plspm_bootstrap(const plspm_model* m, plspm_data* d, int32_t scheme, double 
   char* base = (char*)d->ws.ptr;
   cudaStream_t st = d->stream;
   CK(cudaMemsetAsync(base + bb.ovf, 0, 8, st));
+  PinnedStage stage((size_t)(2 * nb_max + 2) * 4);
+  if (!stage.ints) return fail(PLSPM_ERR_NOMEM, "pinned staging buffer");
   for (int64_t b0 = 0; b0 < rep_count; b0 += nb_max) {
     const int64_t nb = std::min(nb_max, rep_count - b0);
     // a short last batch reuses the plan (and therefore the workspace layout) of a full one
@@ -1502,18 +1536,37 @@ int plspm_bootstrap(const plspm_model* m, plspm_data* d, int32_t scheme, double 
       return rc;
     }
     double* rows = out_is_device ? out + (size_t)b0 * n_out : (double*)(base + bb.out);
+    // ONE host round trip per batch: the overflow flag, the statuses, the iteration counts and (host output) the rows
+    // come back together (round 1 synchronised three times per batch, which is what cost the 8-GPU run 5 % when eight
+    // processes share the host); the rare redo paths re-issue what they changed.
+    int* h_ovf = stage.ints;
+    int* h_status = stage.ints + 2;
+    int* h_iters = h_status + nb_max;
+    static const bool sync_split = getenv("PLSPM_SYNC") && std::string(getenv("PLSPM_SYNC")) == "split";  // A/B: round 1's three syncs
+    auto fetch = [&]() -> int {
+      if (sync_split) {
+        CK(cudaMemcpyAsync(h_ovf, base + bb.ovf, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        CK(cudaMemcpyAsync(h_status, base + bb.status, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+      }
+      CK(cudaMemcpyAsync(h_ovf, base + bb.ovf, 4, cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(h_status, base + bb.status, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(h_iters, base + bb.iters, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
+      if (!out_is_device)
+        CK(cudaMemcpyAsync(out + (size_t)b0 * n_out, rows, (size_t)nb * n_out * 8, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      return 0;
+    };
     for (int attempt = 0; attempt < 2; ++attempt) {
       if (m->numeric) {
         if (int rc = run_batch_num(d, nb, cnt, bb, scheme, tol, max_iter, bp, rows, false)) return rc;
       } else if (int rc = run_batch(d, nb, cnt, bb, scheme, tol, max_iter, bp, rows, false)) {
         return rc;
       }
-      if (!d->i8_colsum) break;
-      // a multiplicity above 127 does not fit the int8 operand of the tensor-core column sums: redo in fp64
-      int ovf = 0;
-      CK(cudaMemcpyAsync(&ovf, base + bb.ovf, 4, cudaMemcpyDeviceToHost, st));
-      CK(cudaStreamSynchronize(st));
-      if (!ovf) break;
+      if (int rc = fetch()) return rc;
+      // a multiplicity above 127 does not fit the int8 operand of the tensor-core routes: redo in fp64
+      if (!d->i8_colsum || !*h_ovf) break;
       CK(cudaMemsetAsync(base + bb.ovf, 0, 8, st));
       d->i8_colsum = false;
       d->img_ready = false;
@@ -1521,12 +1574,9 @@ int plspm_bootstrap(const plspm_model* m, plspm_data* d, int32_t scheme, double 
     }
     if (vote && d->fast_vote) {
       // replicates whose low-precision sign vote was undecided are redone with exact fp64 cross moments
-      std::vector<int> st_host(nb);
-      CK(cudaMemcpyAsync(st_host.data(), base + bb.status, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
-      CK(cudaStreamSynchronize(st));
       std::vector<int> redo;
       for (int64_t r = 0; r < nb; ++r)
-        if (st_host[r] == STATUS_AMBIGUOUS) redo.push_back((int)r);
+        if (h_status[r] == STATUS_AMBIGUOUS) redo.push_back((int)r);
       if (!redo.empty()) {
         int* map_dev = (int*)(base + bb.rep_map);
         CK(cudaMemcpyAsync(map_dev, redo.data(), redo.size() * 4, cudaMemcpyHostToDevice, st));
@@ -1534,13 +1584,11 @@ int plspm_bootstrap(const plspm_model* m, plspm_data* d, int32_t scheme, double 
         if (int rc = redo_exact(d, (int64_t)redo.size(), map_dev, cnt, bb, scheme, tol, max_iter, bp, rows)) return rc;
         g_redo_count += (int64_t)redo.size();
         if ((int64_t)redo.size() * 2 > nb) d->fast_vote = false;  // this data does not suit the fp16 vote
+        if (int rc = fetch()) return rc;
       }
     }
-    if (!out_is_device)
-      CK(cudaMemcpyAsync(out + (size_t)b0 * n_out, rows, (size_t)nb * n_out * 8, cudaMemcpyDeviceToHost, st));
-    if (iters) CK(cudaMemcpyAsync(iters + b0, base + bb.iters, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
-    if (status) CK(cudaMemcpyAsync(status + b0, base + bb.status, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    if (iters) std::memcpy(iters + b0, h_iters, (size_t)nb * 4);
+    if (status) std::memcpy(status + b0, h_status, (size_t)nb * 4);
     d->timer.collect();
     d->img_ready = false;
   }

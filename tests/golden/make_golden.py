@@ -421,8 +421,32 @@ def make_missing():
     np.savez_compressed(os.path.join(HERE, "missing.npz"), **out)
 
 
+def make_collinear():
+    """A Mode-B block with an exactly duplicated column: the reference's lstsq (mode.py:50-52, gelsd) returns the
+    minimum-norm weights, the engine's Cholesky reports the block singular and the replicate is dropped.  The fixture
+    pins both sides of that documented difference."""
+    from plspm_b200.synth import make_synthetic
+    X, pm = make_synthetic(300, 3, 3, 5)
+    X = X.copy()
+    X[:, 4] = X[:, 3]  # block 1: columns 3 and 4 identical
+    lvs = ["L0", "L1", "L2"]
+    mvs = ["x%d" % i for i in range(9)]
+    blocks = {lv: mvs[3 * i:3 * i + 3] for i, lv in enumerate(lvs)}
+    path = pd.DataFrame(pm, index=lvs, columns=lvs)
+    df = pd.DataFrame(X, columns=mvs)
+    out = {"X": X, "path": np.asarray(pm, dtype=np.int8), "block_sizes": np.array([3, 3, 3], dtype=np.int32)}
+    r = run_reference(df, path, blocks, {lv: Mode.B for lv in lvs}, Scheme.CENTROID, True)
+    out["ref/weights"] = r["weights"]
+    out["ref/r_squared"] = r["r_squared"]
+    out["ref/iterations"] = r["iterations"]
+    print("collinear Mode B: reference weights", np.round(r["weights"], 4), "iterations", r["iterations"])
+    np.savez_compressed(os.path.join(HERE, "collinear.npz"), **out)
+
+
 if __name__ == "__main__":
-    if "--only-hoc" in sys.argv:
+    if "--only-collinear" in sys.argv:
+        make_collinear()
+    elif "--only-hoc" in sys.argv:
         make_hoc()
     elif "--only-missing" in sys.argv:
         make_missing()
@@ -430,3 +454,4 @@ if __name__ == "__main__":
         main()
         make_hoc()
         make_missing()
+        make_collinear()

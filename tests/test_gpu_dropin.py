@@ -219,3 +219,28 @@ def test_bootstrap_with_missing_values_philox_replicates_vs_oracle(sat):
         ref, it, st = orc.replicate_row(g["X"], idx, g["block_sizes"], [0] * L, g["path"], "centroid", True)
         assert st == 0 and it == iters[b]
         np.testing.assert_allclose(w[b], ref[:len(mvs)], rtol=1e-6)
+
+
+def test_collinear_mode_b_block_raises_and_bootstrap_drops_it():
+    """Pinned difference to the reference (min-norm lstsq, mode.py:50-52): an exactly collinear Mode-B block is
+    reported singular -- the single fit raises, bootstrap replicates that hit it are dropped and counted."""
+    import os
+    from plspm_b200 import engine
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "collinear.npz"))
+    model = engine.Model(g["block_sizes"], [1, 1, 1], g["path"], True)
+    data = engine.Data(model, g["X"])
+    res = engine.fit(model, data, "centroid")
+    assert res["status"] == engine.STATUS_SINGULAR
+    rows, status, iters = engine.bootstrap(model, data, "centroid", 0, 20, seed=2)
+    assert (status == engine.STATUS_SINGULAR).all()  # every resample keeps columns 3 and 4 identical
+    mvs = ["x%d" % i for i in range(9)]
+    df = pd.DataFrame(g["X"], columns=mvs)
+    s_ = c.Structure()
+    s_.add_path(["L0"], ["L1", "L2"])
+    s_.add_path(["L1"], ["L2"])
+    config = c.Config(s_.path(), scaled=True)
+    for i, lv in enumerate(("L0", "L1", "L2")):
+        config.add_lv(lv, Mode.B, *[c.MV(m) for m in mvs[3 * i:3 * i + 3]])
+    if (np.asarray(s_.path().loc[["L0", "L1", "L2"], ["L0", "L1", "L2"]]) == g["path"]).all():
+        with pytest.raises(Exception, match="singular"):
+            Plspm(df, config)

@@ -159,6 +159,20 @@ def test_bootstrap_with_missing_values_vs_reference(case):
     np.testing.assert_allclose(out[:, P + L + 2 * ne:], g[tag + "loadings"], rtol=tol, atol=1e-12)
 
 
+def test_collinear_mode_b_block_oracle_follows_the_reference_min_norm():
+    """An exactly duplicated column in a Mode-B block: the reference's lstsq (mode.py:50-52, gelsd) returns the
+    minimum-norm weights (equal weights on the two copies; fixture tests/golden/collinear.npz generated by the
+    reference) and so does the oracle.  The CUDA solver works on S_ll (Cholesky) and reports STATUS_SINGULAR instead:
+    a DOCUMENTED DIFFERENCE pinned by tests/test_gpu_dropin.py::test_collinear_mode_b_block_raises_and_bootstrap_drops_it."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "collinear.npz"))
+    w = g["ref/weights"]
+    assert np.isfinite(w).all() and abs(w[3] - w[4]) < 1e-12  # the reference's min-norm answer
+    r = orc.fit(g["X"], g["block_sizes"], [orc.MODE_B] * 3, g["path"], "centroid", True)
+    assert r["status"] == 0 and r["iterations"] == int(g["ref/iterations"])
+    np.testing.assert_allclose(r["weights"], w, rtol=1e-7)
+    np.testing.assert_allclose(r["r_squared"], g["ref/r_squared"], rtol=1e-7, atol=1e-12)
+
+
 def test_effect_pairs_match_reference_effects_index(sat):
     lvs = list(sat["lvs"])
     pairs = orc.effect_pairs(sat["path"])
