@@ -41,11 +41,10 @@ class Bootstrap:
         two_stage = bool(calculator.config().hoc())
         buf = None
         if two_stage:
-            session, rows, status, iters = self._two_stage_rows(calculator, data, begin, count, seed, idx)
-            model = session.model
+            model, lvs, mvs, rows, status, iters = self._two_stage_rows(calculator, data, begin, count, seed, idx)
         else:
             session = calculator.session(data)
-            model = session.model
+            model, lvs, mvs = session.model, session.lvs, session.mvs
             buf = pdist.send_buffer(iterations, model.n_out)
         if two_stage:
             pass  # rows were produced replicate by replicate on the host side of the two engine fits
@@ -57,9 +56,10 @@ class Bootstrap:
             rows, status, iters = session.bootstrap(scheme, tol, its, begin, count, seed, idx)
         rows, status, iters = pdist.allgather_rows(rows, status, iters, iterations, model.n_out, device_buffer=buf)
         self._status, self._iterations, self._seed = status, iters, seed
+        if not (status == 0).any():  # (after the collective: every rank sees the same statuses and raises together)
+            raise Exception("Bootstrapping failed: no replicate could be estimated")
         rows = rows[status == 0]  # bootstrap.py:67-68
         w, r2, total, direct, load = model.split_row(rows)
-        lvs, mvs = session.lvs, session.mvs
         cols = mvs if two_stage else list(data.columns)  # stage-2 manifest variables include the constituents
         weights = pd.DataFrame(w, columns=mvs).loc[:, cols]
         loadings = pd.DataFrame(load, columns=mvs).loc[:, cols]
@@ -81,12 +81,24 @@ class Bootstrap:
     def _two_stage_rows(calculator, data, begin, count, seed, idx):
         """Higher-order constructs: the stage-2 manifest variables are the replicate's own stage-1 scores, so
         every replicate is a two-stage estimate of its resampled rows (bootstrap.py:54-66 as written: two
-        engine fits per replicate).  Failed replicates keep status != 0 and are dropped (bootstrap.py:67-68)."""
+        engine fits per replicate).  Failed replicates keep status != 0 and are dropped (bootstrap.py:67-68).
+        Nothing raises here: a rank whose replicates all fail must still reach the all-gather (the row layout
+        comes from the configuration, not from a successful fit)."""
         from plspm.estimator import Estimator
         from plspm_b200 import engine
-        estimator = Estimator(calculator.config())
+        config = calculator.config()
+        estimator = Estimator(config)
+        # layout of the stage-2 (structural) model: a construct's block = the scores of its constituents
+        path = config.path()
+        lvs = list(path)
+        blocks = {lv: (list(config.hoc()[lv]) if lv in config.hoc() else list(config.mvs(lv))) for lv in lvs}
+        mvs = [mv for lv in lvs for mv in blocks[lv]]
+        model = engine.Model([len(blocks[lv]) for lv in lvs], [config.mode(lv).value.engine_id for lv in lvs],
+                             path.loc[lvs, lvs].to_numpy(dtype=np.int8), True, numeric=True)
         n = data.shape[0]
-        rows, status, iters, session = None, np.ones(count, dtype=np.int32), np.zeros(count, dtype=np.int32), None
+        rows = np.zeros((count, model.n_out))
+        status, iters = np.ones(count, dtype=np.int32), np.zeros(count, dtype=np.int32)
+        ef, et = model.effects_from, model.effects_to
         for b in range(count):
             pick = idx[b] if idx is not None else engine.resample_indices(seed, begin + b, n)
             try:
@@ -96,16 +108,11 @@ class Bootstrap:
             except Exception:
                 continue
             session, res = estimator.last_result()
-            model = session.model
-            if rows is None:
-                rows = np.zeros((count, model.n_out))
-            ef, et = model.effects_from, model.effects_to
+            assert session.mvs == mvs and session.lvs == lvs
             rows[b] = np.concatenate([res["weights"], res["r_squared"], res["total_effects"][et, ef],
                                       res["path_coefficients"][et, ef], res["loadings"]])
             status[b], iters[b] = 0, res["iterations"]
-        if session is None:
-            raise Exception("Bootstrapping failed: no replicate could be estimated")
-        return session, rows, status, iters
+        return model, lvs, mvs, rows, status, iters
 
     def weights(self) -> pd.DataFrame:
         """Outer weights calculated from bootstrap validation."""
