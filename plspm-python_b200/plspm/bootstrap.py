@@ -45,7 +45,7 @@ class Bootstrap:
         else:
             session = calculator.session(data)
             model, lvs, mvs = session.model, session.lvs, session.mvs
-            buf = pdist.send_buffer(iterations, model.n_out)
+            buf = None if getattr(session, "host", False) else pdist.send_buffer(iterations, model.n_out)
         if two_stage:
             pass  # rows were produced replicate by replicate on the host side of the two engine fits
         elif buf is not None:  # NCCL: the solver writes its rows straight into the all-gather send buffer

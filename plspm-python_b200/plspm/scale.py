@@ -1,8 +1,8 @@
 """Measurement scales of non-metric data (reference plspm/scale.py:91-104).
 
-Kept importable for API compatibility.  The non-metric (optimal scaling) path is outside the
-accelerated hot path: configuring any scale makes Plspm raise
-NotImplementedError instead of silently running something else.
+NUM / RAW configurations run the non-metric estimator on the device (csrc/solver_num.h); ORD / NOM (optimal
+scaling, scale.py:42-89) and non-metric data with missing values take the reference-style host path of
+plspm/nonmetric_host.py.
 """
 from enum import Enum
 

@@ -41,7 +41,14 @@ class WeightsCalculatorFactory:
         key = (id(data), tuple(path.columns), self._config.scaled() if scaled is None else scaled)
         hit = self._sessions.get(key)
         if hit is None or hit[0] is not data:
-            hit = (data, EngineSession(self._config, data, path, scaled))
+            config = self._config
+            host = (not config.metric()) and (not config.numeric() or bool(data.loc[:, [mv for lv in list(path) for mv in config.mvs(lv)]].isnull().values.any()))
+            if host and not config.hoc():
+                # ordinal / nominal scales, non-metric data with missing values: the reference-style host path
+                from plspm.nonmetric_host import HostNonmetricSession
+                hit = (data, HostNonmetricSession(config, data, path, self._correction))
+            else:
+                hit = (data, EngineSession(config, data, path, scaled))
             self._sessions[key] = hit
         return hit[1]
 

@@ -421,6 +421,84 @@ def make_missing():
     np.savez_compressed(os.path.join(HERE, "missing.npz"), **out)
 
 
+def make_categorical():
+    """Ordinal / nominal scales and non-metric missing data on russa (reference tests/test_regression_nonmetric.py:
+    97-137): outputs of the reference + the R golden inner summaries of its own tests."""
+    from plspm.scale import Scale
+    tdata = os.path.join(REF, "tests", "data")
+    russa = pd.read_csv(os.path.join(tdata, "russa.csv"), index_col=0)
+    st = c.Structure()
+    st.add_path(["AGRI", "IND"], ["POLINS"])
+    rpath = st.path()
+    lvs = list(rpath)
+    out = {"columns": np.array(list(russa.columns)), "X": russa.to_numpy(dtype=np.float64), "lvs": np.array(lvs),
+           "path": rpath.loc[lvs, lvs].to_numpy(dtype=np.int8)}
+    O, Nm = Scale.ORD, Scale.NOM
+    cases = {
+        "categorical": (Mode.A, {"IND": [("gnpr", O), ("labo", O)], "POLINS": [("ecks", None), ("death", None), ("demo", Nm), ("inst", None)],
+                                 "AGRI": [("gini", None), ("farm", None), ("rent", None)]}, "russa.categorical.inner_summary.csv", None),
+        "categorical_mode_b": (Mode.B, {"AGRI": [("gini", None), ("farm", None), ("rent", None)], "IND": [("gnpr", O), ("labo", O)],
+                                        "POLINS": [("ecks", None), ("death", None), ("demo", Nm), ("inst", None)]},
+                               "russa.categorical.mode_b.inner_summary.csv", None),
+        "missing": (Mode.A, {"AGRI": [("gini", None), ("farm", None), ("rent", None)], "IND": [("gnpr", None), ("labo", None)],
+                             "POLINS": [("ecks", None), ("death", None), ("demo", None), ("inst", None)]},
+                    "russa.missing.inner_summary.csv", [(0, 0), (3, 3), (5, 5)]),
+    }
+    for name, (mode, spec, csv, holes) in cases.items():
+        data = russa.copy()
+        for r, col in holes or []:
+            data.iloc[r, col] = np.nan
+        for sname in (("centroid", "factorial", "path") if name == "categorical" else ("centroid",)):
+            config = c.Config(rpath, default_scale=Scale.NUM)
+            for lv, mvs in spec.items():
+                config.add_lv(lv, mode, *[c.MV(m, sc) for m, sc in mvs])
+            calc = Plspm(data, config, SCHEMES[sname], 100, 0.0000001)
+            mvs_all = [m for lv in lvs for m, _ in spec[lv]]
+            om = calc.outer_model()
+            tag = "%s/%s/" % (name, sname)
+            out[tag + "mvs"] = np.array(mvs_all)
+            out[tag + "weights"] = om.loc[mvs_all, "weight"].to_numpy(dtype=np.float64)
+            out[tag + "loadings"] = om.loc[mvs_all, "loading"].to_numpy(dtype=np.float64)
+            out[tag + "scores"] = calc.scores().loc[:, lvs].to_numpy(dtype=np.float64)
+            out[tag + "path_coefficients"] = calc.path_coefficients().loc[lvs, lvs].to_numpy(dtype=np.float64)
+            out[tag + "crossloadings"] = calc.crossloadings().loc[mvs_all, lvs].to_numpy(dtype=np.float64)
+            isum = calc.inner_summary().loc[lvs]
+            for col in ("r_squared", "block_communality", "mean_redundancy", "ave"):
+                out[tag + "inner_summary/" + col] = isum[col].to_numpy(dtype=np.float64)
+            out[tag + "gof"] = np.float64(calc.goodness_of_fit())
+            print(tag, "weights", np.round(out[tag + "weights"], 4))
+        exp = pd.read_csv(os.path.join(tdata, csv), index_col=0).loc[lvs]
+        for col in ("r_squared", "block_communality", "mean_redundancy", "ave"):
+            out["R/%s/%s" % (name, col)] = exp[col].to_numpy(dtype=np.float64)
+        out["R/%s/type" % name] = np.array([str(v) for v in exp["type"]])
+        if holes:
+            out[name + "/holes"] = np.array(holes, dtype=np.int64)
+    # a few bootstrap replicates of the categorical model with injected indices (bootstrap.py:54-66)
+    idx = np.random.default_rng(5).integers(0, russa.shape[0], (6, russa.shape[0]), dtype=np.int32)
+    out["categorical/boot/idx"] = idx
+    mode, spec, _, _ = cases["categorical"]
+    config = c.Config(rpath, default_scale=Scale.NUM)
+    for lv, mvs in spec.items():
+        config.add_lv(lv, mode, *[c.MV(m, sc) for m, sc in mvs])
+    filtered = config.filter(russa)
+    n = filtered.shape[0]
+    calculator = ref_weights.WeightsCalculatorFactory(config, 100, 1e-7, np.sqrt(n / (n - 1)), Scheme.CENTROID)
+    estimator = Estimator(config)
+    mvs_all = [m for lv in lvs for m, _ in spec[lv]]
+    W = np.full((len(idx), len(mvs_all)), np.nan)
+    ok = np.zeros(len(idx), dtype=np.int8)
+    for b in range(len(idx)):
+        try:
+            fd, sc, w = estimator.estimate(calculator, filtered.iloc[idx[b], :])
+            W[b] = w.loc[mvs_all, "weight"].to_numpy()
+            ok[b] = 1
+        except Exception as e:
+            print("categorical replicate", b, "failed in the reference:", repr(e))
+    out["categorical/boot/weights"], out["categorical/boot/ok"] = W, ok
+    assert not [k for k, v in out.items() if np.asarray(v).dtype == object]
+    np.savez_compressed(os.path.join(HERE, "categorical.npz"), **out)
+
+
 def make_collinear():
     """A Mode-B block with an exactly duplicated column: the reference's lstsq (mode.py:50-52, gelsd) returns the
     minimum-norm weights, the engine's Cholesky reports the block singular and the replicate is dropped.  The fixture
@@ -446,6 +524,8 @@ def make_collinear():
 if __name__ == "__main__":
     if "--only-collinear" in sys.argv:
         make_collinear()
+    elif "--only-categorical" in sys.argv:
+        make_categorical()
     elif "--only-hoc" in sys.argv:
         make_hoc()
     elif "--only-missing" in sys.argv:
@@ -455,3 +535,4 @@ if __name__ == "__main__":
         make_hoc()
         make_missing()
         make_collinear()
+        make_categorical()

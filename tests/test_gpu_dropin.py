@@ -147,11 +147,10 @@ def test_argument_rules_and_errors(sat):
         nonmetric = c.Config(satisfaction_path_matrix(), default_scale=scale)
         for lv in ("IMAG", "EXPE", "QUAL", "VAL", "SAT", "LOY"):
             nonmetric.add_lv_with_columns_named(lv, Mode.A, df, lv.lower())
-        if ok:  # numeric scales run on the device (tests/test_gpu_nonmetric.py)
-            assert Plspm(df, nonmetric).iterations() > 0
-        else:   # ordinal / nominal quantification is outside the accelerated path and says so
-            with pytest.raises(NotImplementedError):
-                Plspm(df, nonmetric)
+        # numeric scales run on the device (tests/test_gpu_nonmetric.py); ordinal / nominal quantification takes the
+        # reference-style host path (plspm/nonmetric_host.py, tests/test_host_nonmetric.py)
+        assert ok or scale in (Scale.ORD, Scale.NOM)
+        assert Plspm(df, nonmetric).iterations() > 0
 
 
 def test_missing_values_single_fit_is_mean_imputed(sat):
