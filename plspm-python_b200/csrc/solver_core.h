@@ -105,6 +105,17 @@ PL_HD void vote_add(int* votes, int l, int v) {
 #endif
 }
 
+// votes[l] += the sum of v over the warp: one shared-memory atomic per warp instead of one per lane.  Every lane of
+// the warp must call it (lanes with nothing to add pass 0).
+PL_HD void vote_add_warp(int* votes, int l, int v) {
+#if PL_DEVICE_BUILD
+  const int s = __reduce_add_sync(0xffffffffu, v);
+  if ((threadIdx.x & 31) == 0 && s != 0) atomicAdd(&votes[l], s);
+#else
+  votes[l] += v;
+#endif
+}
+
 // raw weighted cross moment sum_i c_i x~_ip x~_iq from the tile store
 PL_HD double gram_raw(const ModelView& M, const double* G, int p, int q) {
   int t = M.tile_of[(p >> 3) * M.ns + (q >> 3)];
@@ -254,9 +265,22 @@ PL_HD void solve_replicate(const SolveArgs& A, double* smem) {
       int l = M.pair_l[d], j = M.pair_j[d];
       if (r >= M.lv_k[l]) continue;
       int kj = M.lv_k[j], ol = M.lv_off[l], oj = M.lv_off[j];
-      double acc = 0.0;
-      for (int c = 0; c < kj; ++c) acc += PL_S(ol + r, oj + c) * w[oj + c];
-      V[M.pair_voff[d] + r] = acc;
+      // sum_c S(p, oj + c) w_c with S = (G/N - m m') iss, slot by slot of block j (blocks start on slot boundaries):
+      // one tile lookup per slot instead of one per element
+      const int pp = ol + r;
+      double g = 0.0, mw = 0.0;
+      for (int c0 = 0; c0 < kj; c0 += SLOT) {
+        const int tt = M.tile_of[(pp >> 3) * M.ns + ((oj + c0) >> 3)];
+        const double* T = tt >= 0 ? A.G + (size_t)tt * TILE + (pp & 7) * SLOT : A.G + (size_t)(-(tt + 2)) * TILE + (pp & 7);
+        const int step = tt >= 0 ? 1 : SLOT;
+        const int cn = kj - c0 < SLOT ? kj - c0 : SLOT;
+        for (int c = 0; c < cn; ++c) {
+          const double wc = w[oj + c0 + c];
+          g += T[c * step] * wc;
+          mw += m[oj + c0 + c] * wc;
+        }
+      }
+      V[M.pair_voff[d] + r] = (g * invN - m[pp] * mw) * iss;
     }
     PL_SYNC();
     // ---- population variance of Y_l, standardisation factor (weights.py:44) ---------------------
@@ -423,32 +447,50 @@ PL_HD void solve_replicate(const SolveArgs& A, double* smem) {
         bsum[l] = 1.0e-3 * sqrt(wp2 * gh);
         sgn[l] = sh;  // (sgn is free until the votes are counted) mean of the un-centred score
       }
+      // the whole LV-side factor of the bound: E = sum_i xh_ip (c_i t_il) has the sign of cov(x_p, score_l); fp16
+      // operands + truncating fp32 tensor-core accumulation give |fl(E) - E| <= gamma sqrt(sum c xh^2) sqrt(sum c t^2)
+      // (Cauchy-Schwarz), sum c t^2 = N / iss (unit-variance scores on the treated scale) + N sh^2 when the scores
+      // were not centred.  2e-3 covers the fp16 roundings of both MMA operands (2^-10), <= 1100 truncating fp32
+      // accumulation steps per CTA (2^-22 each, measured 1e-7) and the fp32 adds that join the row ranges.
+      bsum[l] = 2.0e-3 * sqrt(N / iss + (A.fast_uncentred ? N * sh * sh : 0.0)) + bsum[l];
     }
   }
   PL_SYNC();
+  if (A.phase == 3) {
+    // thread = manifest variable, loop over the LVs: the per-column factors stay in registers, the strided loads of
+    // the cross moments are independent of each other, votes are summed over the warp before they touch shared memory
+    for (int p0 = 0; p0 < Ppad; p0 += nt) {
+      const int p = p0 + tid;
+      const int lp = p < Ppad ? M.col_lv[p] : -1;
+      const double colf = lp >= 0 ? wold[p] : 0.0;
+      const double shift = (lp >= 0 && A.fast_uncentred) ? A.colsum[p] * A.inv_sd[p] : 0.0;
+      const float* cf = A.fast_cross + ((size_t)(lp >= 0 ? p : 0) * L) * A.fast_nb + A.fast_b;
+      for (int l = 0; l < L; ++l) {
+        int dv = 0, du = 0;
+        if (lp >= 0) {
+          if (!M.omega[lp * L + l]) {
+            // E = E' - sh_l sum_i c_i xh_ip (exact in fp64) when the scores behind E' were not centred
+            const double v = (double)cf[(size_t)l * A.fast_nb] - (A.fast_uncentred ? sgn[l] * shift : 0.0);
+            if (v - v == 0.0 && fabs(v) > bsum[l] * colf) dv = v < 0.0 ? -1 : 1;
+            else du = 1;
+          } else {  // LV pair inside the tile set: exact covariance from the Gram tiles
+            double acc = 0.0;
+            const int o = M.lv_off[l];
+            for (int c = 0; c < M.lv_k[l]; ++c) acc += PL_S(p, o + c) * u[o + c];
+            if (A.crossloadings) A.crossloadings[(size_t)M.col_src[p] * L + l] = acc / sqrt(PL_S(p, p));
+            if (acc == acc) dv = signbit(acc) ? -1 : 1;
+          }
+        }
+        vote_add_warp(votes, l, dv);
+        vote_add_warp(unc, l, du);
+      }
+    }
+  } else
   // cov(x_p, score_l) for ALL (p, l): every manifest variable votes on every LV (quirk Q6)
   for (int t = tid; t < Ppad * L; t += nt) {
     int p = t / L, l = t - p * L;
     if (M.col_lv[p] < 0) continue;
     double acc = 0.0;
-    if (A.phase == 3 && !M.omega[M.col_lv[p] * L + l]) {
-      // E = sum_i xh_ip (c_i t_il) has the sign of cov(x_p, score_l); fp16 operands + fp32 tensor-core
-      // accumulation over <= 4096-row chunks give |fl(E) - E| <= gamma * sqrt(sum c xh^2) * sqrt(sum c t^2)
-      // (Cauchy-Schwarz); sum c t^2 = N / iss because the scores have unit variance on the treated scale
-      double v = (double)A.fast_cross[((size_t)p * L + l) * A.fast_nb + A.fast_b];
-      double t2 = N / iss;
-      if (A.fast_uncentred) {
-        // E = E' - sh_l sum_i c_i xh_ip (exact in fp64); the un-centred scores have sum c t'^2 = N/iss + N sh^2.
-        // 2e-3 covers the fp16 roundings of both MMA operands (2^-10), <= 1100 truncating fp32 accumulation steps
-        // per CTA (2^-22 each, measured 1e-7) and the fp32 adds that join the row ranges.
-        v -= sgn[l] * A.colsum[p] * A.inv_sd[p];
-        t2 += N * sgn[l] * sgn[l];
-      }
-      const double bound = (2.0e-3 * sqrt(t2) + bsum[l]) * wold[p];
-      if (v - v == 0.0 && fabs(v) > bound) vote_add(votes, l, v < 0.0 ? -1 : 1);
-      else vote_add(unc, l, 1);
-      continue;
-    }
     if (A.phase == 2) {
       const double raw = A.cross[((size_t)(p >> 3) * M.ng + (l >> 3)) * TILE + (p & 7) * SLOT + (l & 7)];
       acc = (raw * invN - m[p] * bsum[l]) * iss;
