@@ -28,7 +28,7 @@
 #pragma once
 #include "umma.cuh"
 
-constexpr int VM_STAGES = 4, VM_STAGE_ROWS = 64, VM_CHUNK = 64, VM_THREADS = 640, VM_MAX_ROWS = 16384, VM_MAX_K16 = 4;
+constexpr int VM_MAX_STAGES = 6, VM_STAGE_ROWS = 64, VM_CHUNK = 64, VM_THREADS = 640, VM_MAX_ROWS = 16384, VM_MAX_K16 = 4;
 constexpr uint32_t VM_XT_BYTES = 256 * 128, VM_C8_BYTES = 128 * 64, VM_XL_BYTES = 64 * 32, VM_W_BYTES = 128 * 32;
 // tensor-memory columns: E [0,256), scores D1 2 x 64 at 256, fp16 A operand 2 x 32 at 384
 constexpr uint32_t VM_COL_E = 0, VM_COL_D1 = 256, VM_COL_A = 384;
@@ -49,12 +49,21 @@ struct VoteMmaParams {
   int n_rep_tiles, n_pchunks, ksplit;
   int rows_per_cta;      // multiple of VM_STAGE_ROWS, <= VM_MAX_ROWS
   int k16_max;           // K = 16 steps of the widest block (<= VM_MAX_K16): sizes the ring stages
+  int stages;            // ring depth (vm_stages(k16_max): as many as fit the shared memory, <= VM_MAX_STAGES)
   unsigned long long* stats;  // optional [16]: cycles waited per barrier, summed over CTAs (PLSPM_KERNEL_STATS)
 };
 
 __host__ __device__ inline uint32_t vm_stage_bytes(int k16_max) { return VM_XT_BYTES + VM_C8_BYTES + (uint32_t)k16_max * VM_XL_BYTES; }
-__host__ inline size_t vm_smem_bytes(int k16_max) {
-  return 1024 + (size_t)VM_STAGES * vm_stage_bytes(k16_max) + (size_t)k16_max * VM_W_BYTES;
+// Ring depth: a stage is held from its bulk copies until the vote MMA of its chunk has completed (three chunk periods:
+// score MMA, epilogue, vote MMA), so every stage beyond four is a copy in flight; take what the 227 KB allow.
+__host__ inline int vm_stages(int k16_max, int max_smem = 227 * 1024) {
+  static const int forced = getenv("PLSPM_VOTE_STAGES") ? atoi(getenv("PLSPM_VOTE_STAGES")) : 0;
+  const int fit = (int)(((size_t)max_smem - 2048 - (size_t)k16_max * VM_W_BYTES) / vm_stage_bytes(k16_max));
+  const int st = forced > 0 ? forced : fit;
+  return st < 3 ? 3 : (st > VM_MAX_STAGES ? VM_MAX_STAGES : (st > fit ? fit : st));
+}
+__host__ inline size_t vm_smem_bytes(int k16_max, int stages) {
+  return 1024 + (size_t)stages * vm_stage_bytes(k16_max) + (size_t)k16_max * VM_W_BYTES;
 }
 
 #define VM_TIMED(acc, ...)                                \
@@ -67,13 +76,14 @@ __host__ inline size_t vm_smem_bytes(int k16_max) {
 __global__ void __launch_bounds__(VM_THREADS, 1) vote_mma_kernel(const VoteMmaParams P) {
   using namespace umma;
   extern __shared__ uint8_t vm_smem_raw[];
-  // barriers (8 bytes each): full[4] | empty[4] | d1_full[2] | d1_empty[2] | a_full[2] | e_full
-  __shared__ uint64_t bars[15];
+  // barriers (8 bytes each): full[6] | empty[6] | d1_full[2] | d1_empty[2] | a_full[2] | e_full
+  __shared__ uint64_t bars[19];
   __shared__ uint32_t tmem_base_sm;
-  constexpr int B_FULL = 0, B_EMPTY = 4, B_D1F = 8, B_D1E = 10, B_AF = 12, B_EF = 14;
+  constexpr int B_FULL = 0, B_EMPTY = 6, B_D1F = 12, B_D1E = 14, B_AF = 16, B_EF = 18;
+  const int S = P.stages;
   uint8_t* smem = vm_smem_raw + ((1024u - (s32(vm_smem_raw) & 1023u)) & 1023u);
   const uint32_t stage_bytes = vm_stage_bytes(P.k16_max);
-  uint8_t* wtile = smem + (size_t)VM_STAGES * stage_bytes;  // [k16][128 x 16] fp16, no swizzle (8x16B core matrices)
+  uint8_t* wtile = smem + (size_t)S * stage_bytes;  // [k16][128 x 16] fp16, no swizzle (8x16B core matrices)
 
   // tile of this CTA
   int t = blockIdx.x;
@@ -93,7 +103,7 @@ __global__ void __launch_bounds__(VM_THREADS, 1) vote_mma_kernel(const VoteMmaPa
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 2) tmem_alloc(&tmem_base_sm, 512);
   if (threadIdx.x == 0) {
-    for (int s = 0; s < 4; ++s) { bar_init(&bars[B_FULL + s], 1); bar_init(&bars[B_EMPTY + s], 1); }
+    for (int s = 0; s < VM_MAX_STAGES; ++s) { bar_init(&bars[B_FULL + s], 1); bar_init(&bars[B_EMPTY + s], 1); }
     for (int s = 0; s < 2; ++s) { bar_init(&bars[B_D1F + s], 1); bar_init(&bars[B_D1E + s], 8); bar_init(&bars[B_AF + s], 8); }
     bar_init(&bars[B_EF], 1);
     bar_fence_init();
@@ -127,14 +137,14 @@ __global__ void __launch_bounds__(VM_THREADS, 1) vote_mma_kernel(const VoteMmaPa
                      xl_step = (size_t)P.n_blocks * VM_XL_BYTES;
         const uint32_t xl_bytes = (uint32_t)k16 * VM_XL_BYTES, tx = VM_XT_BYTES + VM_C8_BYTES + xl_bytes;
         long long w1 = 0;
-        for (int j = 0; j < n_chunks; ++j, xt += xt_step, c8 += c8_step, xl += xl_step) {
-          const int s = j & 3;
+        for (int j = 0, s = 0, ph = 0; j < n_chunks; ++j, xt += xt_step, c8 += c8_step, xl += xl_step) {
           const uint32_t st = smem0 + (uint32_t)s * stage_bytes, fb = bar0 + 8 * (B_FULL + s);
-          VM_TIMED(w1, bar0 + 8 * (B_EMPTY + s), ((j >> 2) & 1) ^ 1, 1);
+          VM_TIMED(w1, bar0 + 8 * (B_EMPTY + s), ph ^ 1, 1);
           bar_expect_tx_a(fb, tx);
           bulk_load_a(st, xt, VM_XT_BYTES, fb);
           bulk_load_a(st + VM_XT_BYTES, c8, VM_C8_BYTES, fb);
           bulk_load_a(st + VM_XT_BYTES + VM_C8_BYTES, xl, xl_bytes, fb);
+          if (++s == S) { s = 0; ph ^= 1; }
         }
         if (P.stats) atomicAdd(P.stats + 1, (unsigned long long)w1);
       }
@@ -147,15 +157,16 @@ __global__ void __launch_bounds__(VM_THREADS, 1) vote_mma_kernel(const VoteMmaPa
         const uint32_t d1_col = tbase + VM_COL_D1;
         long long w3 = 0, w4 = 0;
         const long long t_begin = clock64();
-        for (int j = 0; j < n_chunks; ++j) {
-          const int s = j & 3, u = j & 1;
-          VM_TIMED(w3, bar0 + 8 * (B_FULL + s), (j >> 2) & 1, 3);
+        for (int j = 0, s = 0, ph = 0; j < n_chunks; ++j) {
+          const int u = j & 1;
+          VM_TIMED(w3, bar0 + 8 * (B_FULL + s), ph, 3);
           VM_TIMED(w4, bar0 + 8 * (B_D1E + u), ((j >> 1) & 1) ^ 1, 4);
           tc_fence_after();
           const uint64_t xdesc = xdesc0 + (uint64_t)(sdesc * s);
           for (int q = 0; q < k16; ++q)
             mma_f16_ss(d1_col + 64 * u, wdesc + (uint64_t)(q * (VM_W_BYTES >> 4)), xdesc + (uint64_t)(q * (VM_XL_BYTES >> 4)), idesc1, q ? 1u : 0u);
           mma_commit_a(bar0 + 8 * (B_D1F + u));
+          if (++s == S) { s = 0; ph ^= 1; }
         }
         if (P.stats) {
           atomicAdd(P.stats + 3, (unsigned long long)w3);
@@ -172,8 +183,8 @@ __global__ void __launch_bounds__(VM_THREADS, 1) vote_mma_kernel(const VoteMmaPa
         const uint32_t a_col = tbase + VM_COL_A, e_col = tbase + VM_COL_E;
         long long w2 = 0;
         const long long t_begin = clock64();
-        for (int j = 0; j < n_chunks; ++j) {
-          const int s = j & 3, u = j & 1;
+        for (int j = 0, s = 0; j < n_chunks; ++j) {
+          const int u = j & 1;
           VM_TIMED(w2, bar0 + 8 * (B_AF + u), (j >> 1) & 1, 2);
           // (a_full of chunk j implies full[s]: the epilogue waited for it)
           tc_fence_after();
@@ -183,6 +194,7 @@ __global__ void __launch_bounds__(VM_THREADS, 1) vote_mma_kernel(const VoteMmaPa
             mma_f16_ts(e_col, a_col + 32 * u + 8 * k, bdesc + 2 * k, idesc2, (j | k) ? 1u : 0u);
           // the ring stage is free, and so is the A buffer (the epilogue of chunk j + 2 waits for the same event)
           mma_commit_a(bar0 + 8 * (B_EMPTY + s));
+          if (++s == S) s = 0;
         }
         mma_commit_a(bar0 + 8 * B_EF);
         if (P.stats) {
@@ -203,12 +215,12 @@ __global__ void __launch_bounds__(VM_THREADS, 1) vote_mma_kernel(const VoteMmaPa
       const int u = grp;
       long long w5 = 0, w7 = 0;
       for (int j = grp; j < n_chunks; j += 2) {
-        const int s = j & 3, n = j >> 1;  // n: use count of this group's buffers
+        const int s = j % S, n = j >> 1;  // n: use count of this group's buffers
         VM_TIMED(w5, bar0 + 8 * (B_D1F + u), n & 1, 5);
         tc_fence_after();
         uint32_t tt[32];
         tmem_ld32(lane_addr + VM_COL_D1 + 64 * u + 32 * h, tt);
-        bar_wait_a(bar0 + 8 * (B_FULL + s), (j >> 2) & 1, 6);  // (complete long ago: acquires the bulk-copy writes)
+        bar_wait_a(bar0 + 8 * (B_FULL + s), (j / S) & 1, 6);  // (complete long ago: acquires the bulk-copy writes)
         const uint8_t* st = smem + (size_t)s * stage_bytes;
         const uint4 ca = *reinterpret_cast<const uint4*>(st + c8a);
         const uint4 cb = *reinterpret_cast<const uint4*>(st + c8b);
@@ -227,7 +239,7 @@ __global__ void __launch_bounds__(VM_THREADS, 1) vote_mma_kernel(const VoteMmaPa
           pk[e >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
         }
         // MMA 2 of this group's previous chunk (j - 2) has read the A buffer: the event that released its ring stage
-        if (j >= 2) VM_TIMED(w7, bar0 + 8 * (B_EMPTY + ((j - 2) & 3)), ((j - 2) >> 2) & 1, 7);
+        if (j >= 2) VM_TIMED(w7, bar0 + 8 * (B_EMPTY + ((j - 2) % S)), ((j - 2) / S) & 1, 7);
         tc_fence_after();
         tmem_st16(lane_addr + VM_COL_A + 32 * u + 16 * h, pk);
         tmem_wait_st();

@@ -1281,7 +1281,8 @@ static int run_batch(plspm_data* d, int64_t nb, const uint32_t* counts_dev, cons
       if (kstats && !kstats_dev) CK(cudaMalloc((void**)&kstats_dev, 16 * 8));
       if (kstats) CK(cudaMemsetAsync(kstats_dev, 0, 16 * 8, st));
       vp.stats = kstats ? kstats_dev : nullptr;
-      const size_t vm_smem = vm_smem_bytes(vp.k16_max);
+      vp.stages = vm_stages(vp.k16_max, d->max_smem);
+      const size_t vm_smem = vm_smem_bytes(vp.k16_max, vp.stages);
       CK(cudaFuncSetAttribute(vote_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vm_smem));
       CK(cudaMemsetAsync(Cf, 0, (size_t)ldl * h.L * h.Ppad * sizeof(float), st));
       const int64_t grid = tiles0 * vp.ksplit;
