@@ -957,7 +957,7 @@ static int redo_exact(plspm_data* d, int64_t n_list, const int* rep_map_dev, con
   b.phase = 2; b.rep_map = rep_map_dev;
   b.state = D(bb.state); b.state_stride = (int64_t)plspm::solver_state_doubles(m->dv); b.resume = 1;
   b.out_rows = out_rows; b.out_stride = h.n_out();
-  const size_t smem = h.solver_smem_doubles() * sizeof(double);
+  const size_t smem = h.solver_core_smem_doubles() * sizeof(double);
   d->timer.begin(ST_SOLVE, st);
   solve_kernel<<<(unsigned)n_list, SOLVE_THREADS, smem, st>>>(b);
   d->timer.end(st);
@@ -1214,7 +1214,7 @@ static int run_batch(plspm_data* d, int64_t nb, const uint32_t* counts_dev, cons
     b.iters = (int*)(base + bb.iters); b.status = (int*)(base + bb.status);
     b.phase = 0;
     b.out_rows = out_rows; b.out_stride = hb.n_out();
-    const size_t smem_b = hb.solver_smem_doubles() * sizeof(double);
+    const size_t smem_b = hb.solver_core_smem_doubles() * sizeof(double);
     if (smem_b > (size_t)d->max_smem) return fail(PLSPM_ERR_UNSUPPORTED, "model too large for the solver's shared memory");
     CK(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
     d->timer.begin(ST_SOLVE, st);
@@ -1232,7 +1232,7 @@ static int run_batch(plspm_data* d, int64_t nb, const uint32_t* counts_dev, cons
   if (!h.full) { b.state = D(bb.state); b.state_stride = (int64_t)plspm::solver_state_doubles(m->dv); }
   b.wf = h.full ? nullptr : D(bb.wf);
   b.cross = h.full ? nullptr : D(bb.CG); b.cross_stride = (int64_t)h.n_cross * TILE;
-  const size_t smem = h.solver_smem_doubles() * sizeof(double);
+  const size_t smem = h.solver_core_smem_doubles() * sizeof(double);
   if (smem > (size_t)d->max_smem) return fail(PLSPM_ERR_UNSUPPORTED, "model too large for the solver's shared memory");
   CK(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (!h.full) {

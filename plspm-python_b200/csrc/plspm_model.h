@@ -66,6 +66,9 @@ struct HostModel {
   int n_out() const { return 2 * P + L + 2 * n_eff; }
   // shared-memory doubles the solver needs (see solver_core.h layout)
   size_t solver_smem_doubles() const { return (size_t)4 * Ppad + n_v + 4 * (size_t)L + 3 * (size_t)L * L + 40 + 2 * ((L + 1) / 2) + 8; }
+  // solve_replicate (solver_core.h) keeps TWO L x L arrays (the path coefficients reuse the inner weights' storage, the
+  // total effects the score correlations'): 8 KB less for L = 32, which is a sixth resident CTA per SM on c3
+  size_t solver_core_smem_doubles() const { return solver_smem_doubles() - (size_t)L * L; }
   ModelView host_view() const;
 };
 

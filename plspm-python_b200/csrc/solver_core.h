@@ -168,7 +168,7 @@ PL_HD bool regress_on_predecessors(const ModelView& M, const double* R, int i, d
   return true;
 }
 
-// Shared-memory layout (doubles): see HostModel::solver_smem_doubles().
+// Shared-memory layout (doubles): see HostModel::solver_core_smem_doubles().
 PL_HD void solve_replicate(const SolveArgs& A, double* smem) {
   const ModelView& M = A.M;
   const int L = M.L, Ppad = M.Ppad, tid = PL_TID, nt = PL_NT;
@@ -181,10 +181,10 @@ PL_HD void solve_replicate(const SolveArgs& A, double* smem) {
   double* sgn = dinv + L;            // [L]
   double* r2 = sgn + L;              // [L]
   double* bsum = r2 + L;             // [L]
-  double* R = bsum + L;              // [L*L]
-  double* E = R + (size_t)L * L;     // [L*L]  inner weights; reused for total effects
-  double* Bm = E + (size_t)L * L;    // [L*L]  path coefficients
-  double* red = Bm + (size_t)L * L;  // [40] reduction scratch + flags
+  double* R = bsum + L;              // [L*L]  score correlations; after the inner model: total effects
+  double* E = R + (size_t)L * L;     // [L*L]  inner weights (dead after the iteration)
+  double* Bm = E;                    //        ... then the path coefficients
+  double* red = E + (size_t)L * L;   // [40] reduction scratch + flags
   int* flag = (int*)(red + 34);      // [0] status
   int* votes = (int*)(red + 40);     // [L] ints
   int* unc = votes + 2 * ((L + 1) / 2);  // [L] ints: undecided voters (phase 3)
@@ -547,7 +547,7 @@ PL_HD void solve_replicate(const SolveArgs& A, double* smem) {
   PL_SYNC();
   if (status == STATUS_OK) status = flag[0];
   // ---- total effects (inner_model.py:33-49): T = B + B T, column by column ----------------------
-  double* T = E;
+  double* T = R;  // (the score correlations are dead: the regressions above were their last readers)
   for (int j = tid; j < L; j += nt)
     for (int i = 0; i < L; ++i) {
       double acc = Bm[i * L + j];

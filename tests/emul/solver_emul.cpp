@@ -68,7 +68,7 @@ extern "C" int emul_fit(int L, const int32_t* block_sizes, const int8_t* modes, 
         for (int c = 0; c < SLOT; ++c) g[r * SLOT + c] += xa[r] * (cnt[i] * xb[c]);
     }
   }
-  std::vector<double> smem(m.solver_smem_doubles(), 0.0), ws(m.ws_doubles, 0.0), coef(Pp, 0.0), shift(L, 0.0);
+  std::vector<double> smem(m.solver_core_smem_doubles(), 0.0), ws(m.ws_doubles, 0.0), coef(Pp, 0.0), shift(L, 0.0);
   SolveArgs A;
   std::memset(&A, 0, sizeof(A));
   A.M = m.host_view();
