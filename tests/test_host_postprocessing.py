@@ -139,3 +139,31 @@ def test_util_helpers_match_the_reference_semantics():
     t = util.treat_numpy(y)
     np.testing.assert_allclose(np.nanmean(t), 0.0, atol=1e-15)
     np.testing.assert_allclose(np.nanstd(t, ddof=1), 1.0)
+
+
+def test_unidimensionality_with_no_more_observations_than_manifest_variables():
+    """N <= block size: the reference runs its PCA on the transposed block (unidimensionality.py:46); mirrored here and
+    checked against the reference's literal computation with scikit-learn."""
+    sk = pytest.importorskip("sklearn.decomposition")
+    import plspm.config as c
+    from plspm.mode import Mode
+    rng = np.random.default_rng(3)
+    n, k = 5, 7
+    cols = ["a%d" % i for i in range(k)] + ["b0", "b1"]
+    df = pd.DataFrame(np.column_stack([rng.normal(size=(n, k)) + rng.normal(size=(n, 1)), rng.normal(size=(n, 2))]), columns=cols)
+    s = c.Structure()
+    s.add_path(["A"], ["B"])
+    cfg = c.Config(s.path(), scaled=False)
+    cfg.add_lv("A", Mode.A, *[c.MV(m) for m in cols[:k]])
+    cfg.add_lv("B", Mode.A, c.MV("b0"), c.MV("b1"))
+    corr_n = np.sqrt(n / (n - 1))
+    ours = Unidimensionality(cfg, df, corr_n).summary().loc["A"]
+    blk = df[cols[:k]]
+    inp = ((blk - blk.mean()) / blk.std() * corr_n).transpose()
+    scores = sk.PCA().fit_transform(inp)
+    sd = np.std(scores, axis=0)
+    ca = max(0, (2 * np.tril(inp.corr(), -1).sum() / (inp.sum(axis=1).var() / corr_n ** 2)) * (k / (k - 1)))
+    cr = np.corrcoef(np.column_stack((inp.values, scores[:, 0])), rowvar=False)[:, -1][:-1]
+    rho = sum(cr) ** 2 / (sum(cr) ** 2 + (k - np.sum(np.power(cr, 2))))
+    np.testing.assert_allclose([ours["eig_1st"], ours["eig_2nd"], ours["cronbach_alpha"], ours["dillon_goldstein_rho"]],
+                               [sd[0] ** 2, sd[1] ** 2, ca, rho], rtol=1e-9, atol=1e-12)
