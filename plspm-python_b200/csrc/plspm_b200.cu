@@ -168,6 +168,22 @@ static int upload_vec(plspm_model* m, const std::vector<T>& v, const T** out) {
 // ------------------------------------------------------------------------------------------------
 // C ABI
 // ------------------------------------------------------------------------------------------------
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) costs microseconds per call and a single fit launches five kernels
+// that need it: remember, per device and kernel, the largest size already granted.
+template <typename F>
+static cudaError_t ensure_smem(F* func, size_t bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<int, const void*>, size_t> granted;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lk(mu);
+  size_t& cur = granted[{dev, (const void*)func}];
+  if (bytes <= cur) return cudaSuccess;
+  const cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess) cur = bytes;
+  return e;
+}
+
 extern "C" {
 
 int plspm_version(void) { return 100; }
@@ -914,10 +930,10 @@ static int launch_stream(plspm_data* d, bool cross, int64_t nb, const uint32_t* 
   if (grid > 0x7fffffff) return fail(PLSPM_ERR_UNSUPPORTED, "batch too large for one launch");
   d->timer.begin(cross ? ST_CROSS : ST_GRAM, st);
   if (cross) {
-    CK(cudaFuncSetAttribute(gram_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp.smem));
+    CK(ensure_smem(gram_kernel<true>, (size_t)(sp.smem)));
     gram_kernel<true><<<(unsigned)grid, GRAM_THREADS, sp.smem, st>>>(p);
   } else {
-    CK(cudaFuncSetAttribute(gram_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp.smem));
+    CK(ensure_smem(gram_kernel<false>, (size_t)(sp.smem)));
     gram_kernel<false><<<(unsigned)grid, GRAM_THREADS, sp.smem, st>>>(p);
   }
   d->timer.end(st);
@@ -1006,7 +1022,7 @@ static int launch_moments(plspm_data* d, int64_t nb, const uint32_t* counts_dev,
     CK(cudaMemsetAsync(D(bb.colsum), 0, (size_t)nb * h.Ppad * 8, st));
     const int64_t grid = (int64_t)gp.n_mtiles * gp.n_groups * gp.ksplit;
     if (grid > 0x7fffffff) return fail(PLSPM_ERR_UNSUPPORTED, "batch too large for one launch");
-    CK(cudaFuncSetAttribute(gram_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gm_smem_bytes()));
+    CK(ensure_smem(gram_mma_kernel, (size_t)(gm_smem_bytes())));
     d->timer.begin(ST_GRAM_I8, st);
     gram_mma_kernel<<<(unsigned)grid, GM_THREADS, gm_smem_bytes(), st>>>(gp);
     d->timer.end(st);
@@ -1094,7 +1110,7 @@ static int launch_moments(plspm_data* d, int64_t nb, const uint32_t* counts_dev,
   dim3 grid_cs((h.Ppad + CS_COLS - 1) / CS_COLS, (unsigned)((nb + CS_REPS - 1) / CS_REPS), bp.cs_chunks);
   d->timer.begin(ST_COLSUM, st);
   const size_t cs_smem_bytes = (size_t)(CS_ROWS * CS_COLS + CS_ROWS * CS_REPS) * 8;
-  CK(cudaFuncSetAttribute(colsum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs_smem_bytes));
+  CK(ensure_smem(colsum_kernel, (size_t)(cs_smem_bytes)));
   colsum_kernel<<<grid_cs, 256, cs_smem_bytes, st>>>(d->X, counts_dev, d->N, h.Ppad, nb, bp.cs_chunks, bp.cs_chunk_rows,
                                                      bp.cs_chunks > 1 ? D(bb.cspart) : D(bb.colsum));
   d->timer.end(st);
@@ -1142,9 +1158,9 @@ static int run_batch_num(plspm_data* d, int64_t nb, const uint32_t* counts_dev, 
   CK(cudaMemsetAsync(D(bb.num_cmain), 0, (size_t)nb * 8, st));
   const size_t smem = h.solver_smem_doubles() * sizeof(double);
   if (smem > (size_t)d->max_smem) return fail(PLSPM_ERR_UNSUPPORTED, "model too large for the solver's shared memory");
-  CK(cudaFuncSetAttribute(num_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  CK(cudaFuncSetAttribute(conv_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bp.cv_smem));
-  CK(cudaFuncSetAttribute(conv_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bp.cv_smem));
+  CK(ensure_smem(num_step_kernel, (size_t)(smem)));
+  CK(ensure_smem(conv_kernel<float>, (size_t)(bp.cv_smem)));
+  CK(ensure_smem(conv_kernel<double>, (size_t)(bp.cv_smem)));
   const unsigned gy = (unsigned)((nb + bp.cv_reps_per_cta - 1) / bp.cv_reps_per_cta);
   int done = 0;
   for (int step = 0; step < max_iter + 4; ++step) {
@@ -1216,7 +1232,7 @@ static int run_batch(plspm_data* d, int64_t nb, const uint32_t* counts_dev, cons
     b.out_rows = out_rows; b.out_stride = hb.n_out();
     const size_t smem_b = hb.solver_core_smem_doubles() * sizeof(double);
     if (smem_b > (size_t)d->max_smem) return fail(PLSPM_ERR_UNSUPPORTED, "model too large for the solver's shared memory");
-    CK(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+    CK(ensure_smem(solve_kernel, (size_t)(smem_b)));
     d->timer.begin(ST_SOLVE, st);
     solve_kernel<<<(unsigned)nb, SOLVE_THREADS, smem_b, st>>>(b);
     d->timer.end(st);
@@ -1234,7 +1250,7 @@ static int run_batch(plspm_data* d, int64_t nb, const uint32_t* counts_dev, cons
   b.cross = h.full ? nullptr : D(bb.CG); b.cross_stride = (int64_t)h.n_cross * TILE;
   const size_t smem = h.solver_core_smem_doubles() * sizeof(double);
   if (smem > (size_t)d->max_smem) return fail(PLSPM_ERR_UNSUPPORTED, "model too large for the solver's shared memory");
-  CK(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CK(ensure_smem(solve_kernel, (size_t)(smem)));
   if (!h.full) {
     // sparse tile set: final weights first, then the P x L cross-moment pass for the sign vote
     b.phase = 1;
@@ -1283,7 +1299,7 @@ static int run_batch(plspm_data* d, int64_t nb, const uint32_t* counts_dev, cons
       vp.stats = kstats ? kstats_dev : nullptr;
       vp.stages = vm_stages(vp.k16_max, d->max_smem);
       const size_t vm_smem = vm_smem_bytes(vp.k16_max, vp.stages);
-      CK(cudaFuncSetAttribute(vote_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vm_smem));
+      CK(ensure_smem(vote_mma_kernel, (size_t)(vm_smem)));
       CK(cudaMemsetAsync(Cf, 0, (size_t)ldl * h.L * h.Ppad * sizeof(float), st));
       const int64_t grid = tiles0 * vp.ksplit;
       if (grid > 0x7fffffff) return fail(PLSPM_ERR_UNSUPPORTED, "batch too large for one launch");
@@ -1319,7 +1335,7 @@ static int run_batch(plspm_data* d, int64_t nb, const uint32_t* counts_dev, cons
       const int SG_ROWS = (int)std::max<size_t>(1, std::min<size_t>(SG_MAX_ROWS, (size_t)(d->max_smem / 2 - 8192) / sg_row_bytes));
       const size_t sg_smem = (size_t)SG_ROWS * sg_row_bytes;
       auto sg_kernel = (nsl_pad == 1) ? scoregen_kernel<true> : scoregen_kernel<false>;
-      CK(cudaFuncSetAttribute(sg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sg_smem));
+      CK(ensure_smem(sg_kernel, (size_t)(sg_smem)));
       const float one = 1.f, zero = 0.f;
       const int64_t ldl = (nb + 7) / 8 * 8;
       const int gemm_m = (int)(ldl * h.L);
@@ -1365,53 +1381,6 @@ static int run_batch(plspm_data* d, int64_t nb, const uint32_t* counts_dev, cons
   return 0;
 }
 
-int plspm_fit(const plspm_model* m, plspm_data* d, int32_t scheme, double tol, int32_t max_iter, double* weights,
-              double* loadings, double* r_squared, double* paths, double* total_effects, double* crossloadings,
-              double* scores, int32_t* iters, int32_t* status) {
-  if (!m || !d || !same_layout(d->model, m)) return fail(PLSPM_ERR_INVALID, "model/data mismatch");
-  if (scheme < 0 || scheme > 2) return fail(PLSPM_ERR_INVALID, "unknown scheme");
-  d->model = m;  // the handle carries the model of the call in flight (one call at a time per handle)
-  const HostModel& h = m->h;
-  const int64_t N = d->N;
-  const size_t L = h.L, P = h.P;
-  BatchPlan bp;
-  if (int rc = plan_batch(d, 1, bp)) return rc;
-  const BatchBuffers bb = layout_batch(d, 1, bp, false, false, false, true, scores != nullptr);
-  if (int rc = ws_reserve(d, bb.total)) return rc;
-  char* base = (char*)d->ws.ptr;
-  auto D = [&](size_t o) { return (double*)(base + o); };
-  cudaStream_t st = d->stream;
-  if (m->numeric) {
-    if (crossloadings && !h.full)
-      return fail(PLSPM_ERR_UNSUPPORTED, "numeric non-metric fit: crossloadings need a model with the full tile set");
-    if (int rc = run_batch_num(d, 1, nullptr, bb, scheme, tol, max_iter, bp, nullptr, true)) return rc;
-  } else if (int rc = run_batch(d, 1, nullptr, bb, scheme, tol, max_iter, bp, nullptr, true)) {
-    return rc;
-  }
-  if (scores) {
-    d->timer.begin(ST_SCORES, st);
-    scores_kernel<<<d->sm_count * 8, 256, 0, st>>>(d->X, N, h.Ppad, h.L, m->dv.lv_off, m->dv.lv_k, D(bb.coef),
-                                                   D(bb.shift), D(bb.scores));
-    d->timer.end(st);
-    CK(cudaGetLastError());
-  }
-  int host_it = 0, host_st = 0;
-  CK(cudaMemcpyAsync(&host_it, base + bb.iters, 4, cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(&host_st, base + bb.status, 4, cudaMemcpyDeviceToHost, st));
-  if (weights) CK(cudaMemcpyAsync(weights, D(bb.weights), P * 8, cudaMemcpyDeviceToHost, st));
-  if (loadings) CK(cudaMemcpyAsync(loadings, D(bb.loadings), P * 8, cudaMemcpyDeviceToHost, st));
-  if (r_squared) CK(cudaMemcpyAsync(r_squared, D(bb.r2), L * 8, cudaMemcpyDeviceToHost, st));
-  if (paths) CK(cudaMemcpyAsync(paths, D(bb.paths), L * L * 8, cudaMemcpyDeviceToHost, st));
-  if (total_effects) CK(cudaMemcpyAsync(total_effects, D(bb.totalfx), L * L * 8, cudaMemcpyDeviceToHost, st));
-  if (crossloadings) CK(cudaMemcpyAsync(crossloadings, D(bb.crossl), P * L * 8, cudaMemcpyDeviceToHost, st));
-  if (scores) CK(cudaMemcpyAsync(scores, D(bb.scores), (size_t)N * L * 8, cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
-  d->timer.collect();
-  if (iters) *iters = host_it;
-  if (status) *status = host_st;
-  return PLSPM_OK;
-}
-
 // Small page-locked staging buffers for the per-batch read-back (status, iterations, overflow flag): cached
 // process-wide, because plspm_bootstrap_host creates a handle per call and cudaMallocHost costs ~0.1 ms.
 struct PinnedStage {
@@ -1443,6 +1412,60 @@ struct PinnedStage {
   PinnedStage(const PinnedStage&) = delete;
   PinnedStage& operator=(const PinnedStage&) = delete;
 };
+
+int plspm_fit(const plspm_model* m, plspm_data* d, int32_t scheme, double tol, int32_t max_iter, double* weights,
+              double* loadings, double* r_squared, double* paths, double* total_effects, double* crossloadings,
+              double* scores, int32_t* iters, int32_t* status) {
+  if (!m || !d || !same_layout(d->model, m)) return fail(PLSPM_ERR_INVALID, "model/data mismatch");
+  if (scheme < 0 || scheme > 2) return fail(PLSPM_ERR_INVALID, "unknown scheme");
+  d->model = m;  // the handle carries the model of the call in flight (one call at a time per handle)
+  const HostModel& h = m->h;
+  const int64_t N = d->N;
+  const size_t L = h.L, P = h.P;
+  BatchPlan bp;
+  if (int rc = plan_batch(d, 1, bp)) return rc;
+  const BatchBuffers bb = layout_batch(d, 1, bp, false, false, false, true, scores != nullptr);
+  if (int rc = ws_reserve(d, bb.total)) return rc;
+  char* base = (char*)d->ws.ptr;
+  auto D = [&](size_t o) { return (double*)(base + o); };
+  cudaStream_t st = d->stream;
+  if (m->numeric) {
+    if (crossloadings && !h.full)
+      return fail(PLSPM_ERR_UNSUPPORTED, "numeric non-metric fit: crossloadings need a model with the full tile set");
+    if (int rc = run_batch_num(d, 1, nullptr, bb, scheme, tol, max_iter, bp, nullptr, true)) return rc;
+  } else if (int rc = run_batch(d, 1, nullptr, bb, scheme, tol, max_iter, bp, nullptr, true)) {
+    return rc;
+  }
+  if (scores) {
+    d->timer.begin(ST_SCORES, st);
+    scores_kernel<<<d->sm_count * 8, 256, 0, st>>>(d->X, N, h.Ppad, h.L, m->dv.lv_off, m->dv.lv_k, D(bb.coef),
+                                                   D(bb.shift), D(bb.scores));
+    d->timer.end(st);
+    CK(cudaGetLastError());
+  }
+  // The small outputs are consecutive in the workspace (layout_batch): ONE copy into page-locked staging instead of
+  // eight copies into the caller's pageable arrays (each of those is a synchronous round trip of ~10 us, which was
+  // most of the host-side gap of a 0.8 ms fit).  iters / status sit next to each other as well.
+  const size_t small_bytes = bb.crossl + P * L * 8 - bb.weights, tail_bytes = bb.status + 4 - bb.iters;
+  PinnedStage stage(small_bytes + tail_bytes);
+  if (!stage.ints) return fail(PLSPM_ERR_NOMEM, "pinned staging buffer");
+  char* hs = (char*)stage.ints;
+  CK(cudaMemcpyAsync(hs, base + bb.weights, small_bytes, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(hs + small_bytes, base + bb.iters, tail_bytes, cudaMemcpyDeviceToHost, st));
+  if (scores) CK(cudaMemcpyAsync(scores, D(bb.scores), (size_t)N * L * 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  d->timer.collect();
+  auto from = [&](size_t off) { return hs + (off - bb.weights); };
+  if (weights) std::memcpy(weights, from(bb.weights), P * 8);
+  if (loadings) std::memcpy(loadings, from(bb.loadings), P * 8);
+  if (r_squared) std::memcpy(r_squared, from(bb.r2), L * 8);
+  if (paths) std::memcpy(paths, from(bb.paths), L * L * 8);
+  if (total_effects) std::memcpy(total_effects, from(bb.totalfx), L * L * 8);
+  if (crossloadings) std::memcpy(crossloadings, from(bb.crossl), P * L * 8);
+  if (iters) std::memcpy(iters, hs + small_bytes, 4);
+  if (status) std::memcpy(status, hs + small_bytes + (bb.status - bb.iters), 4);
+  return PLSPM_OK;
+}
 
 int plspm_bootstrap(const plspm_model* m, plspm_data* d, int32_t scheme, double tol, int32_t max_iter,
                     int64_t rep_begin, int64_t rep_count, uint64_t seed, const int32_t* idx, double* out,
@@ -1525,7 +1548,7 @@ int plspm_bootstrap(const plspm_model* m, plspm_data* d, int32_t scheme, double 
       const int64_t n_ranges = (n_pad + RI_MAX_ROWS - 1) / RI_MAX_ROWS;
       const int64_t range_rows = ((n_pad + n_ranges - 1) / n_ranges + 127) / 128 * 128;
       const int n_groups = (int)((nb + 511) / 512);
-      CK(cudaFuncSetAttribute(resample_images_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)range_rows));
+      CK(ensure_smem(resample_images_kernel, (size_t)(range_rows)));
       d->timer.begin(ST_COUNTS, st);
       resample_images_kernel<<<dim3((unsigned)n_groups * 512, (unsigned)n_ranges), RI_THREADS, (size_t)range_rows, st>>>(
           idx_dev, N, nb, rep_begin + b0, seed, range_rows, n_groups, vote ? (int)((nb + 127) / 128) : 0, d->n_chunks64,
