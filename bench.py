@@ -479,7 +479,9 @@ def run_gpu_arm(args):
         # measured DRAM traffic of the step's kernels (ncu, per launch; profiles/kernel_traffic.json, tools/ncu_summary.py)
         traffic_tab = {}
         try:
-            traffic_tab = json.load(open(os.path.join(ROOT, "profiles", "kernel_traffic.json"))).get(args.workload, {})
+            tab = json.load(open(os.path.join(ROOT, "profiles", "kernel_traffic.json")))
+            # c4 runs the same kernels on the same data as c3 (only the solver's mode / scheme differ): its capture serves both
+            traffic_tab = tab.get(args.workload) or (tab.get("c3", {}) if args.workload == "c4" else {})
         except Exception:
             pass
         scale = reps / float(traffic_tab.get("_replicates_per_launch", reps))
