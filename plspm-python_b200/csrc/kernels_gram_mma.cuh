@@ -381,10 +381,10 @@ __global__ void __launch_bounds__(256) counts8_image_kernel(const uint32_t* __re
 // is the value of one unit of x'_p
 __global__ void gram_xunit_kernel(const double* __restrict__ absmax_partial, int nblocks, int Ppad, double* __restrict__ xunit,
                                   double* __restrict__ xscale) {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // one warp per column (warp_column_reduce)
   if (p >= Ppad) return;
-  double m = 0.0;
-  for (int b = 0; b < nblocks; ++b) m = fmax(m, absmax_partial[(int64_t)b * Ppad + p]);
+  const double m = warp_column_reduce(absmax_partial, nblocks, (int64_t)Ppad, p, 0.0, OpMax());
+  if (threadIdx.x & 31) return;
   int e = 0;
   if (m > 0.0) frexp(m, &e);  // m = f 2^e, f in [0.5, 1): |x~| < 2^e
   xunit[p] = ldexp(1.0, e - 23);
@@ -405,11 +405,10 @@ __global__ void gram_tailcount_partial_kernel(const double* __restrict__ X, int6
   }
 }
 __global__ void gram_tailcount_final_kernel(const int* __restrict__ partial, int nblocks, int Ppad, int* __restrict__ count) {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // one warp per column
   if (p >= Ppad) return;
-  int n = 0;
-  for (int b = 0; b < nblocks; ++b) n += partial[(int64_t)b * Ppad + p];
-  count[p] = n;
+  const int n = warp_column_reduce(partial, nblocks, (int64_t)Ppad, p, 0, OpAdd());
+  if ((threadIdx.x & 31) == 0) count[p] = n;
 }
 __global__ void __launch_bounds__(256) gram_xst_kernel(const double* __restrict__ X, int64_t N, int Ppad, int64_t ldx,
                                                        const double* __restrict__ xscale, int2* __restrict__ XsT) {

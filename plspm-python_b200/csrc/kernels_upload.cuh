@@ -14,13 +14,42 @@ __global__ void colsum_partial_kernel(const double* __restrict__ X, int64_t N, i
     partial[(int64_t)blockIdx.x * P + p] = s;
   }
 }
+// Second stage of the two-stage column reductions: ONE WARP per column (launch <<<(P + 3) / 4, 128>>>).  Lane l owns
+// the partials l, l + 32, ... as four independent chains, then a xor butterfly -- a fixed order, so the result is
+// deterministic and identical in every lane.  (One thread per column walking all 1024 partials was a 100 us chain of
+// dependent loads per kernel, five kernels per upload: 0.5 ms of every end-to-end call.)
+template <typename T, typename Op>
+__device__ __forceinline__ T warp_column_reduce(const T* __restrict__ partial, int nblocks, int64_t stride, int p, T init, Op op) {
+  const int lane = threadIdx.x & 31;
+  T a0 = init, a1 = init, a2 = init, a3 = init;
+  int b = lane;
+  for (; b + 96 < nblocks; b += 128) {
+    a0 = op(a0, partial[(int64_t)b * stride + p]);
+    a1 = op(a1, partial[(int64_t)(b + 32) * stride + p]);
+    a2 = op(a2, partial[(int64_t)(b + 64) * stride + p]);
+    a3 = op(a3, partial[(int64_t)(b + 96) * stride + p]);
+  }
+  for (; b < nblocks; b += 32) a0 = op(a0, partial[(int64_t)b * stride + p]);
+  T s = op(op(a0, a1), op(a2, a3));
+  for (int o = 16; o; o >>= 1) s = op(s, __shfl_xor_sync(0xffffffffu, s, o));
+  return s;
+}
+struct OpAdd { template <typename T> __device__ T operator()(T a, T b) const { return a + b; } };
+struct OpMax { __device__ double operator()(double a, double b) const { return fmax(a, b); } };
+
 __global__ void colmean_final_kernel(const double* __restrict__ partial, int nblocks, int P, int64_t N,
                                      const int* __restrict__ src_col, double* __restrict__ mu) {
-  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (p >= P) return;
-  double s = 0.0;
-  for (int b = 0; b < nblocks; ++b) s += partial[(int64_t)b * P + p];
-  mu[src_col[p]] = s / (double)N;
+  const double s = warp_column_reduce(partial, nblocks, (int64_t)P, p, 0.0, OpAdd());
+  if ((threadIdx.x & 31) == 0) mu[src_col[p]] = s / (double)N;
+}
+// plain column totals (the sums of the centred columns kept in the data handle)
+__global__ void colsum_final_kernel(const double* __restrict__ partial, int nblocks, int P, double* __restrict__ out) {
+  const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (p >= P) return;
+  const double s = warp_column_reduce(partial, nblocks, (int64_t)P, p, 0.0, OpAdd());
+  if ((threadIdx.x & 31) == 0) out[p] = s;
 }
 __global__ void relayout_kernel(const double* __restrict__ X, int64_t N, int64_t ld, int Ppad,
                                 const int* __restrict__ col_src, const double* __restrict__ mu,
@@ -46,11 +75,10 @@ __global__ void colsq_partial_kernel(const double* __restrict__ X, int64_t N, in
 }
 __global__ void inv_sd_kernel(const double* __restrict__ partial, int nblocks, int Ppad, int64_t N,
                               double* __restrict__ inv_sd) {
-  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (p >= Ppad) return;
-  double s = 0.0;
-  for (int b = 0; b < nblocks; ++b) s += partial[(int64_t)b * Ppad + p];
-  inv_sd[p] = s > 0.0 ? 1.0 / sqrt(s / (double)N) : 0.0;
+  const double s = warp_column_reduce(partial, nblocks, (int64_t)Ppad, p, 0.0, OpAdd());
+  if ((threadIdx.x & 31) == 0) inv_sd[p] = s > 0.0 ? 1.0 / sqrt(s / (double)N) : 0.0;
 }
 __global__ void make_half_kernel(const double* __restrict__ X, int64_t N, int Ppad, const double* __restrict__ inv_sd,
                                  __half* __restrict__ out) {

@@ -335,6 +335,10 @@ int plspm_data_create(const plspm_model* m, const double* X, int64_t N, int64_t 
   double* raw = nullptr;
   const double* Xd = X;
   int rc = 0;
+  // scratch released (and pageable host staging kept alive) until the stream has drained at the end of the upload:
+  // no intermediate synchronisation just to free a buffer
+  std::vector<void*> deferred;
+  std::vector<int> blk_col, lv_blk_host;
   auto body = [&]() -> int {
     CK(g_pool.alloc((void**)&d->X, (size_t)N * h.Ppad * sizeof(double)));
     CK(g_pool.alloc((void**)&d->mu, (size_t)h.Ppad * sizeof(double)));
@@ -361,7 +365,7 @@ int plspm_data_create(const plspm_model* m, const double* X, int64_t N, int64_t 
     colsum_partial_kernel<<<nblocks, 256, 0, st>>>(Xd, N, ld, h.P, rpb, partial);
     d->timer.end(st);
     d->timer.begin(ST_UPLOAD, st);
-    colmean_final_kernel<<<(h.P + 127) / 128, 128, 0, st>>>(partial, nblocks, h.P, N, src_col, d->mu);
+    colmean_final_kernel<<<(h.P + 3) / 4, 128, 0, st>>>(partial, nblocks, h.P, N, src_col, d->mu);
     d->timer.end(st);
     d->timer.begin(ST_UPLOAD, st);
     relayout_kernel<<<d->sm_count * 8, 256, 0, st>>>(Xd, N, ld, h.Ppad, m->dv.col_src, d->mu, d->X);
@@ -374,7 +378,7 @@ int plspm_data_create(const plspm_model* m, const double* X, int64_t N, int64_t 
     colsum_partial_kernel<<<nblocks, 256, 0, st>>>(d->X, N, h.Ppad, h.Ppad, rpb, partial0);
     d->timer.end(st);
     d->timer.begin(ST_UPLOAD, st);
-    reduce_chunks_kernel<<<(h.Ppad + 255) / 256, 256, 0, st>>>(partial0, 1, nblocks, h.Ppad, d->colsum0);
+    colsum_final_kernel<<<(h.Ppad + 3) / 4, 128, 0, st>>>(partial0, nblocks, h.Ppad, d->colsum0);
     d->timer.end(st);
     CK(cudaGetLastError());
     trace("relayout done");
@@ -393,14 +397,15 @@ int plspm_data_create(const plspm_model* m, const double* X, int64_t N, int64_t 
       colsq_partial_kernel<<<nblocks, 256, 0, st>>>(d->X, N, h.Ppad, rpb, sq);
       d->timer.end(st);
       d->timer.begin(ST_UPLOAD, st);
-      inv_sd_kernel<<<(h.Ppad + 127) / 128, 128, 0, st>>>(sq, nblocks, h.Ppad, N, d->inv_sd);
+      inv_sd_kernel<<<(h.Ppad + 3) / 4, 128, 0, st>>>(sq, nblocks, h.Ppad, N, d->inv_sd);
       d->timer.end(st);
       // fused tcgen05 vote (default): blocks of at most 64 manifest variables (four K = 16 score steps)
       if (fused_ok && N < ((int64_t)1 << 31) - 256) {
         // operand images of the fused vote kernel (kernels_vote_mma.cuh): what its producer fetches with linear bulk copies
         d->n_chunks64 = (N + 63) / 64;
         const int n_pchunks = (h.Ppad + 255) / 256;
-        std::vector<int> blk_col, lv_blk(h.L);
+        std::vector<int>& lv_blk = lv_blk_host;
+        lv_blk.assign(h.L, 0);
         for (int l = 0; l < h.L; ++l) {
           lv_blk[l] = (int)blk_col.size();
           for (int q = 0; q < (h.lv_k[l] + 15) / 16; ++q) blk_col.push_back(h.lv_off[l] + 16 * q);
@@ -421,8 +426,7 @@ int plspm_data_create(const plspm_model* m, const double* X, int64_t N, int64_t 
                                                               d->xl_img);
         d->timer.end(st);
         CK(cudaGetLastError());
-        CK(cudaStreamSynchronize(st));  // (pageable host vectors above)
-        g_pool.release(blk_col_dev);
+        deferred.push_back(blk_col_dev);
         d->mma_vote = true;
       } else {  // legacy route: fp32 score generation + library fp16 GEMM
         CK(g_pool.alloc((void**)&d->Xh, (size_t)N * h.Ppad * sizeof(__half)));
@@ -439,8 +443,7 @@ int plspm_data_create(const plspm_model* m, const double* X, int64_t N, int64_t 
         d->blas_device = dev;
         cublasSetStream(d->blas, st);
       }
-      CK(cudaStreamSynchronize(st));
-      g_pool.release(sq);
+      deferred.push_back(sq);
       d->fast_vote = true;
       trace("fp16 copies");
     }
@@ -468,7 +471,7 @@ int plspm_data_create(const plspm_model* m, const double* X, int64_t N, int64_t 
       colabsmax_partial_kernel<<<nblocks, 256, 0, st>>>(d->X, N, h.Ppad, rpb, amax);
       d->timer.end(st);
       d->timer.begin(ST_UPLOAD, st);
-      gram_xunit_kernel<<<(h.Ppad + 127) / 128, 128, 0, st>>>(amax, nblocks, h.Ppad, d->xunit, xscale);
+      gram_xunit_kernel<<<(h.Ppad + 3) / 4, 128, 0, st>>>(amax, nblocks, h.Ppad, d->xunit, xscale);
       d->timer.end(st);
       d->timer.begin(ST_UPLOAD, st);
       gram_xst_kernel<<<dim3((unsigned)((d->ldx + 31) / 32), (h.Ppad + 31) / 32), 256, 0, st>>>(d->X, N, h.Ppad, d->ldx, xscale,
@@ -482,7 +485,7 @@ int plspm_data_create(const plspm_model* m, const double* X, int64_t N, int64_t 
       gram_tailcount_partial_kernel<<<nblocks, 256, 0, st>>>(d->X, N, h.Ppad, rpb, d->xunit, tail_part);
       d->timer.end(st);
       d->timer.begin(ST_UPLOAD, st);
-      gram_tailcount_final_kernel<<<(h.Ppad + 127) / 128, 128, 0, st>>>(tail_part, nblocks, h.Ppad, tail);
+      gram_tailcount_final_kernel<<<(h.Ppad + 3) / 4, 128, 0, st>>>(tail_part, nblocks, h.Ppad, tail);
       d->timer.end(st);
       CK(cudaGetLastError());
       std::vector<int> tail_host(h.Ppad);
@@ -599,9 +602,15 @@ int plspm_data_create(const plspm_model* m, const double* X, int64_t N, int64_t 
     g_pool.release(partial);
     g_pool.release(partial0);
     g_pool.release(src_col);
+    for (void* q : deferred) g_pool.release(q);
+    deferred.clear();
     return 0;
   };
   rc = body();
+  if (!deferred.empty()) {  // (an error path left them behind)
+    cudaStreamSynchronize(d->stream);
+    for (void* q : deferred) g_pool.release(q);
+  }
   if (raw) g_pool.release(raw);
   if (rc) return bail(rc);
   *out = d;
