@@ -138,6 +138,8 @@ struct plspm_data {
   StageTimer timer;
   int sm_count = 148;
   ImputeCtx* imp = nullptr;
+  struct ImagePrefetch* prefetch = nullptr;  // multiplicity images of the first batch, generated during the upload (plspm_bootstrap_host)
+  const uint8_t *c8img_ovr = nullptr, *c8vote_ovr = nullptr;  // ... and what the kernels of that batch read instead of the workspace images
   bool img_ready = false;  // the multiplicity images of the batch in flight were written by resample_images_kernel
   int max_smem = 227 * 1024;
 };
@@ -1020,7 +1022,7 @@ static int launch_moments(plspm_data* d, int64_t nb, const uint32_t* counts_dev,
     gp.nb = nb; gp.nb_pad = bp.gm_nb_pad; gp.N = d->N;
     gp.n_mtiles = d->gm_n_tiles; gp.n_groups = (int)((nb + 511) / 512); gp.ksplit = bp.gm_ksplit; gp.rows_per_cta = bp.gm_rows;
     gp.XsT = d->XsT; gp.ldx = d->ldx;
-    gp.c8img = (const uint8_t*)(base + bb.c8img);
+    gp.c8img = d->c8img_ovr ? d->c8img_ovr : (const uint8_t*)(base + bb.c8img);
     static const bool gstats = getenv("PLSPM_KERNEL_STATS") != nullptr;
     static unsigned long long* gstats_dev = nullptr;
     if (gstats && !gstats_dev) CK(cudaMalloc((void**)&gstats_dev, 16 * 8));
@@ -1276,7 +1278,7 @@ static int run_batch(plspm_data* d, int64_t nb, const uint32_t* counts_dev, cons
       const int64_t ldl = (nb + 7) / 8 * 8;
       VoteMmaParams vp;
       vp.wf = D(bb.wf); vp.inv_sd = d->inv_sd; vp.lv_off = m->dv.lv_off; vp.lv_k = m->dv.lv_k; vp.lv_blk = d->lv_blk; vp.Cf = Cf;
-      vp.xt_img = d->xt_img; vp.xl_img = d->xl_img; vp.c8_img = (const uint8_t*)(base + bb.c8vote);
+      vp.xt_img = d->xt_img; vp.xl_img = d->xl_img; vp.c8_img = d->c8vote_ovr ? d->c8vote_ovr : (const uint8_t*)(base + bb.c8vote);
       vp.n_blocks = d->vm_n_blocks; vp.n_rep_tiles_img = (int)((nb + 127) / 128);
       if (!d->img_ready) {
         d->timer.begin(ST_COLSUM, st);
@@ -1476,6 +1478,101 @@ int plspm_fit(const plspm_model* m, plspm_data* d, int32_t scheme, double tol, i
   return PLSPM_OK;
 }
 
+// Replicates per batch of plspm_bootstrap: bounds the workspace and keeps the grids whole waves.  A function of the
+// model, the row count and the route flags only, so plspm_bootstrap_host can know the first batch before the data
+// handle exists (prefetch of the multiplicity images, below).
+static int64_t bootstrap_batch_size(const plspm_model* m, int64_t N, size_t n_out, bool with_idx, bool gram_mma, bool i8_colsum,
+                                    int64_t Npad, int n_zcols, bool z_resident, int sm_count, int64_t rep_count) {
+  const HostModel& h = m->h;
+  const bool vote = !h.full && !m->numeric;
+  const size_t per_rep = (size_t)N * 4 + ((size_t)h.n_tiles * TILE + (vote ? (size_t)h.n_cross * TILE : 0) +
+                                          (m->numeric ? 6 : 2) * h.Ppad + h.ws_doubles + n_out) * 8 +
+                         (with_idx ? (size_t)N * 4 : 0) +
+                         (gram_mma ? (size_t)Npad + (size_t)gm_count_tiles(h) * GM_PAIRS_PER_TILE * sizeof(longlong2) * 3 +
+                                         (vote ? (size_t)h.L * h.Ppad * 4 : 0)
+                                   : i8_colsum ? (size_t)Npad + I8_DIGITS * ((size_t)h.Ppad + n_zcols) * 4 : 0) + 64;
+  // the planes of a chunk are regenerated for every batch in streaming mode: large batches amortise that
+  const size_t ws_budget = n_zcols && !z_resident ? (size_t)12 << 30 : gram_mma ? (size_t)3 << 30 : (size_t)1536 << 20;
+  int64_t nb_max = std::max<int64_t>(1, (int64_t)(ws_budget / per_rep));
+  if (getenv("PLSPM_MAX_BATCH")) nb_max = std::max<int64_t>(1, std::min<int64_t>(nb_max, atoll(getenv("PLSPM_MAX_BATCH"))));
+  nb_max = std::min<int64_t>(nb_max, rep_count);
+  const int64_t wave = (int64_t)sm_count * GRAM_WARPS;  // warp items per wave
+  const int64_t items_per_rep = vote ? std::max(h.n_tg, h.n_tg_cross) : h.n_tg;
+  if (gram_mma) {
+    // tensor-core kernels: CTAs own 512 (Gram) / 128 (sign vote) replicates and row ranges even out the waves.
+    // Batches of equal size (no small tail batch), whole 128-replicate tiles where the run is large enough.
+    if (nb_max >= 512) nb_max = nb_max / 512 * 512;
+    const int64_t n_batches = (rep_count + nb_max - 1) / nb_max;
+    int64_t even = (rep_count + n_batches - 1) / n_batches;
+    if (even >= 128) even = (even + 127) / 128 * 128;
+    nb_max = std::min(nb_max, even);
+  } else if (nb_max * items_per_rep > wave) {
+    int64_t waves = nb_max * items_per_rep / wave;
+    nb_max = std::max<int64_t>(1, waves * wave / items_per_rep);
+  }
+  return nb_max;
+}
+
+// The multiplicity images of the FIRST batch of a plspm_bootstrap_host call do not depend on the data: they are
+// generated on a side stream while the observation matrix crosses PCIe (3.8 of the 11.7 ms of a c3 call), into pooled
+// buffers the first batch then reads in place of its workspace images.  Speculative: if the data handle ends up on
+// another route (heavy-tailed data, small N) the images are simply dropped.
+struct ImagePrefetch {
+  uint8_t *c8img = nullptr, *c8vote = nullptr;
+  int* ovf = nullptr;
+  cudaEvent_t done = nullptr;
+  int64_t nb = 0, rep_begin = 0;
+  uint64_t seed = 0;
+  bool valid = false;
+};
+static cudaStream_t side_stream() {
+  static thread_local cudaStream_t s = nullptr;
+  static thread_local int dev_of = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!s || dev_of != dev) {
+    if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) s = nullptr;
+    dev_of = dev;
+  }
+  return s;
+}
+static void prefetch_release(ImagePrefetch& pf) {
+  if (pf.c8img) g_pool.release(pf.c8img);
+  if (pf.c8vote) g_pool.release(pf.c8vote);
+  if (pf.ovf) g_pool.release(pf.ovf);
+  if (pf.done) cudaEventDestroy(pf.done);
+  pf = ImagePrefetch();
+}
+static void prefetch_images(const plspm_model* m, int64_t N, int64_t rep_begin, int64_t rep_count, uint64_t seed, ImagePrefetch& pf) {
+  static const bool off = getenv("PLSPM_GRAM") || getenv("PLSPM_VOTE") || getenv("PLSPM_COUNTS") || getenv("PLSPM_PREFETCH_OFF");
+  const HostModel& h = m->h;
+  const bool vote = !h.full && !m->numeric;
+  if (off || m->numeric || N < 4096 || N >= ((int64_t)1 << 31) - 256 || rep_count < 1 || (vote && h.kmax > 16 * VM_MAX_K16)) return;
+  int dev = 0, sm_count = 148;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return;
+  cudaStream_t ss = side_stream();
+  if (!ss) return;
+  const int64_t nb = bootstrap_batch_size(m, N, h.n_out(), false, true, true, (N + 15) / 16 * 16, 0, false, sm_count, rep_count);
+  const int n_groups = (int)((nb + 511) / 512), n_rep_tiles = vote ? (int)((nb + 127) / 128) : 0;
+  const int64_t n_pad = (N + 127) / 128 * 128, n_chunks64 = (N + 63) / 64;
+  const int64_t n_ranges = (n_pad + RI_MAX_ROWS - 1) / RI_MAX_ROWS;
+  const int64_t range_rows = ((n_pad + n_ranges - 1) / n_ranges + 127) / 128 * 128;
+  if (g_pool.alloc((void**)&pf.c8img, (size_t)(n_pad / 128) * n_groups * 65536) != cudaSuccess ||
+      (vote && g_pool.alloc((void**)&pf.c8vote, (size_t)n_chunks64 * n_rep_tiles * 8192) != cudaSuccess) ||
+      g_pool.alloc((void**)&pf.ovf, 8) != cudaSuccess || cudaEventCreateWithFlags(&pf.done, cudaEventDisableTiming) != cudaSuccess ||
+      ensure_smem(resample_images_kernel, (size_t)range_rows) != cudaSuccess) {
+    prefetch_release(pf);
+    cudaGetLastError();
+    return;
+  }
+  cudaMemsetAsync(pf.ovf, 0, 8, ss);
+  resample_images_kernel<<<dim3((unsigned)n_groups * 512, (unsigned)n_ranges), RI_THREADS, (size_t)range_rows, ss>>>(
+      nullptr, N, nb, rep_begin, seed, range_rows, n_groups, n_rep_tiles, n_chunks64, pf.c8img, pf.c8vote, pf.ovf);
+  cudaEventRecord(pf.done, ss);
+  if (cudaGetLastError() != cudaSuccess) { prefetch_release(pf); return; }
+  pf.nb = nb; pf.rep_begin = rep_begin; pf.seed = seed; pf.valid = true;
+}
+
 int plspm_bootstrap(const plspm_model* m, plspm_data* d, int32_t scheme, double tol, int32_t max_iter,
                     int64_t rep_begin, int64_t rep_count, uint64_t seed, const int32_t* idx, double* out,
                     int32_t out_is_device, int32_t* status, int32_t* iters) {
@@ -1491,33 +1588,9 @@ int plspm_bootstrap(const plspm_model* m, plspm_data* d, int32_t scheme, double 
   if (idx)
     for (int64_t e = 0; e < rep_count * N; ++e)
       if (idx[e] < 0 || idx[e] >= N) return fail(PLSPM_ERR_INVALID, "resample index out of range");
-  // batch size: bound the workspace (~1.5 GB) and keep the Gram grid a whole number of waves
   const bool vote = !h.full && !m->numeric;
-  const size_t per_rep = (size_t)N * 4 + ((size_t)h.n_tiles * TILE + (vote ? (size_t)h.n_cross * TILE : 0) +
-                                          (m->numeric ? 6 : 2) * h.Ppad + h.ws_doubles + n_out) * 8 +
-                         (idx ? (size_t)N * 4 : 0) +
-                         (d->gram_mma ? (size_t)d->Npad + (size_t)gm_count_tiles(h) * GM_PAIRS_PER_TILE * sizeof(longlong2) * 3 +
-                                            (vote ? (size_t)h.L * h.Ppad * 4 : 0)
-                                      : d->i8_colsum ? (size_t)d->Npad + I8_DIGITS * ((size_t)h.Ppad + d->n_zcols) * 4 : 0) + 64;
-  // the planes of a chunk are regenerated for every batch in streaming mode: large batches amortise that
-  const size_t ws_budget = d->n_zcols && !d->Z8 ? (size_t)12 << 30 : d->gram_mma ? (size_t)3 << 30 : (size_t)1536 << 20;
-  int64_t nb_max = std::max<int64_t>(1, (int64_t)(ws_budget / per_rep));
-  if (getenv("PLSPM_MAX_BATCH")) nb_max = std::max<int64_t>(1, std::min<int64_t>(nb_max, atoll(getenv("PLSPM_MAX_BATCH"))));
-  nb_max = std::min<int64_t>(nb_max, rep_count);
-  const int64_t wave = (int64_t)d->sm_count * GRAM_WARPS;  // warp items per wave
-  const int64_t items_per_rep = vote ? std::max(h.n_tg, h.n_tg_cross) : h.n_tg;
-  if (d->gram_mma) {
-    // tensor-core kernels: CTAs own 512 (Gram) / 128 (sign vote) replicates and row ranges even out the waves.
-    // Batches of equal size (no small tail batch), whole 128-replicate tiles where the run is large enough.
-    if (nb_max >= 512) nb_max = nb_max / 512 * 512;
-    const int64_t n_batches = (rep_count + nb_max - 1) / nb_max;
-    int64_t even = (rep_count + n_batches - 1) / n_batches;
-    if (even >= 128) even = (even + 127) / 128 * 128;
-    nb_max = std::min(nb_max, even);
-  } else if (nb_max * items_per_rep > wave) {
-    int64_t waves = nb_max * items_per_rep / wave;
-    nb_max = std::max<int64_t>(1, waves * wave / items_per_rep);
-  }
+  const int64_t nb_max = bootstrap_batch_size(m, N, n_out, idx != nullptr, d->gram_mma, d->i8_colsum, d->Npad, d->n_zcols,
+                                              d->Z8 != nullptr, d->sm_count, rep_count);
   BatchPlan bp;
   if (int rc = plan_batch(d, nb_max, bp)) return rc;
   const BatchBuffers bb = layout_batch(d, nb_max, bp, true, idx != nullptr, out_is_device != 0, false, false);
@@ -1552,7 +1625,18 @@ int plspm_bootstrap(const plspm_model* m, plspm_data* d, int32_t scheme, double 
     };
     static const bool counts_split = getenv("PLSPM_COUNTS") && std::string(getenv("PLSPM_COUNTS")) == "split";
     d->img_ready = false;
-    if (!counts_split && !m->numeric && d->gram_mma && d->i8_colsum && (!vote || (d->mma_vote && d->fast_vote))) {
+    d->c8img_ovr = d->c8vote_ovr = nullptr;
+    const bool fuse_images = !counts_split && !m->numeric && d->gram_mma && d->i8_colsum && (!vote || (d->mma_vote && d->fast_vote));
+    ImagePrefetch* pf = d->prefetch;
+    if (fuse_images && pf && pf->valid && b0 == 0 && !idx && pf->nb == nb && pf->rep_begin == rep_begin && pf->seed == seed &&
+        (pf->c8vote != nullptr) == vote) {
+      // generated on the side stream while X was uploading: wait for it, adopt its overflow flag
+      CK(cudaStreamWaitEvent(st, pf->done, 0));
+      CK(cudaMemcpyAsync(base + bb.ovf, pf->ovf, 4, cudaMemcpyDeviceToDevice, st));
+      d->c8img_ovr = pf->c8img;
+      d->c8vote_ovr = pf->c8vote;
+      d->img_ready = true;
+    } else if (fuse_images) {
       const int64_t n_pad = (N + 127) / 128 * 128;
       const int64_t n_ranges = (n_pad + RI_MAX_ROWS - 1) / RI_MAX_ROWS;
       const int64_t range_rows = ((n_pad + n_ranges - 1) / n_ranges + 127) / 128 * 128;
@@ -1603,6 +1687,7 @@ int plspm_bootstrap(const plspm_model* m, plspm_data* d, int32_t scheme, double 
       CK(cudaMemsetAsync(base + bb.ovf, 0, 8, st));
       d->i8_colsum = false;
       d->img_ready = false;
+      d->c8img_ovr = d->c8vote_ovr = nullptr;
       if (int rc = ensure_counts()) return rc;
     }
     if (vote && d->fast_vote) {
@@ -1624,6 +1709,7 @@ int plspm_bootstrap(const plspm_model* m, plspm_data* d, int32_t scheme, double 
     if (status) std::memcpy(status + b0, h_status, (size_t)nb * 4);
     d->timer.collect();
     d->img_ready = false;
+    d->c8img_ovr = d->c8vote_ovr = nullptr;
   }
   return PLSPM_OK;
 }
@@ -1635,11 +1721,21 @@ int plspm_bootstrap_host(const plspm_model* m, const double* X, int64_t N, int64
   const auto t0 = std::chrono::steady_clock::now();
   const int64_t miss0 = g_pool.misses.load(), ev0 = g_pool.evictions.load();
   plspm_data* d = nullptr;
+  ImagePrefetch pf;
+  if (m && X && !idx && out) prefetch_images(m, N, rep_begin, rep_count, seed, pf);
   int rc = plspm_data_create(m, X, N, ld, 0, &d);
-  if (rc) return rc;
+  if (rc) {
+    if (pf.done) cudaEventSynchronize(pf.done);
+    prefetch_release(pf);
+    return rc;
+  }
+  d->prefetch = &pf;
   const auto t1 = std::chrono::steady_clock::now();
   rc = plspm_bootstrap(m, d, scheme, tol, max_iter, rep_begin, rep_count, seed, idx, out, 0, status, iters);
   const auto t2 = std::chrono::steady_clock::now();
+  d->prefetch = nullptr;
+  if (pf.done) cudaEventSynchronize(pf.done);  // (an unused prefetch may still be running)
+  prefetch_release(pf);
   plspm_data_destroy(d);
   if (trace) {
     const auto t3 = std::chrono::steady_clock::now();

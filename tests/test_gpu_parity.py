@@ -529,3 +529,31 @@ def test_integer_gram_and_outlier_columns(eng, outlier, integer_route):
         ref, it, st = orc.replicate_row(X, orc.philox_indices(11, b, N), [K] * L, [0] * L, path, "centroid", True)
         assert status[b] == st == 0 and iters[b] == it
         np.testing.assert_allclose(rows[b], ref, rtol=REL, atol=1e-9)
+
+
+def test_bootstrap_host_matches_resident_path_and_prefetches_the_images(eng):
+    """plspm_bootstrap_host (upload + bootstrap + release in one call): the multiplicity images of its first batch are
+    generated on a side stream while X crosses PCIe.  Rows must be identical to the resident-data path, for one batch,
+    for several batches (only the first is prefetched) and for injected indices (no prefetch)."""
+    N, L, K = 9000, 6, 5
+    X, path = make_synthetic(N, L, K, 29)
+    model = eng.Model([K] * L, [0] * L, path, True, eng.TILES_SPARSE)
+    data = eng.Data(model, X)
+    for reps in (37, 300):
+        ref_rows, ref_status, ref_iters = eng.bootstrap(model, data, "centroid", 5, reps, seed=77)
+        eng.profile_reset()
+        rows, status, iters = eng.bootstrap_host(model, np.ascontiguousarray(X), "centroid", 5, reps, seed=77)
+        prof = eng.profile_get()
+        assert prof["gram_i8"][1] >= 1 and prof["gram"][1] == 0 and prof["colsum"][1] == 0, prof
+        assert np.array_equal(rows, ref_rows) and np.array_equal(status, ref_status) and np.array_equal(iters, ref_iters)
+    # one prefetch kernel on the side stream is not a stage launch of the handle's stream: the counts stage shows
+    # only the batches after the first (none here)
+    eng.profile_reset()
+    eng.bootstrap_host(model, np.ascontiguousarray(X), "centroid", 0, 64, seed=1)
+    assert eng.profile_get()["counts"][1] == 0
+    idx = np.random.default_rng(2).integers(0, N, size=(9, N)).astype(np.int32)
+    a = eng.bootstrap(model, data, "centroid", 0, 9, idx=idx)[0]
+    b = eng.bootstrap_host(model, np.ascontiguousarray(X), "centroid", 0, 9, idx=idx)[0]
+    assert np.array_equal(a, b)
+    ref, it, st = orc.replicate_row(X, idx[4], [K] * L, [0] * L, path, "centroid", True)
+    np.testing.assert_allclose(b[4], ref, rtol=1e-6, atol=1e-9)
