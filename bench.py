@@ -37,10 +37,11 @@ for p in (ROOT, os.path.join(ROOT, "plspm-python_b200")):
 
 WORKLOADS = {
     # name: (N, L, K, mode, scheme, replicates per GPU per step, description)
-    "c3": (100_000, 32, 8, 0, "centroid", 1536,
+    # (c3 / c4: 3072 = the batch the library forms by itself under its 3 GB workspace budget; a step = one batch)
+    "c3": (100_000, 32, 8, 0, "centroid", 3072,
            "synthetic N=100k, 32 LVs x 8 MVs (P=256), Mode A, centroid, bootstrap (north-star headline config)"),
-    "c3f": (100_000, 32, 8, 0, "factorial", 1536, "synthetic N=100k, 32 LVs x 8 MVs, Mode A, factorial, bootstrap"),
-    "c4": (100_000, 32, 8, 1, "path", 1536, "synthetic N=100k, 32 LVs x 8 MVs, Mode B, path scheme, bootstrap"),
+    "c3f": (100_000, 32, 8, 0, "factorial", 3072, "synthetic N=100k, 32 LVs x 8 MVs, Mode A, factorial, bootstrap"),
+    "c4": (100_000, 32, 8, 1, "path", 3072, "synthetic N=100k, 32 LVs x 8 MVs, Mode B, path scheme, bootstrap"),
     "c5": (1_000_000, 64, 16, 0, "centroid", 512, "synthetic N=1M, 64 LVs x 16 MVs (P=1024), Mode A, centroid, bootstrap"),
     "c3n": (100_000, 32, 8, 0, "centroid", 1536,
             "synthetic N=100k, 32 LVs x 8 MVs, Scale.NUM (non-metric estimator), Mode A, centroid, bootstrap"),
@@ -392,17 +393,37 @@ def run_gpu_arm(args):
     # nvidia-smi needs ~100 ms per sample and the timed region can be shorter than that: the sampler runs from
     # the warm-up through the timed steps and a tail of identical (untimed) steps, all under the same load
     sampler = ClockSampler(local) if rank == 0 else None
-    for _ in range(args.warmup):
-        step(0)
+    if args.per_step_calls:
+        for _ in range(args.warmup):
+            step(0)
+    elif args.warmup > 0:
+        # the same call shape as the timed region (one call, W pipelined batches): the doubled workspace and the
+        # page-locked staging of the pipeline are allocated here, not inside the timed region
+        wbuf = torch.empty((args.warmup, reps, n_out), dtype=torch.float64, device=dev)
+        engine.bootstrap(model, data, w["scheme"], (step_id[0] * world + rank * args.warmup) * reps, args.warmup * reps, seed=0,
+                         out_device_ptr=wbuf.data_ptr())
+        step_id[0] += args.warmup
+        del wbuf
     finish_run()
     barrier()
     engine.profile_reset()
     t0 = time.perf_counter()
     iters_all, begins, bad = [], [], 0
-    for k in range(args.steps):
-        begin, status, iters = step(k)
-        begins.append(begin)
-        iters_all.append(iters.astype(np.float64))
+    if args.per_step_calls:  # A/B: one library call per step (the device idles while the host turns around)
+        for k in range(args.steps):
+            begin, status, iters = step(k)
+            begins.append(begin)
+            iters_all.append(iters.astype(np.float64))
+            bad += int((status != 0).sum())
+    else:
+        # ONE library call for the K steps, as a user bootstrapping K x reps replicates calls it: the library runs them as
+        # K batches of `reps` and enqueues batch k + 1 before it waits for batch k (same kernels, same work per step)
+        begin = (step_id[0] * world + rank * args.steps) * reps
+        step_id[0] += args.steps
+        _, status, iters = engine.bootstrap(model, data, w["scheme"], begin, args.steps * reps, seed=0,
+                                            out_device_ptr=rows_dev.data_ptr())
+        begins = [begin + k * reps for k in range(args.steps)]
+        iters_all = [iters[k * reps:(k + 1) * reps].astype(np.float64) for k in range(args.steps)]
         bad += int((status != 0).sum())
     finish_run()
     barrier()
@@ -543,9 +564,11 @@ def run_gpu_arm(args):
             "roofline": roof,
             "stages_ms_per_step": stages,
             "timing": "value = replicates / wall clock around the K steps + the one all-gather (barrier + synchronize on both "
-                      "sides, max over ranks); every step ends in a stream synchronize inside the library, so this is >= the "
-                      "device time.  CUDA-event sum of the step's kernels on the library's stream: %.3f ms per step"
-                      % (total_ms / args.steps),
+                      "sides, max over ranks).  %s.  CUDA-event sum of the step's kernels on the library's stream: %.3f ms per "
+                      "step" % ("one library call per step, each ending in a stream synchronize" if args.per_step_calls else
+                                "The K steps are ONE library call of K x %d replicates = K batches; the library enqueues "
+                                "batch k + 1 before it waits for batch k" % reps, total_ms / args.steps),
+            "calls": "per step" if args.per_step_calls else "one call, K pipelined batches",
             "mean_iterations": float(iters_cat.mean()), "failed_replicates": bad,
         }
         if world == 1 and not args.no_cpu:
@@ -634,6 +657,7 @@ def main():
     ap.add_argument("--replicates", type=int, default=0, help="replicates per GPU per step (default: per workload)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--per-step-calls", action="store_true", help="one library call per timed step instead of one call for all K steps")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of four timed replicate rows")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

@@ -129,16 +129,20 @@ struct StageTimer {
     recs.push_back(r);
   }
   void end(cudaStream_t s) { cudaEventRecord(recs.back().b, s); }
-  void collect() {  // call after the stream is synchronised
+  // call after the stream is synchronised; `upto` < recs.size(): only the first `upto` records are known to have
+  // completed (a later batch is already in flight), the rest stay queued
+  void collect(size_t upto = (size_t)-1) {
     std::lock_guard<std::mutex> lk(g_prof.mu);
-    for (auto& r : recs) {
+    const size_t n = std::min(upto, recs.size());
+    for (size_t i = 0; i < n; ++i) {
+      Rec& r = recs[i];
       float ms = 0.f;
       if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) g_prof.ms[r.stage] += ms;
       g_prof.launches[r.stage] += 1;
       pool.push_back(r.a);
       pool.push_back(r.b);
     }
-    recs.clear();
+    recs.erase(recs.begin(), recs.begin() + n);
   }
   ~StageTimer() {
     for (auto& r : recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }

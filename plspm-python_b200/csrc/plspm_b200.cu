@@ -140,6 +140,7 @@ struct plspm_data {
   ImputeCtx* imp = nullptr;
   struct ImagePrefetch* prefetch = nullptr;  // multiplicity images of the first batch, generated during the upload (plspm_bootstrap_host)
   const uint8_t *c8img_ovr = nullptr, *c8vote_ovr = nullptr;  // ... and what the kernels of that batch read instead of the workspace images
+  size_t ws_off = 0;       // workspace of the batch being enqueued (plspm_bootstrap pipelines two)
   bool img_ready = false;  // the multiplicity images of the batch in flight were written by resample_images_kernel
   int max_smem = 227 * 1024;
 };
@@ -966,7 +967,7 @@ static int redo_exact(plspm_data* d, int64_t n_list, const int* rep_map_dev, con
   const plspm_model* m = d->model;
   const HostModel& h = m->h;
   cudaStream_t st = d->stream;
-  char* base = (char*)d->ws.ptr;
+  char* base = (char*)d->ws.ptr + d->ws_off;
   auto D = [&](size_t o) { return (double*)(base + o); };
   StreamPlan sp = bp.cross;
   sp.n_chunks = 1;  // partial buffers are laid out per replicate position; keep whole-row passes here
@@ -997,7 +998,7 @@ static int launch_moments(plspm_data* d, int64_t nb, const uint32_t* counts_dev,
                           const BatchPlan& bp) {
   const HostModel& h = d->model->h;
   cudaStream_t st = d->stream;
-  char* base = (char*)d->ws.ptr;
+  char* base = (char*)d->ws.ptr + d->ws_off;
   auto D = [&](size_t o) { return (double*)(base + o); };
   const bool i8 = d->i8_colsum && counts_dev;
   int8_t* c8 = (int8_t*)(base + bb.c8);
@@ -1142,7 +1143,7 @@ static int run_batch_num(plspm_data* d, int64_t nb, const uint32_t* counts_dev, 
   const plspm_model* m = d->model;
   const HostModel& h = m->h;
   cudaStream_t st = d->stream;
-  char* base = (char*)d->ws.ptr;
+  char* base = (char*)d->ws.ptr + d->ws_off;
   auto D = [&](size_t o) { return (double*)(base + o); };
   if (int rc = launch_moments(d, nb, counts_dev, bb, bp)) return rc;
   NumBatch b;
@@ -1208,7 +1209,7 @@ static int run_batch(plspm_data* d, int64_t nb, const uint32_t* counts_dev, cons
   const bool use_mma = want_fast && d->mma_vote && d->i8_colsum && counts_dev != nullptr;
   const bool use_fast = use_mma || (want_fast && d->Xf && d->blas);
   cudaStream_t st = d->stream;
-  char* base = (char*)d->ws.ptr;
+  char* base = (char*)d->ws.ptr + d->ws_off;
   auto D = [&](size_t o) { return (double*)(base + o); };
   if (int rc = launch_moments(d, nb, counts_dev, bb, bp)) return rc;
   SolveBatch b;
@@ -1437,7 +1438,7 @@ int plspm_fit(const plspm_model* m, plspm_data* d, int32_t scheme, double tol, i
   if (int rc = plan_batch(d, 1, bp)) return rc;
   const BatchBuffers bb = layout_batch(d, 1, bp, false, false, false, true, scores != nullptr);
   if (int rc = ws_reserve(d, bb.total)) return rc;
-  char* base = (char*)d->ws.ptr;
+  char* base = (char*)d->ws.ptr + d->ws_off;
   auto D = [&](size_t o) { return (double*)(base + o); };
   cudaStream_t st = d->stream;
   if (m->numeric) {
@@ -1594,36 +1595,93 @@ int plspm_bootstrap(const plspm_model* m, plspm_data* d, int32_t scheme, double 
   BatchPlan bp;
   if (int rc = plan_batch(d, nb_max, bp)) return rc;
   const BatchBuffers bb = layout_batch(d, nb_max, bp, true, idx != nullptr, out_is_device != 0, false, false);
-  if (int rc = ws_reserve(d, bb.total)) return rc;
-  char* base = (char*)d->ws.ptr;
+  // Batches are software-pipelined: the kernels of batch k + 1 are enqueued (into a second workspace) BEFORE the host
+  // waits for batch k, so the device never idles while the host reads statuses and prepares the next launch -- the
+  // 0.15 ms (one process) to 0.45 ms (eight processes sharing a host) per batch that kept the 8-GPU run at 0.96.
+  // The host-driven non-metric path synchronises inside a batch anyway and stays serial.
+  const int64_t n_batches = (rep_count + nb_max - 1) / nb_max;
+  static const bool serial_env = getenv("PLSPM_PIPELINE") && std::string(getenv("PLSPM_PIPELINE")) == "0";
+  const bool pipelined = n_batches > 1 && !m->numeric && !serial_env;
+  const size_t ws_stride = align_up(bb.total, 4096);
+  if (int rc = ws_reserve(d, pipelined ? 2 * ws_stride : bb.total)) return rc;
   cudaStream_t st = d->stream;
-  CK(cudaMemsetAsync(base + bb.ovf, 0, 8, st));
-  PinnedStage stage((size_t)(2 * nb_max + 2) * 4);
+  PinnedStage stage((size_t)2 * (2 * nb_max + 2) * 4);
   if (!stage.ints) return fail(PLSPM_ERR_NOMEM, "pinned staging buffer");
-  for (int64_t b0 = 0; b0 < rep_count; b0 += nb_max) {
-    const int64_t nb = std::min(nb_max, rep_count - b0);
-    // a short last batch reuses the plan (and therefore the workspace layout) of a full one
-    uint32_t* cnt = (uint32_t*)(base + bb.counts);
+  static const bool counts_split = getenv("PLSPM_COUNTS") && std::string(getenv("PLSPM_COUNTS")) == "split";
+  static const bool sync_split = getenv("PLSPM_SYNC") && std::string(getenv("PLSPM_SYNC")) == "split";  // A/B: round 1's three syncs
+
+  size_t timer_base = 0;  // stage-timer records of this call already collected (marks below are absolute)
+  struct Batch {
+    int64_t b0 = 0, nb = 0;
+    size_t ws_off = 0;
+    char* base = nullptr;
+    uint32_t* cnt = nullptr;
     int32_t* idx_dev = nullptr;
-    if (idx) {
-      idx_dev = (int32_t*)(base + bb.idx);
-      CK(cudaMemcpyAsync(idx_dev, idx + b0 * N, (size_t)nb * N * 4, cudaMemcpyHostToDevice, st));
+    double* rows = nullptr;
+    int *h_ovf = nullptr, *h_status = nullptr, *h_iters = nullptr;
+    bool have_counts = false, used_i8 = false;
+    cudaEvent_t done = nullptr;
+    size_t timer_mark = 0;  // stage-timer records up to here belong to batches <= this one
+  } slot[2];
+  for (int k = 0; k < 2; ++k) {
+    slot[k].ws_off = (pipelined && k) ? ws_stride : 0;
+    slot[k].base = (char*)d->ws.ptr + slot[k].ws_off;
+    slot[k].h_ovf = stage.ints + (size_t)k * (2 * nb_max + 2);
+    slot[k].h_status = slot[k].h_ovf + 2;
+    slot[k].h_iters = slot[k].h_status + nb_max;
+    if (cudaEventCreateWithFlags(&slot[k].done, cudaEventDisableTiming) != cudaSuccess) return fail(PLSPM_ERR_CUDA, "cudaEventCreate failed");
+  }
+  struct EventGuard { Batch* s; ~EventGuard() { for (int k = 0; k < 2; ++k) if (s[k].done) cudaEventDestroy(s[k].done); } } guard{slot};
+
+  // the [nb x N] uint32 multiplicity table: what the fp64 kernels, the legacy routes and the exact redo read.  The
+  // tensor-core routes take their int8 tile images straight from resample_images_kernel and never build it.
+  auto ensure_counts = [&](Batch& B) -> int {
+    if (B.have_counts) return 0;
+    CK(cudaMemsetAsync(B.cnt, 0, (size_t)B.nb * N * 4, st));
+    const int64_t threads = ((N + 3) / 4) * B.nb;
+    d->timer.begin(ST_COUNTS, st);
+    counts_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(B.cnt, B.idx_dev, N, B.nb, rep_begin + B.b0, seed);
+    d->timer.end(st);
+    CK(cudaGetLastError());
+    B.have_counts = true;
+    return 0;
+  };
+  // overflow flag, statuses, iteration counts and (host output) the rows of a batch come back together, behind one event
+  auto read_back = [&](Batch& B) -> int {
+    if (sync_split) {
+      CK(cudaMemcpyAsync(B.h_ovf, B.base + bb.ovf, 4, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      CK(cudaMemcpyAsync(B.h_status, B.base + bb.status, (size_t)B.nb * 4, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
     }
-    // the [nb x N] uint32 multiplicity table: what the fp64 kernels, the legacy routes and the exact redo read.  The
-    // tensor-core routes take their int8 tile images straight from resample_images_kernel and never build it.
-    bool have_counts = false;
-    auto ensure_counts = [&]() -> int {
-      if (have_counts) return 0;
-      CK(cudaMemsetAsync(cnt, 0, (size_t)nb * N * 4, st));
-      const int64_t threads = ((N + 3) / 4) * nb;
-      d->timer.begin(ST_COUNTS, st);
-      counts_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(cnt, idx_dev, N, nb, rep_begin + b0, seed);
-      d->timer.end(st);
-      CK(cudaGetLastError());
-      have_counts = true;
-      return 0;
-    };
-    static const bool counts_split = getenv("PLSPM_COUNTS") && std::string(getenv("PLSPM_COUNTS")) == "split";
+    CK(cudaMemcpyAsync(B.h_ovf, B.base + bb.ovf, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(B.h_status, B.base + bb.status, (size_t)B.nb * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(B.h_iters, B.base + bb.iters, (size_t)B.nb * 4, cudaMemcpyDeviceToHost, st));
+    if (!out_is_device)
+      CK(cudaMemcpyAsync(out + (size_t)B.b0 * n_out, B.rows, (size_t)B.nb * n_out * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(B.done, st));
+    B.timer_mark = timer_base + d->timer.recs.size();
+    return 0;
+  };
+  auto solve_batch = [&](Batch& B) -> int {
+    d->ws_off = B.ws_off;
+    if (m->numeric) return run_batch_num(d, B.nb, B.cnt, bb, scheme, tol, max_iter, bp, B.rows, false);
+    return run_batch(d, B.nb, B.cnt, bb, scheme, tol, max_iter, bp, B.rows, false);
+  };
+  // everything of one batch up to its read-back, without waiting for anything
+  auto enqueue = [&](Batch& B, int64_t b0) -> int {
+    B.b0 = b0;
+    B.nb = std::min(nb_max, rep_count - b0);  // (a short last batch reuses the plan and the workspace layout of a full one)
+    B.have_counts = false;
+    B.cnt = (uint32_t*)(B.base + bb.counts);
+    B.idx_dev = nullptr;
+    B.rows = out_is_device ? out + (size_t)b0 * n_out : (double*)(B.base + bb.out);
+    const int64_t nb = B.nb;
+    CK(cudaMemsetAsync(B.base + bb.ovf, 0, 8, st));
+    if (idx) {
+      B.idx_dev = (int32_t*)(B.base + bb.idx);
+      CK(cudaMemcpyAsync(B.idx_dev, idx + b0 * N, (size_t)nb * N * 4, cudaMemcpyHostToDevice, st));
+    }
     d->img_ready = false;
     d->c8img_ovr = d->c8vote_ovr = nullptr;
     const bool fuse_images = !counts_split && !m->numeric && d->gram_mma && d->i8_colsum && (!vote || (d->mma_vote && d->fast_vote));
@@ -1632,7 +1690,7 @@ int plspm_bootstrap(const plspm_model* m, plspm_data* d, int32_t scheme, double 
         (pf->c8vote != nullptr) == vote) {
       // generated on the side stream while X was uploading: wait for it, adopt its overflow flag
       CK(cudaStreamWaitEvent(st, pf->done, 0));
-      CK(cudaMemcpyAsync(base + bb.ovf, pf->ovf, 4, cudaMemcpyDeviceToDevice, st));
+      CK(cudaMemcpyAsync(B.base + bb.ovf, pf->ovf, 4, cudaMemcpyDeviceToDevice, st));
       d->c8img_ovr = pf->c8img;
       d->c8vote_ovr = pf->c8vote;
       d->img_ready = true;
@@ -1644,72 +1702,73 @@ int plspm_bootstrap(const plspm_model* m, plspm_data* d, int32_t scheme, double 
       CK(ensure_smem(resample_images_kernel, (size_t)(range_rows)));
       d->timer.begin(ST_COUNTS, st);
       resample_images_kernel<<<dim3((unsigned)n_groups * 512, (unsigned)n_ranges), RI_THREADS, (size_t)range_rows, st>>>(
-          idx_dev, N, nb, rep_begin + b0, seed, range_rows, n_groups, vote ? (int)((nb + 127) / 128) : 0, d->n_chunks64,
-          (uint8_t*)(base + bb.c8img), (uint8_t*)(base + bb.c8vote), (int*)(base + bb.ovf));
+          B.idx_dev, N, nb, rep_begin + b0, seed, range_rows, n_groups, vote ? (int)((nb + 127) / 128) : 0, d->n_chunks64,
+          (uint8_t*)(B.base + bb.c8img), (uint8_t*)(B.base + bb.c8vote), (int*)(B.base + bb.ovf));
       d->timer.end(st);
       CK(cudaGetLastError());
       d->img_ready = true;
-    } else if (int rc = ensure_counts()) {
+    } else if (int rc = ensure_counts(B)) {
       return rc;
     }
-    double* rows = out_is_device ? out + (size_t)b0 * n_out : (double*)(base + bb.out);
-    // ONE host round trip per batch: the overflow flag, the statuses, the iteration counts and (host output) the rows
-    // come back together (round 1 synchronised three times per batch, which is what cost the 8-GPU run 5 % when eight
-    // processes share the host); the rare redo paths re-issue what they changed.
-    int* h_ovf = stage.ints;
-    int* h_status = stage.ints + 2;
-    int* h_iters = h_status + nb_max;
-    static const bool sync_split = getenv("PLSPM_SYNC") && std::string(getenv("PLSPM_SYNC")) == "split";  // A/B: round 1's three syncs
-    auto fetch = [&]() -> int {
-      if (sync_split) {
-        CK(cudaMemcpyAsync(h_ovf, base + bb.ovf, 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        CK(cudaMemcpyAsync(h_status, base + bb.status, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-      }
-      CK(cudaMemcpyAsync(h_ovf, base + bb.ovf, 4, cudaMemcpyDeviceToHost, st));
-      CK(cudaMemcpyAsync(h_status, base + bb.status, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
-      CK(cudaMemcpyAsync(h_iters, base + bb.iters, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
-      if (!out_is_device)
-        CK(cudaMemcpyAsync(out + (size_t)b0 * n_out, rows, (size_t)nb * n_out * 8, cudaMemcpyDeviceToHost, st));
-      CK(cudaStreamSynchronize(st));
-      return 0;
-    };
-    for (int attempt = 0; attempt < 2; ++attempt) {
-      if (m->numeric) {
-        if (int rc = run_batch_num(d, nb, cnt, bb, scheme, tol, max_iter, bp, rows, false)) return rc;
-      } else if (int rc = run_batch(d, nb, cnt, bb, scheme, tol, max_iter, bp, rows, false)) {
-        return rc;
-      }
-      if (int rc = fetch()) return rc;
-      // a multiplicity above 127 does not fit the int8 operand of the tensor-core routes: redo in fp64
-      if (!d->i8_colsum || !*h_ovf) break;
-      CK(cudaMemsetAsync(base + bb.ovf, 0, 8, st));
+    B.used_i8 = d->i8_colsum;
+    if (int rc = solve_batch(B)) return rc;
+    d->img_ready = false;
+    d->c8img_ovr = d->c8vote_ovr = nullptr;
+    return read_back(B);
+  };
+  // wait for a batch, run the (rare) redo paths, hand statuses / iteration counts to the caller
+  auto finish = [&](Batch& B) -> int {
+    CK(cudaEventSynchronize(B.done));
+    const int64_t nb = B.nb;
+    if (B.used_i8 && *B.h_ovf) {
+      // a multiplicity above 127 does not fit the int8 operand of the tensor-core routes: redo the batch in fp64
+      CK(cudaMemsetAsync(B.base + bb.ovf, 0, 8, st));
       d->i8_colsum = false;
       d->img_ready = false;
       d->c8img_ovr = d->c8vote_ovr = nullptr;
-      if (int rc = ensure_counts()) return rc;
+      if (int rc = ensure_counts(B)) return rc;
+      B.used_i8 = false;
+      if (int rc = solve_batch(B)) return rc;
+      if (int rc = read_back(B)) return rc;
+      CK(cudaEventSynchronize(B.done));
     }
     if (vote && d->fast_vote) {
       // replicates whose low-precision sign vote was undecided are redone with exact fp64 cross moments
       std::vector<int> redo;
       for (int64_t r = 0; r < nb; ++r)
-        if (h_status[r] == STATUS_AMBIGUOUS) redo.push_back((int)r);
+        if (B.h_status[r] == STATUS_AMBIGUOUS) redo.push_back((int)r);
       if (!redo.empty()) {
-        int* map_dev = (int*)(base + bb.rep_map);
+        int* map_dev = (int*)(B.base + bb.rep_map);
         CK(cudaMemcpyAsync(map_dev, redo.data(), redo.size() * 4, cudaMemcpyHostToDevice, st));
-        if (int rc = ensure_counts()) return rc;
-        if (int rc = redo_exact(d, (int64_t)redo.size(), map_dev, cnt, bb, scheme, tol, max_iter, bp, rows)) return rc;
+        if (int rc = ensure_counts(B)) return rc;
+        d->ws_off = B.ws_off;
+        if (int rc = redo_exact(d, (int64_t)redo.size(), map_dev, B.cnt, bb, scheme, tol, max_iter, bp, B.rows)) return rc;
         g_redo_count += (int64_t)redo.size();
         if ((int64_t)redo.size() * 2 > nb) d->fast_vote = false;  // this data does not suit the fp16 vote
-        if (int rc = fetch()) return rc;
+        if (int rc = read_back(B)) return rc;
+        CK(cudaEventSynchronize(B.done));  // (redo.data() is pageable: the copy above has completed by now)
       }
     }
-    if (iters) std::memcpy(iters + b0, h_iters, (size_t)nb * 4);
-    if (status) std::memcpy(status + b0, h_status, (size_t)nb * 4);
+    if (iters) std::memcpy(iters + B.b0, B.h_iters, (size_t)nb * 4);
+    if (status) std::memcpy(status + B.b0, B.h_status, (size_t)nb * 4);
+    const size_t n_done = std::min(B.timer_mark - timer_base, d->timer.recs.size());
+    d->timer.collect(n_done);
+    timer_base += n_done;
+    return 0;
+  };
+
+  int rc = enqueue(slot[0], 0);
+  for (int64_t k = 0; k < n_batches && rc == 0; ++k) {
+    Batch& cur = slot[pipelined ? (k & 1) : 0];
+    if (pipelined && k + 1 < n_batches) rc = enqueue(slot[(k + 1) & 1], (k + 1) * nb_max);
+    if (rc == 0) rc = finish(cur);
+    if (rc == 0 && !pipelined && k + 1 < n_batches) rc = enqueue(slot[0], (k + 1) * nb_max);
+  }
+  d->ws_off = 0;
+  if (rc) {
+    cudaStreamSynchronize(st);
     d->timer.collect();
-    d->img_ready = false;
-    d->c8img_ovr = d->c8vote_ovr = nullptr;
+    return rc;
   }
   return PLSPM_OK;
 }
