@@ -1619,7 +1619,7 @@ int plspm_bootstrap(const plspm_model* m, plspm_data* d, int32_t scheme, double 
     int32_t* idx_dev = nullptr;
     double* rows = nullptr;
     int *h_ovf = nullptr, *h_status = nullptr, *h_iters = nullptr;
-    bool have_counts = false, used_i8 = false;
+    bool have_counts = false, used_i8 = false, used_fast_vote = false;  // routes the batch was ENQUEUED with (a later batch may be in flight when an earlier one switches them off)
     cudaEvent_t done = nullptr;
     size_t timer_mark = 0;  // stage-timer records up to here belong to batches <= this one
   } slot[2];
@@ -1711,6 +1711,7 @@ int plspm_bootstrap(const plspm_model* m, plspm_data* d, int32_t scheme, double 
       return rc;
     }
     B.used_i8 = d->i8_colsum;
+    B.used_fast_vote = vote && d->fast_vote;
     if (int rc = solve_batch(B)) return rc;
     d->img_ready = false;
     d->c8img_ovr = d->c8vote_ovr = nullptr;
@@ -1728,11 +1729,12 @@ int plspm_bootstrap(const plspm_model* m, plspm_data* d, int32_t scheme, double 
       d->c8img_ovr = d->c8vote_ovr = nullptr;
       if (int rc = ensure_counts(B)) return rc;
       B.used_i8 = false;
+      B.used_fast_vote = vote && d->fast_vote;
       if (int rc = solve_batch(B)) return rc;
       if (int rc = read_back(B)) return rc;
       CK(cudaEventSynchronize(B.done));
     }
-    if (vote && d->fast_vote) {
+    if (B.used_fast_vote) {
       // replicates whose low-precision sign vote was undecided are redone with exact fp64 cross moments
       std::vector<int> redo;
       for (int64_t r = 0; r < nb; ++r)

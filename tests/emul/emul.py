@@ -83,6 +83,12 @@ def set_vote_mode(mode: int):
     lib().emul_set_vote_mode(int(mode))
 
 
+def set_resume(on: bool):
+    """True (default): solver phases 2 / 3 resume from the converged state phase 1 saved, like the CUDA library;
+    False: they iterate again from the initial weights (round 1's behaviour)."""
+    lib().emul_set_resume(int(bool(on)))
+
+
 def last_ambiguous() -> bool:
     return bool(lib().emul_last_ambiguous())
 

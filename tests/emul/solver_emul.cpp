@@ -32,7 +32,9 @@ extern "C" int emul_model_info(int L, const int32_t* block_sizes, const int8_t* 
 
 static int g_vote_mode = 0;      // 0: exact cross moments; 1: emulate the low-precision vote (phase 3)
 static int g_last_ambiguous = 0;
+static int g_resume = 1;         // 1: phases 2 / 3 resume from the state phase 1 saved (what the CUDA library does); 0: iterate again
 extern "C" void emul_set_vote_mode(int mode) { g_vote_mode = mode; }
+extern "C" void emul_set_resume(int on) { g_resume = on; }
 extern "C" int emul_last_ambiguous() { return g_last_ambiguous; }
 
 extern "C" int emul_fit(int L, const int32_t* block_sizes, const int8_t* modes, const int8_t* path, int scaled,
@@ -83,8 +85,9 @@ extern "C" int emul_fit(int L, const int32_t* block_sizes, const int8_t* modes, 
     solve_replicate(A, smem.data());
   } else {
     // sparse tile set: weights first, then the P x L cross-moment pass, then the full solve
-    std::vector<double> sh(L, 0.0);
+    std::vector<double> sh(L, 0.0), state(solver_state_doubles(A.M), 0.0);
     A.phase = 1; A.wf_out = wf.data(); A.sh_out = sh.data();
+    if (g_resume) { A.state = state.data(); A.resume = 1; }
     solve_replicate(A, smem.data());
     g_last_ambiguous = 0;
     bool need_exact = true;

@@ -261,7 +261,7 @@ def test_sparse_ragged_mixed_modes(eng):
     np.testing.assert_allclose(rows, orows, rtol=REL, atol=1e-9)
 
 
-def test_fast_vote_decides_or_falls_back_exactly(eng):
+def test_fast_vote_decides_or_falls_back_exactly(eng, monkeypatch):
     """Sparse tile sets vote with an fp16 tensor-core pass when its error bound allows it; undecided
     replicates are redone with exact fp64 cross moments.  Both routes must reproduce the oracle."""
     # (1) independent blocks, N = 300k: far cross-correlations are noise ~ 0.0018, inside the 0.002 bound
@@ -281,6 +281,15 @@ def test_fast_vote_decides_or_falls_back_exactly(eng):
     assert (status == 0).all()
     np.testing.assert_array_equal(iters, oiters)
     np.testing.assert_allclose(rows, orows, rtol=REL, atol=1e-9)
+    # (1b) the same data in pipelined batches of two: batch 0's redo switches the fast vote off for the handle while
+    # batch 1 (enqueued with it on) is already in flight -- its undecided replicates must still be redone
+    data2 = eng.Data(model, X)
+    monkeypatch.setenv("PLSPM_MAX_BATCH", "2")
+    rows_b, status_b, iters_b = eng.bootstrap(model, data2, "centroid", 0, 6, seed=4)
+    monkeypatch.delenv("PLSPM_MAX_BATCH")
+    assert (status_b == 0).all()
+    np.testing.assert_array_equal(iters_b, oiters)
+    np.testing.assert_allclose(rows_b, orows, rtol=REL, atol=1e-9)
     # (2) a correlated chain with reverse-coded blocks: decided by the fast vote (no redo), signs still right
     N, L, K = 20000, 12, 8
     X, path = make_synthetic(N, L, K, seed=6, reverse_blocks=(2, 7))

@@ -163,6 +163,32 @@ def test_low_precision_vote_logic(syn):
         emul.set_vote_mode(0)
 
 
+def test_resumed_phases_equal_a_second_iteration():
+    """Sparse tile sets: phase 1 stores the converged iteration state (w, V, dinv, R, pooled scale, counts) and phases
+    2 / 3 resume from it (what the CUDA library does since round 2).  Must give exactly what iterating again gives."""
+    rng = np.random.default_rng(5)
+    for scheme, mode, scaled in (("centroid", 0, True), ("path", 1, True), ("factorial", 0, False)):
+        X, path = make_synthetic(700, 7, 4, 13, reverse_blocks=(3,))
+        idx = rng.integers(0, 700, 700).astype(np.int32)
+        outs = []
+        for vote_mode in (0, 1):
+            emul.set_vote_mode(vote_mode)
+            pair = []
+            for resume in (True, False):
+                emul.set_resume(resume)
+                pair.append(emul.fit(X, [4] * 7, [mode] * 7, path, scheme, scaled, idx=idx, tile_policy=2))
+            emul.set_resume(True)
+            emul.set_vote_mode(0)
+            a, b = pair
+            assert a["info"]["full"] == 0 and a["iterations"] == b["iterations"] and a["status"] == b["status"] == 0
+            for key in ("out_row", "weights", "loadings", "r_squared", "path_coefficients", "total_effects"):
+                np.testing.assert_array_equal(a[key], b[key], err_msg="%s %s vote_mode=%d" % (scheme, key, vote_mode))
+            outs.append(a)
+        ref, it, st = orc.replicate_row(X, idx, [4] * 7, [mode] * 7, path, scheme, scaled)
+        assert st == 0 and it == outs[0]["iterations"]
+        np.testing.assert_allclose(outs[0]["out_row"], ref, rtol=1e-8, atol=1e-11)
+
+
 # ---- non-metric path with numeric scales (solver_num.h) ------------------------------------------
 @pytest.fixture(scope="module")
 def nm():
