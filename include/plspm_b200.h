@@ -89,13 +89,17 @@ int plspm_fit(const plspm_model* m, plspm_data* d, int32_t scheme, double tol, i
  * otherwise idx is a HOST int32 [rep_count * N] matrix of injected indices (parity runs).
  * out: [rep_count * info[7]] doubles, each row = weights P | r_squared L | total effects E |
  * direct effects E | loadings P; a host pointer, or a device pointer if out_is_device.
- * status / iters: host int32 [rep_count]. */
+ * status / iters: host int32 [rep_count].
+ * Replicates run in batches sized by a 3 GB workspace budget (PLSPM_MAX_BATCH caps them); with several batches the
+ * kernels of batch k + 1 are enqueued before the host waits for batch k (two workspaces).  The call returns after the
+ * stream has drained. */
 int plspm_bootstrap(const plspm_model* m, plspm_data* d, int32_t scheme, double tol, int32_t max_iter,
                     int64_t rep_begin, int64_t rep_count, uint64_t seed, const int32_t* idx, double* out,
                     int32_t out_is_device, int32_t* status, int32_t* iters);
 
 /* Same call with a HOST observation matrix: upload + bootstrap + release in one entry point
- * (what a caller without a resident data handle pays end to end). */
+ * (what a caller without a resident data handle pays end to end).  With idx == NULL the int8 multiplicity images of
+ * the first batch are generated on a side stream while X is uploading. */
 int plspm_bootstrap_host(const plspm_model* m, const double* X, int64_t N, int64_t ld, int32_t scheme, double tol,
                          int32_t max_iter, int64_t rep_begin, int64_t rep_count, uint64_t seed, const int32_t* idx,
                          double* out, int32_t* status, int32_t* iters);
