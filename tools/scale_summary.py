@@ -11,7 +11,7 @@ SERIES = {
     "c3": ["bench_r02_c3_final.json", "bench_r02_c3_2gpu_final.json", "bench_r02_c3_4gpu_final.json", "bench_r02_c3_8gpu_final.json"],
     "c3_before_pipelining_1536_per_step": ["bench_r02_c3_v10.json", "bench_r02f_c3_2gpu.json", "bench_r02f_c3_4gpu.json", "bench_r02f_c3_8gpu.json"],
     "c4": ["bench_r02_c4_final.json", "bench_r02_c4_8gpu_final.json"],
-    "c5": ["bench_r02_c5_v7.json", "bench_r02_c5_8gpu.json"],
+    "c5": ["bench_r02_c5_final.json", "bench_r02_c5_2gpu_final.json", "bench_r02_c5_8gpu.json"],
 }
 out = {"format": "per-N lines of bench.py (weak scaling: per-GPU work fixed; value = whole-job fits/s, time = max over ranks)"}
 for name, files in SERIES.items():
