@@ -240,8 +240,10 @@ def workload_config(name, w, reps):
     return {"workload": w["desc"], "name": name, "N": int(N), "P": int(P), "L": len(w["blocks"]),
             "mode": "B" if w["modes"][0] else "A", "scheme": w["scheme"], "scaled": bool(w["scaled"]), "numeric_scales": bool(w.get("numeric")),
             "tol": 1e-6, "max_iter": 100, "replicates_per_gpu_per_step": int(reps),
-            "l2": "inputs larger than L2: X (%.1f MB fp64) + %.1f MB of per-replicate resample counts + Gram "
-                  "workspace per step are streamed every step (L2 is 126 MB)" % (N * P * 8 / 1e6, reps * N * 4 / 1e6)}
+            "l2": "inputs larger than L2, no flush needed: per step the kernels stream the operands derived from X (%.0f MB: "
+                  "the pre-scaled transposed copy and the fp16 images of the sign vote; X itself is %.1f MB fp64), %.0f MB of "
+                  "int8 multiplicity images of the step's own resamples and the Gram partials (L2 is 126 MB)"
+                  % (N * P * 8 / 1e6 + N * P * 2 * 1.5 / 1e6, N * P * 8 / 1e6, 2.0 * reps * N / 1e6)}
 
 
 # ------------------------------------------------------------------------------------------------
