@@ -67,8 +67,9 @@ struct HostModel {
   // shared-memory doubles the solver needs (see solver_core.h layout)
   size_t solver_smem_doubles() const { return (size_t)4 * Ppad + n_v + 4 * (size_t)L + 3 * (size_t)L * L + 40 + 2 * ((L + 1) / 2) + 8; }
   // solve_replicate (solver_core.h) keeps TWO L x L arrays (the path coefficients reuse the inner weights' storage, the
-  // total effects the score correlations'): 8 KB less for L = 32, which is a sixth resident CTA per SM on c3
-  size_t solver_core_smem_doubles() const { return solver_smem_doubles() - (size_t)L * L; }
+  // total effects the score correlations') and THREE Ppad vectors (no separate copy of the previous weights): 10 KB less
+  // for c3, which is seven resident CTAs per SM instead of five
+  size_t solver_core_smem_doubles() const { return solver_smem_doubles() - (size_t)L * L - (size_t)Ppad; }
   ModelView host_view() const;
 };
 

@@ -173,8 +173,8 @@ PL_HD void solve_replicate(const SolveArgs& A, double* smem) {
   const ModelView& M = A.M;
   const int L = M.L, Ppad = M.Ppad, tid = PL_TID, nt = PL_NT;
   double* w = smem;                  // [Ppad] current outer weights (un-normalised)
-  double* wold = w + Ppad;           // [Ppad]
-  double* u = wold + Ppad;           // [Ppad] new weights / temporaries
+  double* u = w + Ppad;              // [Ppad] new weights / temporaries (the previous weights are w itself: the loop
+                                     //        leaves w == w_old at its end, so no third array)
   double* m = u + Ppad;              // [Ppad] replicate column means of x~
   double* V = m + Ppad;              // [n_v]
   double* dinv = V + M.n_v;          // [L] 1/sd_pop(Y_l)
@@ -244,7 +244,6 @@ PL_HD void solve_replicate(const SolveArgs& A, double* smem) {
     double wi = 1.0 / sqrt(bs);
     for (int r = 0; r < SLOT * ((k + SLOT - 1) / SLOT); ++r) {
       w[o + r] = (r < k) ? wi : 0.0;
-      wold[o + r] = w[o + r];
       u[o + r] = 0.0;
     }
     // Mode B: factor S_ll once per replicate (the block Gram is iteration-invariant)
@@ -358,9 +357,8 @@ PL_HD void solve_replicate(const SolveArgs& A, double* smem) {
     // ---- convergence (weights.py:51-53) ----------------------------------------------------------
     double part = 0.0;
     for (int p = tid; p < Ppad; p += nt) {
-      double df = fabs(wold[p]) - fabs(u[p]);
+      double df = fabs(w[p]) - fabs(u[p]);
       part += df * df;
-      wold[p] = u[p];
       w[p] = u[p];
     }
     double conv = block_sum(part, red);
@@ -415,8 +413,8 @@ PL_HD void solve_replicate(const SolveArgs& A, double* smem) {
       bsum[l] = sh;
     }
   if (A.phase == 3) {
-    // per-column factor of the vote's error bound (wold is free after the iteration)
-    for (int p = tid; p < Ppad; p += nt) wold[p] = M.col_lv[p] >= 0 ? sqrt(gram_raw(M, A.G, p, p)) * A.inv_sd[p] : 0.0;
+    // per-column factor of the vote's error bound (w is dead once u = w dinv is formed)
+    for (int p = tid; p < Ppad; p += nt) w[p] = M.col_lv[p] >= 0 ? sqrt(gram_raw(M, A.G, p, p)) * A.inv_sd[p] : 0.0;
     for (int l = tid; l < L; l += nt) {
       unc[l] = 0;
       // fp32 score generation: |t^ - t| <= (k+4) 2^-24 (sum_k |x_k w_k| + |sh|) per row, hence (Cauchy-Schwarz
@@ -462,7 +460,7 @@ PL_HD void solve_replicate(const SolveArgs& A, double* smem) {
     for (int p0 = 0; p0 < Ppad; p0 += nt) {
       const int p = p0 + tid;
       const int lp = p < Ppad ? M.col_lv[p] : -1;
-      const double colf = lp >= 0 ? wold[p] : 0.0;
+      const double colf = lp >= 0 ? w[p] : 0.0;
       const double shift = (lp >= 0 && A.fast_uncentred) ? A.colsum[p] * A.inv_sd[p] : 0.0;
       const float* cf = A.fast_cross + ((size_t)(lp >= 0 ? p : 0) * L) * A.fast_nb + A.fast_b;
       for (int l = 0; l < L; ++l) {
