@@ -582,7 +582,8 @@ def run_gpu_arm(args):
                                         "reference_single_fit_s": single_s, "reference_single_fit_rows": rows,
                                         # quirk Q1: the reference runs its weight iteration twice per fit
                                         # (estimator.py:36,43,52); `value` is the reference as it is, this is the same
-                                        # figure with that duplicate work discounted
+                                        # figure with a whole duplicate fit discounted (an upper bound: treatment and the
+                                        # inner model run once)
                                         "value_without_q1_duplicate": 2.0 * fps}
             else:
                 w_cpu, cpu_scale, cpu_note = cpu_workload(w)
