@@ -235,9 +235,9 @@ int build_model(int L, const int32_t* block_sizes, const int8_t* modes, const in
   for (int l = 0; l < L; ++l)
     if (m.lv_mode[l] == MODE_B) {
       m.chol_b_off[l] = ws;
-      ws += m.lv_k[l] * m.lv_k[l];
+      ws += mode_b_scratch_doubles(m.lv_k[l]);
     }
-  ws += L * (m.max_deg * m.max_deg + 2 * m.max_deg);
+  ws += L * ols_scratch_doubles(m.max_deg);
   m.ws_doubles = std::max(ws, 1);
   return 0;
 }

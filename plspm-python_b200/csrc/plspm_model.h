@@ -37,6 +37,17 @@ struct ModelView {
   const int8_t* omega;                      // [L*L] 1: the Gram tiles of LV pair (i, j) are computed
 };
 
+#if defined(__CUDACC__)
+#define PLSPM_HOST_DEVICE __host__ __device__
+#else
+#define PLSPM_HOST_DEVICE
+#endif
+// Per-LV scratch of the inner regressions: A [deg x deg] | beta [deg] | four vectors for the minimum-norm fallback
+PLSPM_HOST_DEVICE inline int ols_scratch_doubles(int max_deg) { return max_deg * max_deg + 5 * max_deg; }
+// Mode-B block of k manifest variables: Cholesky factor (or, rank deficient, the matrix itself) [k x k] | flag |
+// solution + three vectors of the minimum-norm fallback
+PLSPM_HOST_DEVICE inline int mode_b_scratch_doubles(int k) { return k * k + 1 + 4 * k; }
+
 struct HostModel {
   int L = 0, P = 0, Ppad = 0, ns = 0, scaled = 0, full = 0;
   int n_tiles = 0, n_tg = 0, n_pairs = 0, n_v = 0, n_eff = 0, max_deg = 0, ws_doubles = 0, kmax = 0;

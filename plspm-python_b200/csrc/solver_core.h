@@ -155,16 +155,89 @@ PL_HD void chol_solve(const double* A, int n, int ld, double* b) {
   }
 }
 
-// Regression of LV i on its predecessors from a correlation matrix R (L x L):
-// beta = R_pp^-1 R_pi.  scratch: [deg*deg + deg].  Returns false if R_pp is not PD.
+// Minimum-norm solution of A x = b for a symmetric positive SEMI-definite A (full n x n storage) and b in its range
+// -- the normal equations of a rank-deficient least-squares problem, where the reference's SVD-based solvers
+// (scipy lstsq / gelsd in mode.py:50-52, statsmodels' pinv in scheme.py:50 and inner_model.py:76-77) return the
+// minimum-norm coefficients.  Conjugate gradients started at 0 stay in range(A) and converge to exactly that solution
+// in at most rank(A) steps; the tiny spurious eigenvalues of the null space are never resolved because the iteration
+// stops on the residual.  t: 3 n doubles of scratch.  x must not alias b.
+PL_HD void cg_min_norm(const double* A, int n, const double* b, double* x, double* t) {
+  double *r = t, *p = t + n, *Ap = t + 2 * n;
+  double rs = 0.0;
+  for (int i = 0; i < n; ++i) { x[i] = 0.0; r[i] = b[i]; p[i] = b[i]; rs += b[i] * b[i]; }
+  const double stop = 1e-28 * rs;
+  for (int it = 0; it < 2 * n && rs > stop; ++it) {
+    double pAp = 0.0;
+    for (int i = 0; i < n; ++i) {
+      double a = 0.0;
+      for (int j = 0; j < n; ++j) a += A[i * n + j] * p[j];
+      Ap[i] = a;
+      pAp += p[i] * a;
+    }
+    if (!(pAp > 0.0)) break;
+    const double alpha = rs / pAp;
+    double rs_new = 0.0;
+    for (int i = 0; i < n; ++i) {
+      x[i] += alpha * p[i];
+      r[i] -= alpha * Ap[i];
+      rs_new += r[i] * r[i];
+    }
+    const double beta = rs_new / rs;
+    for (int i = 0; i < n; ++i) p[i] = r[i] + beta * p[i];
+    rs = rs_new;
+  }
+}
+
+// Mode B (mode.py:50-52): the block matrix S_ll is factored once per replicate.  C: mode_b_scratch_doubles(k); `fill`
+// writes element (r, c).  A rank-deficient block keeps the matrix itself and sets the flag C[k*k].
+#define PL_MODE_B_PREPARE(C, k, ELEM)                                               \
+  do {                                                                              \
+    for (int r_ = 0; r_ < (k); ++r_)                                                \
+      for (int c_ = 0; c_ <= r_; ++c_) (C)[r_ * (k) + c_] = ELEM(r_, c_);           \
+    (C)[(k) * (k)] = 0.0;                                                           \
+    if (!chol_factor((C), (k), (k))) {                                              \
+      for (int r_ = 0; r_ < (k); ++r_)                                              \
+        for (int c_ = 0; c_ < (k); ++c_) (C)[r_ * (k) + c_] = ELEM(r_, c_);         \
+      (C)[(k) * (k)] = 1.0;                                                         \
+    }                                                                               \
+  } while (0)
+
+// w <- S_ll^-1 w, or the minimum-norm least-squares weights when the block is rank deficient
+PL_HD void mode_b_solve(double* C, int k, double* w) {
+  if (C[k * k] == 0.0) {
+    chol_solve(C, k, k, w);
+    return;
+  }
+  double* x = C + k * k + 1;
+  cg_min_norm(C, k, w, x, x + k);
+  for (int i = 0; i < k; ++i) w[i] = x[i];
+}
+
+// Regression of LV i on its predecessors from a correlation matrix R (L x L): beta = R_pp^-1 R_pi, or the
+// minimum-norm coefficients when R_pp is singular (collinear scores).  scratch: ols_scratch_doubles(max_deg), beta_out =
+// scratch + max_deg^2.  Returns false only for non-finite input.
 PL_HD bool regress_on_predecessors(const ModelView& M, const double* R, int i, double* scratch, double* beta_out) {
   int b0 = M.pred_begin[i], n = M.pred_begin[i + 1] - b0;
   double* A = scratch;
   for (int a = 0; a < n; ++a)
     for (int c = 0; c <= a; ++c) A[a * n + c] = R[M.pred_idx[b0 + a] * M.L + M.pred_idx[b0 + c]];
   for (int a = 0; a < n; ++a) beta_out[a] = R[M.pred_idx[b0 + a] * M.L + i];
-  if (!chol_factor(A, n, n)) return false;
-  chol_solve(A, n, n, beta_out);
+  if (chol_factor(A, n, n)) {
+    chol_solve(A, n, n, beta_out);
+    return true;
+  }
+  double* rhs = beta_out + M.max_deg;  // four spare vectors follow beta in the scratch
+  bool finite = true;
+  for (int a = 0; a < n; ++a) {
+    rhs[a] = beta_out[a];
+    finite = finite && (rhs[a] - rhs[a] == 0.0);
+    for (int c = 0; c < n; ++c) {
+      A[a * n + c] = R[M.pred_idx[b0 + a] * M.L + M.pred_idx[b0 + c]];
+      finite = finite && (A[a * n + c] - A[a * n + c] == 0.0);
+    }
+  }
+  if (!finite) return false;
+  cg_min_norm(A, n, rhs, beta_out, rhs + M.max_deg);
   return true;
 }
 
@@ -198,8 +271,8 @@ PL_HD void solve_replicate(const SolveArgs& A, double* smem) {
 
   double iss = 1.0;  // 1 / pooled scale^2
 #define PL_S(p, q) ((gram_raw(M, A.G, (p), (q)) * invN - m[p] * m[q]) * iss)
-  double* ols = A.ws + (M.ws_doubles - L * (M.max_deg * M.max_deg + 2 * M.max_deg));
-  const int ols_stride = M.max_deg * M.max_deg + 2 * M.max_deg;
+  const int ols_stride = ols_scratch_doubles(M.max_deg);
+  double* ols = A.ws + (M.ws_doubles - L * ols_stride);
   int iteration = 0, status = STATUS_OK;
   if (A.resume && A.state && A.phase != 1) {
     // the weights converged in phase 1 (same replicate, same moments): take w, V, dinv, R as they were left
@@ -249,9 +322,9 @@ PL_HD void solve_replicate(const SolveArgs& A, double* smem) {
     // Mode B: factor S_ll once per replicate (the block Gram is iteration-invariant)
     if (M.lv_mode[l] == MODE_B) {
       double* C = A.ws + M.chol_b_off[l];
-      for (int r = 0; r < k; ++r)
-        for (int c = 0; c <= r; ++c) C[r * k + c] = PL_S(o + r, o + c);
-      if (!chol_factor(C, k, k)) flag[0] = STATUS_SINGULAR;
+#define PL_BLK(r_, c_) PL_S(o + (r_), o + (c_))
+      PL_MODE_B_PREPARE(C, k, PL_BLK);
+#undef PL_BLK
     }
   }
   PL_SYNC();
@@ -352,7 +425,7 @@ PL_HD void solve_replicate(const SolveArgs& A, double* smem) {
     PL_SYNC();
     for (int l = tid; l < L; l += nt)
       if (M.lv_mode[l] == MODE_B && flag[0] == STATUS_OK)
-        chol_solve(A.ws + M.chol_b_off[l], M.lv_k[l], M.lv_k[l], u + M.lv_off[l]);  // mode.py:50-52
+        mode_b_solve(A.ws + M.chol_b_off[l], M.lv_k[l], u + M.lv_off[l]);  // mode.py:50-52
     PL_SYNC();
     // ---- convergence (weights.py:51-53) ----------------------------------------------------------
     double part = 0.0;

@@ -78,8 +78,8 @@ PL_HD void num_step(const NumStepArgs& A, double* smem) {
 #define PLN_S(p, q) ((gram_raw(M, A.G, (p), (q)) * invN - m[p] * m[q]) * isd[p] * isd[q])
 
   const bool stop = (it >= 1) && ((A.conv_in < A.tol) || (it > A.max_iter) || flag[0] != STATUS_OK);
-  double* ols = A.ws + (M.ws_doubles - L * (M.max_deg * M.max_deg + 2 * M.max_deg));
-  const int ols_stride = M.max_deg * M.max_deg + 2 * M.max_deg;
+  const int ols_stride = ols_scratch_doubles(M.max_deg);
+  double* ols = A.ws + (M.ws_doubles - L * ols_stride);
 
   // ---- V_d = S_lj a_j, variances and covariances of the current scores --------------------------
   for (int t = tid; t < M.n_pairs * M.kmax; t += nt) {
@@ -204,9 +204,9 @@ PL_HD void num_step(const NumStepArgs& A, double* smem) {
       if (M.lv_mode[l] == MODE_B) {
         int o = M.lv_off[l], k = M.lv_k[l];
         double* C = A.ws + M.chol_b_off[l];
-        for (int r = 0; r < k; ++r)
-          for (int c = 0; c <= r; ++c) C[r * k + c] = PLN_S(o + r, o + c);
-        if (!chol_factor(C, k, k)) flag[0] = STATUS_SINGULAR;
+#define PLN_BLK(r_, c_) PLN_S(o + (r_), o + (c_))
+        PL_MODE_B_PREPARE(C, k, PLN_BLK);
+#undef PLN_BLK
       }
   // inner weights from the covariance of the current scores (scheme.py)
   if (A.scheme == SCHEME_PATH) {
@@ -253,7 +253,7 @@ PL_HD void num_step(const NumStepArgs& A, double* smem) {
   PL_SYNC();
   for (int l = tid; l < L; l += nt) {
     int o = M.lv_off[l], k = M.lv_k[l];
-    if (M.lv_mode[l] == MODE_B && flag[0] == STATUS_OK) chol_solve(A.ws + M.chol_b_off[l], k, k, an + o);
+    if (M.lv_mode[l] == MODE_B && flag[0] == STATUS_OK) mode_b_solve(A.ws + M.chol_b_off[l], k, an + o);
     double q = 0.0;  // variance of X_l w: w' S_ll w
     for (int r = 0; r < k; ++r)
       for (int c = 0; c < k; ++c) q += an[o + r] * PLN_S(o + r, o + c) * an[o + c];

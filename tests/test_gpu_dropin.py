@@ -232,26 +232,36 @@ def test_bootstrap_with_missing_values_philox_replicates_vs_oracle(sat):
         np.testing.assert_allclose(w[b], ref[:len(mvs)], rtol=1e-6)
 
 
-def test_collinear_mode_b_block_raises_and_bootstrap_drops_it():
-    """Pinned difference to the reference (min-norm lstsq, mode.py:50-52): an exactly collinear Mode-B block is
-    reported singular -- the single fit raises, bootstrap replicates that hit it are dropped and counted."""
+def test_collinear_mode_b_block_gives_the_reference_min_norm_weights():
+    """An exactly collinear Mode-B block: the reference's lstsq (mode.py:50-52) returns the minimum-norm weights; the
+    device solver falls back from Cholesky to conjugate gradients on the rank-deficient normal equations and must give
+    the same -- single fit against the REFERENCE's output (tests/golden/collinear.npz), bootstrap replicates against
+    the oracle, and the drop-in API end to end."""
     import os
+    from oracle import plspm_oracle as orc
     from plspm_b200 import engine
     g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "collinear.npz"))
     model = engine.Model(g["block_sizes"], [1, 1, 1], g["path"], True)
     data = engine.Data(model, g["X"])
     res = engine.fit(model, data, "centroid")
-    assert res["status"] == engine.STATUS_SINGULAR
+    assert res["status"] == 0 and res["iterations"] == int(g["ref/iterations"])
+    np.testing.assert_allclose(res["weights"], g["ref/weights"], rtol=1e-6)
+    np.testing.assert_allclose(res["r_squared"], g["ref/r_squared"], rtol=1e-6, atol=1e-9)
     rows, status, iters = engine.bootstrap(model, data, "centroid", 0, 20, seed=2)
-    assert (status == engine.STATUS_SINGULAR).all()  # every resample keeps columns 3 and 4 identical
+    assert (status == 0).all()  # every resample keeps columns 3 and 4 identical: none is dropped any more
+    for b in (0, 7, 19):
+        idx = orc.philox_indices(2, b, g["X"].shape[0])
+        ref, it, st = orc.replicate_row(g["X"], idx, g["block_sizes"], [1, 1, 1], g["path"], "centroid", True)
+        assert st == 0 and it == iters[b]
+        np.testing.assert_allclose(rows[b], ref, rtol=1e-6, atol=1e-9)
     mvs = ["x%d" % i for i in range(9)]
     df = pd.DataFrame(g["X"], columns=mvs)
     s_ = c.Structure()
     s_.add_path(["L0"], ["L1", "L2"])
     s_.add_path(["L1"], ["L2"])
-    config = c.Config(s_.path(), scaled=True)
-    for i, lv in enumerate(("L0", "L1", "L2")):
-        config.add_lv(lv, Mode.B, *[c.MV(m) for m in mvs[3 * i:3 * i + 3]])
     if (np.asarray(s_.path().loc[["L0", "L1", "L2"], ["L0", "L1", "L2"]]) == g["path"]).all():
-        with pytest.raises(Exception, match="singular"):
-            Plspm(df, config)
+        config = c.Config(s_.path(), scaled=True)
+        for i, lv in enumerate(("L0", "L1", "L2")):
+            config.add_lv(lv, Mode.B, *[c.MV(m) for m in mvs[3 * i:3 * i + 3]])
+        calc = Plspm(df, config)
+        np.testing.assert_allclose(calc.outer_model().loc[mvs, "weight"].values, g["ref/weights"], rtol=1e-6)

@@ -162,8 +162,9 @@ def test_bootstrap_with_missing_values_vs_reference(case):
 def test_collinear_mode_b_block_oracle_follows_the_reference_min_norm():
     """An exactly duplicated column in a Mode-B block: the reference's lstsq (mode.py:50-52, gelsd) returns the
     minimum-norm weights (equal weights on the two copies; fixture tests/golden/collinear.npz generated by the
-    reference) and so does the oracle.  The CUDA solver works on S_ll (Cholesky) and reports STATUS_SINGULAR instead:
-    a DOCUMENTED DIFFERENCE pinned by tests/test_gpu_dropin.py::test_collinear_mode_b_block_raises_and_bootstrap_drops_it."""
+    reference) and so does the oracle.  The CUDA solver reaches the same answer in the moment domain (Cholesky, then
+    conjugate gradients on the rank-deficient normal equations): tests/test_solver_emul.py and
+    tests/test_gpu_dropin.py::test_collinear_mode_b_block_gives_the_reference_min_norm_weights."""
     g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "collinear.npz"))
     w = g["ref/weights"]
     assert np.isfinite(w).all() and abs(w[3] - w[4]) < 1e-12  # the reference's min-norm answer

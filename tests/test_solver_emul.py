@@ -163,6 +163,36 @@ def test_low_precision_vote_logic(syn):
         emul.set_vote_mode(0)
 
 
+def test_rank_deficient_blocks_and_regressions_give_the_reference_min_norm_solution():
+    """Rank-deficient least squares: the reference's SVD-based solvers (scipy lstsq in mode.py:50-52, statsmodels' pinv in
+    scheme.py:50 / inner_model.py:76-77) return minimum-norm coefficients.  The solver falls back from Cholesky to
+    conjugate gradients on the (consistent, positive semi-definite) normal equations, which converge to the same
+    solution.  (a) Mode-B block with a duplicated column against the REFERENCE's output (tests/golden/collinear.npz);
+    (b) two identical blocks feeding a third LV (singular inner regression) against the oracle, all schemes."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "collinear.npz"))
+    for policy in (1, 2):
+        r = emul.fit(g["X"], g["block_sizes"], [1, 1, 1], g["path"], "centroid", True, tile_policy=policy)
+        assert r["status"] == 0 and r["iterations"] == int(g["ref/iterations"])
+        np.testing.assert_allclose(r["weights"], g["ref/weights"], rtol=1e-9)
+        np.testing.assert_allclose(r["r_squared"], g["ref/r_squared"], rtol=1e-9, atol=1e-12)
+        assert abs(r["weights"][3] - r["weights"][4]) < 1e-12  # equal weights on the two copies: the min-norm answer
+    rng = np.random.default_rng(1)
+    N = 400
+    f = rng.standard_normal((N, 1))
+    b0 = f + 0.5 * rng.standard_normal((N, 3))
+    X = np.concatenate([b0, b0.copy(), f + 0.4 * rng.standard_normal((N, 3))], axis=1)
+    path = np.zeros((3, 3), dtype=np.int8)
+    path[2, 0] = path[2, 1] = 1
+    for scheme in ("centroid", "path", "factorial"):
+        ref = orc.fit(X, [3, 3, 3], [0, 0, 0], path, scheme, True)
+        for policy in (1, 2):
+            r = emul.fit(X, [3, 3, 3], [0, 0, 0], path, scheme, True, tile_policy=policy)
+            assert r["status"] == 0 and r["iterations"] == ref["iterations"]
+            check(r, ref, 3, rel=1e-8)
+            assert abs(r["path_coefficients"][2, 0] - r["path_coefficients"][2, 1]) < 1e-9
+
+
 def test_resumed_phases_equal_a_second_iteration():
     """Sparse tile sets: phase 1 stores the converged iteration state (w, V, dinv, R, pooled scale, counts) and phases
     2 / 3 resume from it (what the CUDA library does since round 2).  Must give exactly what iterating again gives."""
