@@ -33,7 +33,8 @@ enum { PLSPM_OK = 0, PLSPM_ERR_INVALID = 1, PLSPM_ERR_CUDA = 2, PLSPM_ERR_NOMEM 
 enum { PLSPM_SCHEME_CENTROID = 0, PLSPM_SCHEME_FACTORIAL = 1, PLSPM_SCHEME_PATH = 2 };
 enum { PLSPM_MODE_A = 0, PLSPM_MODE_B = 1 };
 /* per-fit status: converged / "Could not converge after N iterations" (weights.py:185-186)
- * / a Mode-B block or an inner regression is not positive definite */
+ * / non-finite moments in a Mode-B block or an inner regression (rank-deficient ones get the minimum-norm solution
+ * the reference's lstsq / pinv return, mode.py:50-52, inner_model.py:76-77) */
 enum { PLSPM_FIT_OK = 0, PLSPM_FIT_NOT_CONVERGED = 1, PLSPM_FIT_SINGULAR = 2 };
 /* Gram tile policy: which manifest-variable cross moments the Gram kernel accumulates */
 enum { PLSPM_TILES_AUTO = 0, PLSPM_TILES_FULL = 1, PLSPM_TILES_SPARSE = 2 };
