@@ -298,7 +298,6 @@ class HostNonmetricSession:
     def bootstrap(self, scheme, tol: float, iterations: int, rep_begin: int, rep_count: int, seed: int = 0, idx=None,
                   out_device_ptr: int = 0):
         """bootstrap.py:54-68 as written: one full host fit per resample; failures are dropped by the caller."""
-        from plspm_b200 import engine
         assert not out_device_ptr
         rows = np.zeros((rep_count, self.model.n_out))
         status, iters = np.ones(rep_count, dtype=np.int32), np.zeros(rep_count, dtype=np.int32)
